@@ -1,0 +1,175 @@
+"""Synthetic SURF3D keypoint sets in the three on-disk formats `bin/match` reads.
+
+Test/bench data only.  The record layout and value distributions follow the reference's
+producer:
+
+* record  = x, y, z, scale, laplacianSign, response, d0..d47
+            (vtkOpenSURF3D/vtk3DSURF.cxx:402-525 -- the .csv / .csv.gz / .bin writers)
+* descriptor = 8 sub-blocks x (dx, dy, dz, |dx|, |dy|, |dz|), L2-normalised
+            (vtkOpenSURF3D/surf.cxx:135-155) => components 3,4,5 (mod 6) are >= 0
+* scale   = spacing * 0.1333 * (m + u*step), filter sizes m/step per octave
+            (vtkOpenSURF3D/fasthessian.cxx:144,285-289,599-605)
+* laplacian in {0, 1} (fasthessian.cxx:453); response sorted descending (vtk3DSURF.cxx:209-221)
+
+Every value is rounded to 6 decimals before being narrowed to float32 so that the "%f" text
+formats and the raw-float .bin format carry bit-identical float32 values.
+"""
+from __future__ import annotations
+
+import gzip
+import os
+from dataclasses import dataclass
+
+import numpy as np
+
+D = 48
+_FILTERS = np.array([(15, 6), (21, 6), (27, 12), (39, 12), (51, 24), (75, 24), (99, 48), (147, 48)], dtype=np.float64)
+_SPACING = 0.75
+
+
+@dataclass
+class Keypoints:
+    """One image's keypoints, float32, in file order."""
+
+    xyz: np.ndarray  # [N,3]
+    scale: np.ndarray  # [N]
+    lap: np.ndarray  # [N]
+    response: np.ndarray  # [N]
+    desc: np.ndarray  # [N,48]
+
+    @property
+    def n(self) -> int:
+        return int(self.scale.shape[0])
+
+    def records(self) -> np.ndarray:
+        """[N,54] float32 rows exactly as the .bin writer lays them out."""
+        return np.concatenate(
+            [self.xyz, self.scale[:, None], self.lap[:, None], self.response[:, None], self.desc], axis=1
+        ).astype(np.float32)
+
+
+def _r6(a: np.ndarray) -> np.ndarray:
+    return np.round(a.astype(np.float64), 6).astype(np.float32)
+
+
+def _surf_pattern(g: np.ndarray) -> np.ndarray:
+    """Impose the (dx,dy,dz,|dx|,|dy|,|dz|) sign pattern and L2-normalise rows."""
+    d = g.reshape(g.shape[0], 8, 6).copy()
+    d[:, :, 3:] = np.abs(d[:, :, 3:])
+    d = d.reshape(g.shape[0], D)
+    d /= np.maximum(np.linalg.norm(d, axis=1, keepdims=True), 1e-30)
+    return d
+
+
+def _scales(rng: np.random.Generator, n: int) -> np.ndarray:
+    w = 8.0 ** -np.arange(4)
+    octave = rng.choice(4, size=n, p=w / w.sum())
+    filt = octave * 2 + rng.integers(0, 2, size=n)
+    m, step = _FILTERS[filt, 0], _FILTERS[filt, 1]
+    u = rng.uniform(-1.0, 1.0, size=n)
+    return _SPACING * 0.1333 * (m + u * step)
+
+
+def _geometry(rng: np.random.Generator, n: int):
+    xyz = rng.uniform(0.0, 1.0, size=(n, 3)) * np.array([300.0, 300.0, 1500.0])
+    response = np.sort(rng.uniform(0.0, 1.0e4, size=n))[::-1]
+    return xyz, response
+
+
+def make_iid(n: int, image: int) -> Keypoints:
+    """`iid` set (throughput): independent random unit descriptors, seed = 1000 + image."""
+    rng = np.random.default_rng(1000 + image)
+    desc = _surf_pattern(rng.standard_normal((n, D)))
+    xyz, response = _geometry(rng, n)
+    lap = rng.integers(0, 2, size=n).astype(np.float64)
+    return Keypoints(_r6(xyz), _r6(_scales(rng, n)), lap.astype(np.float32), _r6(response), _r6(desc))
+
+
+_BANK_CACHE: dict = {}
+
+
+def _bank(n: int):
+    if n not in _BANK_CACHE:
+        rng = np.random.default_rng(7)
+        proto = _surf_pattern(rng.standard_normal((2 * n, D)))
+        _BANK_CACHE[n] = (proto, _scales(rng, 2 * n), rng.integers(0, 2, size=2 * n).astype(np.float64))
+    return _BANK_CACHE[n]
+
+
+def make_bank(n: int, image: int, noise: float = 0.02, outliers: float = 0.10) -> Keypoints:
+    """`bank` set (parity): images share 2n prototypes, so true matches exist at -d 0.22."""
+    proto, pscale, plap = _bank(n)
+    rng = np.random.default_rng(2000 + image)
+    pick = rng.permutation(2 * n)[:n]
+    desc = _surf_pattern(proto[pick] + noise * rng.standard_normal((n, D)))
+    scale = pscale[pick] * (1.0 + rng.uniform(-0.03, 0.03, size=n))
+    lap = plap[pick].copy()
+    out = rng.uniform(size=n) < outliers
+    if out.any():
+        k = int(out.sum())
+        desc[out] = _surf_pattern(rng.standard_normal((k, D)))
+        scale[out] = _scales(rng, k)
+        lap[out] = rng.integers(0, 2, size=k)
+    xyz, response = _geometry(rng, n)
+    return Keypoints(_r6(xyz), _r6(scale), lap.astype(np.float32), _r6(response), _r6(desc))
+
+
+def make(kind: str, n: int, image: int) -> Keypoints:
+    if kind == "iid":
+        return make_iid(n, image)
+    if kind == "bank":
+        return make_bank(n, image)
+    raise ValueError(f"unknown synthetic set {kind!r}")
+
+
+# ----------------------------------------------------------------------------------------------
+# writers (formats of vtk3DSURF.cxx:402-525)
+
+
+def _text_lines(kp: Keypoints) -> bytes:
+    rec = kp.records().astype(np.float64)
+    lines = []
+    for r in rec:
+        head = "%f,%f,%f,%f,%d,%f," % (r[0], r[1], r[2], r[3], int(r[4]), r[5])
+        lines.append(head + ",".join("%f" % v for v in r[6:]))
+    return ("\n".join(lines) + "\n").encode()
+
+
+def write_bin(kp: Keypoints, path: str) -> None:
+    kp.records().astype("<f4").tofile(path)
+
+
+def write_csv(kp: Keypoints, path: str) -> None:
+    with open(path, "wb") as f:
+        f.write(_text_lines(kp))
+
+
+def write_csv_gz(kp: Keypoints, path: str) -> None:
+    with gzip.GzipFile(path, "wb", compresslevel=1, mtime=0) as f:
+        f.write(_text_lines(kp))
+
+
+WRITERS = {"bin": write_bin, "csv": write_csv, "csv.gz": write_csv_gz}
+
+
+def write_group(dirpath: str, kind: str, n_images: int, n_points: int, fmt: str = "bin",
+                rigid: bool = False, first_image: int = 0) -> str:
+    """Write `n_images` keypoint files plus the list file `bin/match` takes; returns the list path.
+
+    List lines are absolute paths (as run.sh:86-88 writes them), optionally followed by a rigid
+    translation `,x,y,z` (match.cpp:478-490).
+    """
+    os.makedirs(dirpath, exist_ok=True)
+    lines = []
+    for i in range(n_images):
+        kp = make(kind, n_points, first_image + i)
+        p = os.path.abspath(os.path.join(dirpath, f"points{i}.{fmt}"))
+        WRITERS[fmt](kp, p)
+        if rigid:
+            lines.append(f"{p},{0.5 * i:.3f},{-0.25 * i:.3f},{1.0 * i:.3f}")
+        else:
+            lines.append(p)
+    lst = os.path.join(dirpath, "points.txt")
+    with open(lst, "w") as f:
+        f.write("\n".join(lines) + "\n")
+    return lst

@@ -1,0 +1,39 @@
+// Test-infrastructure shim: a std::istream that, once a gzip_decompressor tag and a source
+// stream have been pushed (match.cpp:56-58), serves the zlib-inflated bytes of that source.
+#pragma once
+#include <istream>
+#include <sstream>
+#include <string>
+#include <vector>
+#include <zlib.h>
+#include "filter/gzip.hpp"
+namespace boost { namespace iostreams {
+class filtering_istream : public std::istream {
+  std::stringbuf buf_;
+  bool gz_ = false;
+ public:
+  filtering_istream() : std::istream(nullptr) { rdbuf(&buf_); }
+  void push(const gzip_decompressor&) { gz_ = true; }
+  void push(std::istream& src) {
+    std::string raw((std::istreambuf_iterator<char>(src)), std::istreambuf_iterator<char>());
+    if (!gz_) { buf_.str(raw); return; }
+    std::string out;
+    z_stream zs{};
+    if (inflateInit2(&zs, 15 + 32) != Z_OK) { setstate(std::ios::badbit); return; }
+    zs.next_in = reinterpret_cast<Bytef*>(raw.data());
+    zs.avail_in = static_cast<uInt>(raw.size());
+    std::vector<char> chunk(1 << 20);
+    int rc = Z_OK;
+    while (rc != Z_STREAM_END) {
+      zs.next_out = reinterpret_cast<Bytef*>(chunk.data());
+      zs.avail_out = static_cast<uInt>(chunk.size());
+      rc = inflate(&zs, Z_NO_FLUSH);
+      if (rc != Z_OK && rc != Z_STREAM_END) break;
+      out.append(chunk.data(), chunk.size() - zs.avail_out);
+      if (rc == Z_OK && zs.avail_in == 0 && zs.avail_out != 0) break;
+    }
+    inflateEnd(&zs);
+    buf_.str(out);
+  }
+};
+}}
