@@ -1,0 +1,69 @@
+"""Build recipes for the native artefacts (in-tree, so the built files travel with `gpurun`).
+
+    frog_b200/libfrogmatch.so   CUDA kernels + C ABI (include/frogmatch.h), sm_100a only
+    bin/match                   the drop-in `match` executable (C++ host, links libfrogmatch.so)
+
+`python -m frog_b200.build` builds both; nvcc cross-compiles sm_100a without a GPU.
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CSRC = os.path.join(ROOT, "frog_b200", "csrc")
+LIB = os.path.join(ROOT, "frog_b200", "libfrogmatch.so")
+BIN = os.path.join(ROOT, "bin", "match")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-fopenmp",
+]
+
+
+def _newer(target: str, sources) -> bool:
+    if not os.path.exists(target):
+        return False
+    t = os.path.getmtime(target)
+    return all(os.path.getmtime(s) <= t for s in sources)
+
+
+def _sources(exts):
+    out = [os.path.join(ROOT, "include", f) for f in os.listdir(os.path.join(ROOT, "include"))]
+    out += [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(exts)]
+    return out
+
+
+def build_lib(force: bool = False, verbose: bool = False) -> str:
+    srcs = _sources((".cu", ".cuh", ".h"))
+    if not force and _newer(LIB, srcs):
+        return LIB
+    cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [
+        "-shared", "-o", LIB, os.path.join(CSRC, "fm_api.cu")]
+    subprocess.run(cmd, check=True, cwd=ROOT)
+    return LIB
+
+
+def build_cli(force: bool = False) -> str:
+    srcs = _sources((".cpp", ".h"))
+    if not force and _newer(BIN, srcs + [LIB]):
+        return BIN
+    os.makedirs(os.path.dirname(BIN), exist_ok=True)
+    cmd = ["g++", "-O2", "-std=c++17", "-fopenmp", "-I", os.path.join(ROOT, "include"),
+           os.path.join(CSRC, "match_main.cpp"), os.path.join(CSRC, "keypoint_io.cpp"),
+           "-o", BIN, "-L", os.path.dirname(LIB), "-lfrogmatch", "-lz",
+           "-Wl,-rpath,$ORIGIN/../frog_b200"]
+    subprocess.run(cmd, check=True, cwd=ROOT)
+    return BIN
+
+
+def build_all(force: bool = False) -> None:
+    build_lib(force)
+    build_cli(force)
+
+
+if __name__ == "__main__":
+    build_all(force="--force" in sys.argv)
+    print(LIB)
+    print(BIN)

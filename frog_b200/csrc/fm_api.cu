@@ -1,0 +1,582 @@
+// fm_api.cu -- C ABI of libfrogmatch.so (include/frogmatch.h): context, keypoint upload,
+// task batching and kernel orchestration.  sm_100a only; there is no CPU fallback.
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "../../include/frogmatch.h"
+#include "../../include/frogmatch_debug.h"
+#include "fm_compact.cuh"
+#include "fm_exact.cuh"
+#include "fm_fast.cuh"
+#include "fm_host.h"
+
+using namespace fm;
+
+struct fm_result {
+  fm_ctx* ctx = nullptr;
+  size_t n_pairs = 0;
+  uint64_t total = 0;
+  std::vector<uint32_t> counts;
+  std::vector<uint64_t> offsets;
+  DevBuf d_out, d_counts;
+  uint32_t* h_pairs = nullptr;  // pinned
+  size_t h_cap = 0;
+  bool fetched = false;
+};
+
+namespace {
+
+thread_local std::string g_create_error;
+
+int fail(fm_ctx* c, int code, const std::string& msg) {
+  if (c) c->err = msg; else g_create_error = msg;
+  return code;
+}
+
+int cuda_fail(fm_ctx* c, cudaError_t e, const char* what) {
+  return fail(c, e == cudaErrorMemoryAllocation ? FM_ERR_NOMEM : FM_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+#define FM_CUDA(ctx, expr)                                     \
+  do {                                                         \
+    cudaError_t e__ = (expr);                                  \
+    if (e__ != cudaSuccess) return cuda_fail((ctx), e__, #expr); \
+  } while (0)
+
+// Upload the ImageDev table and read the per-image metas (flags, class tables) back.
+int sync_images(fm_ctx* c) {
+  if (!c->images_dirty) return FM_OK;
+  const size_t n = c->h_images.size();
+  FM_CUDA(c, c->d_images.ensure(std::max<size_t>(1, n) * sizeof(ImageDev)));
+  c->h_metas.assign(n, ImageMeta{});
+  if (n) {
+    FM_CUDA(c, cudaMemcpyAsync(c->d_images.p, c->h_images.data(), n * sizeof(ImageDev), cudaMemcpyHostToDevice, c->stream));
+    FM_CUDA(c, cudaMemcpyAsync(c->h_metas.data(), c->d_metas.p, n * sizeof(ImageMeta), cudaMemcpyDeviceToHost, c->stream));
+    FM_CUDA(c, cudaStreamSynchronize(c->stream));
+  }
+  c->images_dirty = false;
+  return FM_OK;
+}
+
+struct Batch {
+  uint32_t t0, t1, rows, blocks, chunks, units;
+  size_t cursor;  // first entry of this batch in the concatenated prefix arrays
+  bool any_exact, any_fast;
+};
+
+}  // namespace
+
+extern "C" {
+
+const char* fm_version(void) { return "frogmatch 0.1 (sm_100a: tcgen05 + TMA bulk copy)"; }
+
+int fm_device_count(int* n) {
+  if (!n) return FM_ERR_INVALID;
+  *n = 0;
+  int k = 0;
+  cudaError_t e = cudaGetDeviceCount(&k);
+  if (e != cudaSuccess) return cuda_fail(nullptr, e, "fm_device_count");
+  *n = k;
+  return FM_OK;
+}
+
+int fm_create(int device, fm_ctx** out) {
+  if (!out) return fail(nullptr, FM_ERR_INVALID, "fm_create: out is NULL");
+  *out = nullptr;
+  int n_dev = 0;
+  cudaError_t e = cudaGetDeviceCount(&n_dev);
+  if (e != cudaSuccess || n_dev == 0)
+    return fail(nullptr, FM_ERR_CUDA, std::string("fm_create: no CUDA device (") + cudaGetErrorString(e) +
+                                          "); libfrogmatch has no CPU fallback");
+  if (device < 0 || device >= n_dev) return fail(nullptr, FM_ERR_INVALID, "fm_create: device index out of range");
+  cudaDeviceProp prop{};
+  if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess)
+    return cuda_fail(nullptr, e, "fm_create");
+  if (prop.major != 10)
+    return fail(nullptr, FM_ERR_UNSUPPORTED, "fm_create: device is sm_" + std::to_string(prop.major) +
+                                                 std::to_string(prop.minor) + ", this library is built for sm_100a only");
+  fm_ctx* c = new (std::nothrow) fm_ctx();
+  if (!c) return fail(nullptr, FM_ERR_NOMEM, "fm_create: out of host memory");
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  if ((e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking)) != cudaSuccess ||
+      (e = cudaMallocHost(reinterpret_cast<void**>(&c->h_pinned), 256)) != cudaSuccess) {
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    delete c;
+    return cuda_fail(nullptr, e, "fm_create");
+  }
+  c->stream = c->own_stream;
+  *out = c;
+  return FM_OK;
+}
+
+void fm_destroy(fm_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  for (auto& im : c->images) {
+    im.desc.release(); im.scale.release(); im.lap.release();
+    im.fast.release();
+  }
+  DevBuf* bufs[] = {&c->d_images, &c->d_metas, &c->d_meta_blob, &c->d_rowres, &c->d_chunk_count, &c->d_chunk_out,
+                    &c->d_totals, &c->d_bands, &c->d_cands, &c->d_redo, &c->d_taskinfo, &c->cache_out, &c->cache_counts};
+  for (auto* b : bufs) b->release();
+  if (c->cache_pinned) cudaFreeHost(c->cache_pinned);
+  if (c->h_pinned) cudaFreeHost(c->h_pinned);
+  c->ev_match.destroy();
+  c->ev_prep.destroy();
+  cudaStreamDestroy(c->own_stream);
+  delete c;
+}
+
+const char* fm_last_error(const fm_ctx* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+
+int fm_set_stream(fm_ctx* c, void* s) {
+  if (!c) return FM_ERR_INVALID;
+  FM_CUDA(c, cudaSetDevice(c->device));
+  FM_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->stream = s ? reinterpret_cast<cudaStream_t>(s) : c->own_stream;
+  return FM_OK;
+}
+
+int fm_synchronize(fm_ctx* c) {
+  if (!c) return FM_ERR_INVALID;
+  FM_CUDA(c, cudaSetDevice(c->device));
+  FM_CUDA(c, cudaStreamSynchronize(c->stream));
+  return FM_OK;
+}
+
+int fm_clear_images(fm_ctx* c) {
+  if (!c) return FM_ERR_INVALID;
+  for (auto& im : c->images) im.valid = false;
+  c->images_dirty = true;
+  c->dim = 0;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  c->ev_prep.reset();
+  return FM_OK;
+}
+
+int fm_image_points(const fm_ctx* c, uint32_t img, uint32_t* n) {
+  if (!c || !n || img >= c->images.size() || !c->images[img].valid) return FM_ERR_INVALID;
+  *n = c->images[img].n;
+  return FM_OK;
+}
+
+int fm_upload_image(fm_ctx* c, uint32_t img, const float* desc, const float* scale, const float* lap, uint32_t n,
+                    uint32_t d) {
+  if (!c) return FM_ERR_INVALID;
+  if ((n && (!desc || !scale || !lap)) || d == 0) return fail(c, FM_ERR_INVALID, "fm_upload_image: null input or d == 0");
+  if (d > 320) return fail(c, FM_ERR_UNSUPPORTED, "fm_upload_image: descriptor length above 320 is not supported");
+  if (img >= 65536u) return fail(c, FM_ERR_INVALID, "fm_upload_image: image index above 65535 (pairs.bin ids are u16, match.cpp:735)");
+  if (c->dim != 0 && c->dim != d) return fail(c, FM_ERR_INVALID, "fm_upload_image: all images of a context must share d");
+  FM_CUDA(c, cudaSetDevice(c->device));
+  c->dim = d;
+  if (img >= c->images.size()) c->images.resize(img + 1);
+  if (img >= c->h_images.size()) c->h_images.resize(img + 1, ImageDev{});
+  Image& im = c->images[img];
+  FM_CUDA(c, im.desc.ensure((size_t)n * d * sizeof(float)));
+  FM_CUDA(c, im.scale.ensure((size_t)n * sizeof(float)));
+  FM_CUDA(c, im.lap.ensure((size_t)n * sizeof(float)));
+  if (n) {
+    FM_CUDA(c, cudaMemcpyAsync(im.desc.p, desc, (size_t)n * d * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    FM_CUDA(c, cudaMemcpyAsync(im.scale.p, scale, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    FM_CUDA(c, cudaMemcpyAsync(im.lap.p, lap, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  }
+  im.valid = true;
+  im.n = n;
+  im.d = d;
+  ImageDev& v = c->h_images[img];
+  v = ImageDev{};
+  v.desc = im.desc.as<float>();
+  v.scale = im.scale.as<float>();
+  v.lap = im.lap.as<float>();
+  v.n = n;
+  v.d = d;
+  {
+    Span sp(&c->ev_prep, c->stream, kPhPrep);
+    cudaError_t e = fast_prepare_image(c, img);
+    if (e != cudaSuccess) return cuda_fail(c, e, "fm_upload_image: prep");
+  }
+  c->images_dirty = true;
+  return FM_OK;
+}
+
+int fm_match(fm_ctx* c, const uint32_t* pair_first, const uint32_t* pair_second, size_t n_pairs, float dist,
+             float dist2second, uint32_t flags, fm_result** out) {
+  if (!c || !out) return FM_ERR_INVALID;
+  *out = nullptr;
+  if (n_pairs && (!pair_first || !pair_second)) return fail(c, FM_ERR_INVALID, "fm_match: null pair arrays");
+  // match.cpp:320-321: a row with no surviving column has d1 == FLT_MAX and is emitted (with a
+  // stale column id) only if sqrt(FLT_MAX) = 1.8e19 < dist.  No caller passes such a threshold
+  // (FROG.py uses 1e10); refuse it rather than imitate an index leak.
+  if (!(dist < 1.8e19f)) return fail(c, FM_ERR_UNSUPPORTED, "fm_match: distance threshold must be below 1.8e19");
+  FM_CUDA(c, cudaSetDevice(c->device));
+  for (size_t p = 0; p < n_pairs; p++) {
+    uint32_t a = pair_first[p], b = pair_second[p];
+    if (a >= c->images.size() || b >= c->images.size() || !c->images[a].valid || !c->images[b].valid)
+      return fail(c, FM_ERR_INVALID, "fm_match: pair " + std::to_string(p) + " names an image that was not uploaded");
+  }
+  int rc = sync_images(c);
+  if (rc != FM_OK) return rc;
+  const bool sym = flags & FM_FLAG_SYM;
+  const bool force_exact = (flags & FM_FLAG_FORCE_EXACT) || c->dim != (uint32_t)kD;
+
+  // ---- tasks --------------------------------------------------------------------------------
+  std::vector<Task> tasks;
+  std::vector<uint32_t> pair_of_task;
+  tasks.reserve(n_pairs * (sym ? 2 : 1));
+  uint64_t total_rows = 0, desc_pairs = 0;
+  auto add_task = [&](uint32_t col, uint32_t row, uint32_t tflags, size_t p) {
+    if (force_exact || c->h_metas[col].flags || c->h_metas[row].flags) tflags |= kTaskExact;
+    tasks.push_back(Task{col, row, 0, tflags});
+    pair_of_task.push_back((uint32_t)p);
+    total_rows += c->images[row].n;
+    desc_pairs += (uint64_t)c->images[col].n * c->images[row].n;
+  };
+  for (size_t p = 0; p < n_pairs; p++) {
+    add_task(pair_first[p], pair_second[p], 0, p);
+    if (sym) add_task(pair_second[p], pair_first[p], kTaskSwap, p);
+  }
+  const uint32_t n_tasks = (uint32_t)tasks.size();
+
+  // ---- batches + prefix arrays (blocks of 128 rows, compaction chunks, score units) ------------
+  uint64_t base_units = 0;
+  for (auto& t : tasks)
+    if (!(t.flags & kTaskExact)) base_units += (c->images[t.row_img].n + kUnitRows - 1) / kUnitRows;
+  uint32_t segs = 1;
+  if (base_units > 0 && base_units < (uint64_t)2 * c->sm_count)
+    segs = (uint32_t)std::min<uint64_t>(8, ((uint64_t)2 * c->sm_count + base_units - 1) / base_units);
+  constexpr uint32_t kMaxBatchRows = 24u << 20;
+  std::vector<Batch> batches;
+  std::vector<uint32_t> blk_off, chunk_off, unit_off;
+  for (uint32_t t = 0; t < n_tasks;) {
+    Batch b{t, t, 0, 0, 0, 0, blk_off.size(), false, false};
+    while (b.t1 < n_tasks) {
+      const uint32_t nr = c->images[tasks[b.t1].row_img].n;
+      if (b.t1 > b.t0 && (uint64_t)b.rows + nr > kMaxBatchRows) break;
+      tasks[b.t1].row_off = b.rows;
+      blk_off.push_back(b.blocks);
+      chunk_off.push_back(b.chunks);
+      unit_off.push_back(b.units);
+      b.rows += nr;
+      b.blocks += (nr + 127) / 128;
+      b.chunks += (nr + kCompactChunk - 1) / kCompactChunk;
+      if (tasks[b.t1].flags & kTaskExact) b.any_exact = true;
+      else { b.any_fast = true; b.units += ((nr + kUnitRows - 1) / kUnitRows) * segs; }
+      b.t1++;
+    }
+    blk_off.push_back(b.blocks);
+    chunk_off.push_back(b.chunks);
+    unit_off.push_back(b.units);
+    batches.push_back(b);
+    t = b.t1;
+  }
+
+  fm_result* r = new (std::nothrow) fm_result();
+  if (!r) return fail(c, FM_ERR_NOMEM, "fm_match: out of host memory");
+  r->ctx = c;
+  r->n_pairs = n_pairs;
+  std::swap(r->d_out, c->cache_out);
+  std::swap(r->d_counts, c->cache_counts);
+#define FM_CUDA_R(expr)                       \
+  do {                                        \
+    cudaError_t e__ = (expr);                 \
+    if (e__ != cudaSuccess) {                 \
+      int code__ = cuda_fail(c, e__, #expr);  \
+      fm_result_free(r);                      \
+      return code__;                          \
+    }                                         \
+  } while (0)
+
+  c->ev_match.reset();
+  fm_stats prev = c->stats;
+  c->stats = fm_stats{};
+  c->stats.ms_prep = prev.ms_prep;
+  c->stats.descriptor_pairs = desc_pairs;
+  c->stats.rows = total_rows;
+
+  // metadata blob: tasks | pair_of_task | blk_off | chunk_off | unit_off
+  const size_t np = blk_off.size();
+  const size_t off_pot = sizeof(Task) * n_tasks;
+  const size_t off_blk = off_pot + sizeof(uint32_t) * n_tasks;
+  const size_t off_chunk = off_blk + sizeof(uint32_t) * np;
+  const size_t off_unit = off_chunk + sizeof(uint32_t) * np;
+  const size_t blob_bytes = off_unit + sizeof(uint32_t) * np;
+  std::vector<unsigned char> blob(std::max<size_t>(blob_bytes, 16));
+  if (n_tasks) {
+    memcpy(blob.data(), tasks.data(), sizeof(Task) * n_tasks);
+    memcpy(blob.data() + off_pot, pair_of_task.data(), sizeof(uint32_t) * n_tasks);
+  }
+  if (np) {
+    memcpy(blob.data() + off_blk, blk_off.data(), sizeof(uint32_t) * np);
+    memcpy(blob.data() + off_chunk, chunk_off.data(), sizeof(uint32_t) * np);
+    memcpy(blob.data() + off_unit, unit_off.data(), sizeof(uint32_t) * np);
+  }
+  FM_CUDA_R(c->d_meta_blob.ensure(blob.size()));
+  FM_CUDA_R(cudaMemcpyAsync(c->d_meta_blob.p, blob.data(), blob.size(), cudaMemcpyHostToDevice, c->stream));
+  const unsigned char* blob_d = c->d_meta_blob.as<unsigned char>();
+  const Task* d_tasks = reinterpret_cast<const Task*>(blob_d);
+  const uint32_t* d_pot = reinterpret_cast<const uint32_t*>(blob_d + off_pot);
+  const uint32_t* d_blk = reinterpret_cast<const uint32_t*>(blob_d + off_blk);
+  const uint32_t* d_chunk = reinterpret_cast<const uint32_t*>(blob_d + off_chunk);
+  const uint32_t* d_unit = reinterpret_cast<const uint32_t*>(blob_d + off_unit);
+
+  uint32_t max_rows = 1, max_chunks = 1;
+  for (auto& b : batches) { max_rows = std::max(max_rows, b.rows); max_chunks = std::max(max_chunks, b.chunks); }
+  FM_CUDA_R(c->d_rowres.ensure((size_t)max_rows * sizeof(uint32_t)));
+  FM_CUDA_R(c->d_chunk_count.ensure((size_t)max_chunks * sizeof(uint32_t)));
+  FM_CUDA_R(c->d_chunk_out.ensure((size_t)max_chunks * sizeof(uint64_t)));
+  FM_CUDA_R(c->d_totals.ensure(sizeof(DeviceCounters)));
+  FM_CUDA_R(r->d_out.ensure(std::max<uint64_t>(total_rows, 1) * sizeof(uint2)));
+  FM_CUDA_R(r->d_counts.ensure(std::max<size_t>(n_pairs, 1) * sizeof(uint32_t)));
+  FM_CUDA_R(cudaMemsetAsync(r->d_counts.p, 0, std::max<size_t>(n_pairs, 1) * sizeof(uint32_t), c->stream));
+  FM_CUDA_R(cudaMemsetAsync(c->d_totals.p, 0, sizeof(DeviceCounters), c->stream));
+  if (c->dim != (uint32_t)kD && !c->exact_attr_set) {
+    FM_CUDA_R(cudaFuncSetAttribute(exact_match_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    c->exact_attr_set = true;
+  }
+
+  const ImageDev* d_images = c->d_images.as<ImageDev>();
+  uint32_t* d_rowres = c->d_rowres.as<uint32_t>();
+  DeviceCounters* d_counters = c->d_totals.as<DeviceCounters>();
+  {
+    Span total_span(&c->ev_match, c->stream, kPhTotal);
+    for (auto& b : batches) {
+      const uint32_t nt = b.t1 - b.t0;
+      const uint32_t* blk = d_blk + b.cursor;
+      const uint32_t* chk = d_chunk + b.cursor;
+      const uint32_t* unt = d_unit + b.cursor;
+      if (b.rows == 0) continue;
+      if (b.any_fast) {
+        FastBatchArgs fa{};
+        fa.images = d_images;
+        fa.tasks = d_tasks + b.t0;
+        fa.n_tasks = nt;
+        fa.rows = b.rows;
+        fa.blk_off = blk;
+        fa.blocks128 = b.blocks;
+        fa.unit_off = unt;
+        fa.units = b.units;
+        fa.segs = segs;
+        fa.thr = dist;
+        fa.ratio = dist2second;
+        fa.rowres = d_rowres;
+        fa.counters = d_counters;
+        cudaError_t e = fast_match_batch(c, fa);
+        if (e != cudaSuccess) {
+          int code = cuda_fail(c, e, "fm_match: tensor-core path");
+          fm_result_free(r);
+          return code;
+        }
+      }
+      if (b.any_exact) {
+        Span sp(&c->ev_match, c->stream, kPhExact);
+        if (c->dim == (uint32_t)kD)
+          exact_match_kernel<kD><<<b.blocks, kExactRows, exact_smem_bytes(kD, false), c->stream>>>(
+              d_images, d_tasks + b.t0, blk, nt, dist, dist2second, kTaskExact, d_rowres);
+        else
+          exact_match_kernel<0><<<b.blocks, kExactRows, exact_smem_bytes((int)c->dim, true), c->stream>>>(
+              d_images, d_tasks + b.t0, blk, nt, dist, dist2second, kTaskExact, d_rowres);
+        c->stats.kernel_launches++;
+        for (uint32_t t = b.t0; t < b.t1; t++)
+          if (tasks[t].flags & kTaskExact) c->stats.rows_exact += c->images[tasks[t].row_img].n;
+      }
+      {
+        Span sp(&c->ev_match, c->stream, kPhCompact);
+        compact_count_kernel<<<b.chunks, kCompactThreads, 0, c->stream>>>(d_images, d_tasks + b.t0, chk, nt, d_rowres,
+                                                                         c->d_chunk_count.as<uint32_t>());
+        compact_scan_kernel<<<1, 1024, 0, c->stream>>>(c->d_chunk_count.as<uint32_t>(), b.chunks, chk, nt, d_pot + b.t0,
+                                                       c->d_chunk_out.as<uint64_t>(), r->d_counts.as<uint32_t>(),
+                                                       &d_counters->running_total);
+        compact_scatter_kernel<<<b.chunks, kCompactThreads, 0, c->stream>>>(d_images, d_tasks + b.t0, chk, nt, d_rowres,
+                                                                           c->d_chunk_out.as<uint64_t>(),
+                                                                           r->d_out.as<uint2>());
+        c->stats.kernel_launches += 3;
+      }
+    }
+  }
+  FM_CUDA_R(cudaGetLastError());
+
+  // ---- totals and (optionally) the lists to the host -------------------------------------------
+  r->counts.assign(n_pairs, 0);
+  FM_CUDA_R(cudaMemcpyAsync(c->h_pinned, c->d_totals.p, sizeof(DeviceCounters), cudaMemcpyDeviceToHost, c->stream));
+  if (n_pairs)
+    FM_CUDA_R(cudaMemcpyAsync(r->counts.data(), r->d_counts.p, n_pairs * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+  FM_CUDA_R(cudaStreamSynchronize(c->stream));
+  const DeviceCounters* hc = reinterpret_cast<const DeviceCounters*>(c->h_pinned);
+  r->total = hc->running_total;
+  c->stats.scored_pairs = hc->scored_cols;
+  c->stats.candidates = hc->rescore.candidates;
+  c->stats.rows_exact += hc->redo_total;
+  r->offsets.assign(n_pairs + 1, 0);
+  for (size_t p = 0; p < n_pairs; p++) r->offsets[p + 1] = r->offsets[p] + r->counts[p];
+  if (r->offsets[n_pairs] != r->total) {
+    fm_result_free(r);
+    return fail(c, FM_ERR_CUDA, "fm_match: internal error, per-pair counts do not sum to the compacted total");
+  }
+  if (!(flags & FM_FLAG_DEVICE_ONLY)) {
+    rc = fm_result_fetch(r);
+    if (rc != FM_OK) { fm_result_free(r); return rc; }
+  }
+  *out = r;
+  return FM_OK;
+#undef FM_CUDA_R
+}
+
+int fm_result_fetch(fm_result* r) {
+  if (!r) return FM_ERR_INVALID;
+  if (r->fetched) return FM_OK;
+  fm_ctx* c = r->ctx;
+  FM_CUDA(c, cudaSetDevice(c->device));
+  const size_t bytes = std::max<uint64_t>(r->total, 1) * sizeof(uint2);
+  if (c->cache_pinned && c->cache_pinned_cap >= bytes) {
+    r->h_pairs = static_cast<uint32_t*>(c->cache_pinned);
+    r->h_cap = c->cache_pinned_cap;
+    c->cache_pinned = nullptr;
+    c->cache_pinned_cap = 0;
+  } else {
+    const size_t want = bytes + bytes / 4 + 4096;
+    FM_CUDA(c, cudaMallocHost(reinterpret_cast<void**>(&r->h_pairs), want));
+    r->h_cap = want;
+  }
+  if (r->total) {
+    FM_CUDA(c, cudaMemcpyAsync(r->h_pairs, r->d_out.p, r->total * sizeof(uint2), cudaMemcpyDeviceToHost, c->stream));
+    FM_CUDA(c, cudaStreamSynchronize(c->stream));
+  }
+  r->fetched = true;
+  return FM_OK;
+}
+
+size_t fm_result_num_pairs(const fm_result* r) { return r ? r->n_pairs : 0; }
+uint64_t fm_result_total(const fm_result* r) { return r ? r->total : 0; }
+uint32_t fm_result_count(const fm_result* r, size_t p) { return (r && p < r->n_pairs) ? r->counts[p] : 0; }
+const uint32_t* fm_result_pairs(const fm_result* r, size_t p) {
+  if (!r || p >= r->n_pairs || !r->fetched) return nullptr;
+  return r->h_pairs + 2 * r->offsets[p];
+}
+const uint32_t* fm_result_device_counts(const fm_result* r) { return r ? r->d_counts.as<uint32_t>() : nullptr; }
+const uint32_t* fm_result_device_pairs(const fm_result* r) { return r ? r->d_out.as<uint32_t>() : nullptr; }
+
+void fm_result_free(fm_result* r) {
+  if (!r) return;
+  fm_ctx* c = r->ctx;
+  cudaSetDevice(c->device);
+  // hand the big buffers back to the context so the next call does not reallocate
+  if (r->d_out.cap > c->cache_out.cap) std::swap(r->d_out, c->cache_out);
+  if (r->d_counts.cap > c->cache_counts.cap) std::swap(r->d_counts, c->cache_counts);
+  r->d_out.release();
+  r->d_counts.release();
+  if (r->h_pairs) {
+    if (r->h_cap > c->cache_pinned_cap) {
+      if (c->cache_pinned) cudaFreeHost(c->cache_pinned);
+      c->cache_pinned = r->h_pairs;
+      c->cache_pinned_cap = r->h_cap;
+    } else {
+      cudaFreeHost(r->h_pairs);
+    }
+  }
+  delete r;
+}
+
+int fm_get_stats(fm_ctx* c, fm_stats* out) {
+  if (!c || !out) return FM_ERR_INVALID;
+  FM_CUDA(c, cudaSetDevice(c->device));
+  FM_CUDA(c, cudaStreamSynchronize(c->stream));
+  float acc[kNumPhases] = {0};
+  for (auto& s : c->ev_match.spans) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, s.a, s.b) == cudaSuccess) acc[s.phase] += ms;
+  }
+  for (auto& s : c->ev_prep.spans) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, s.a, s.b) == cudaSuccess) acc[kPhPrep] += ms;
+  }
+  c->stats.ms_total = acc[kPhTotal];
+  c->stats.ms_score = acc[kPhScore];
+  c->stats.ms_rescore = acc[kPhRescore] + acc[kPhBands];
+  c->stats.ms_exact = acc[kPhExact];
+  c->stats.ms_compact = acc[kPhCompact];
+  c->stats.ms_prep = acc[kPhPrep];
+  *out = c->stats;
+  return FM_OK;
+}
+
+// ---- debug / test hooks (include/frogmatch_debug.h) ---------------------------------------------
+
+int fm_debug_image(fm_ctx* c, uint32_t img, uint32_t* flags, uint32_t* n_classes, float* class_lap,
+                   uint32_t* class_begin, float* max_norm2, uint32_t* perm, float* scale_sorted,
+                   uint16_t* rowop, uint16_t* colop) {
+  if (!c || img >= c->images.size() || !c->images[img].valid) return FM_ERR_INVALID;
+  FM_CUDA(c, cudaSetDevice(c->device));
+  int rc = sync_images(c);
+  if (rc != FM_OK) return rc;
+  const ImageMeta& m = c->h_metas[img];
+  const Image& im = c->images[img];
+  const ImageDev& v = c->h_images[img];
+  if (flags) *flags = m.flags;
+  if (n_classes) *n_classes = m.n_classes;
+  if (max_norm2) *max_norm2 = m.max_norm2;
+  if (class_lap) memcpy(class_lap, m.class_lap, sizeof m.class_lap);
+  if (class_begin) memcpy(class_begin, m.class_begin, sizeof m.class_begin);
+  if (perm && im.n) FM_CUDA(c, cudaMemcpy(perm, v.perm, im.n * 4, cudaMemcpyDeviceToHost));
+  if (scale_sorted && im.n) FM_CUDA(c, cudaMemcpy(scale_sorted, v.scale_sorted, im.n * 4, cudaMemcpyDeviceToHost));
+  for (int role = 0; role < 2; role++) {
+    uint16_t* dst = role ? colop : rowop;
+    const __half* src = role ? v.colop : v.rowop;
+    if (!dst) continue;
+    if (!src) return fail(c, FM_ERR_INVALID, "fm_debug_image: image has no FP16 operands (d != 48)");
+    std::vector<uint8_t> raw((size_t)v.n_pad * 128);
+    FM_CUDA(c, cudaMemcpy(raw.data(), src, raw.size(), cudaMemcpyDeviceToHost));
+    for (uint32_t s = 0; s < v.n_pad; s++)  // undo the SWIZZLE_128B tile layout
+      for (uint32_t q = 0; q < 8; q++)
+        memcpy(dst + (size_t)s * 64 + q * 8, raw.data() + (size_t)(s >> 7) * 16384 + sw128_offset(s & 127u, q), 16);
+  }
+  return FM_OK;
+}
+
+int fm_debug_score_unit(fm_ctx* c, uint32_t first_img, uint32_t second_img, uint32_t row_block, float* t_out,
+                        uint32_t ld, uint32_t* bands_out, float* cand_t, uint32_t* cand_col) {
+  if (!c || first_img >= c->images.size() || second_img >= c->images.size() || !c->images[first_img].valid ||
+      !c->images[second_img].valid || c->dim != (uint32_t)kD)
+    return FM_ERR_INVALID;
+  FM_CUDA(c, cudaSetDevice(c->device));
+  int rc = sync_images(c);
+  if (rc != FM_OK) return rc;
+  const uint32_t nB = c->images[second_img].n;
+  const uint32_t n_pad_a = c->h_images[first_img].n_pad;
+  if (row_block * kUnitRows >= nB || ld < n_pad_a) return fail(c, FM_ERR_INVALID, "fm_debug_score_unit: bad row block or ld");
+  Task task{first_img, second_img, 0, 0};
+  const uint32_t blocks = (nB + 127) / 128, units = (nB + kUnitRows - 1) / kUnitRows;
+  uint32_t meta[4] = {0, blocks, 0, units};
+  DevBuf d_task, d_meta, d_dump;
+  FM_CUDA(c, d_task.ensure(sizeof task));
+  FM_CUDA(c, d_meta.ensure(sizeof meta));
+  FM_CUDA(c, d_dump.ensure((size_t)kUnitRows * ld * sizeof(float)));
+  FM_CUDA(c, c->d_bands.ensure((size_t)nB * sizeof(uint2)));
+  FM_CUDA(c, c->d_cands.ensure((size_t)nB * kTopK * sizeof(Cand)));
+  FM_CUDA(c, cudaMemcpyAsync(d_task.p, &task, sizeof task, cudaMemcpyHostToDevice, c->stream));
+  FM_CUDA(c, cudaMemcpyAsync(d_meta.p, meta, sizeof meta, cudaMemcpyHostToDevice, c->stream));
+  FM_CUDA(c, cudaMemsetAsync(d_dump.p, 0xFF, (size_t)kUnitRows * ld * sizeof(float), c->stream));  // NaN = "not written"
+  FM_CUDA(c, cudaFuncSetAttribute(score_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kScoreSmemBytes));
+  bands_kernel<<<blocks, 128, 0, c->stream>>>(c->d_images.as<ImageDev>(), d_task.as<Task>(), d_meta.as<uint32_t>(), 1,
+                                              c->d_bands.as<uint2>());
+  score_kernel<true><<<1, kScoreThreads, kScoreSmemBytes, c->stream>>>(
+      c->d_images.as<ImageDev>(), d_task.as<Task>(), d_meta.as<uint32_t>() + 2, 1, 1, c->d_bands.as<uint2>(),
+      c->d_cands.as<Cand>(), nullptr, d_dump.as<float>(), ld, row_block);
+  FM_CUDA(c, cudaGetLastError());
+  FM_CUDA(c, cudaStreamSynchronize(c->stream));
+  const uint32_t r0 = row_block * kUnitRows, nr = std::min<uint32_t>(kUnitRows, nB - r0);
+  if (t_out) FM_CUDA(c, cudaMemcpy(t_out, d_dump.p, (size_t)kUnitRows * ld * sizeof(float), cudaMemcpyDeviceToHost));
+  if (bands_out) FM_CUDA(c, cudaMemcpy(bands_out, c->d_bands.as<uint2>() + r0, (size_t)nr * sizeof(uint2), cudaMemcpyDeviceToHost));
+  if (cand_t && cand_col) {
+    std::vector<Cand> h((size_t)nr * kTopK);
+    FM_CUDA(c, cudaMemcpy(h.data(), c->d_cands.as<Cand>() + (size_t)r0 * kTopK, h.size() * sizeof(Cand), cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < h.size(); i++) { cand_t[i] = h[i].t; cand_col[i] = h[i].col; }
+  }
+  d_task.release(); d_meta.release(); d_dump.release();
+  return FM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,151 @@
+// fm_fast.cuh -- host-side driver of the tensor-core path: per-image preparation at upload and
+// the bands -> score -> rescore -> redo kernel sequence for one batch of tasks.
+#pragma once
+#include "fm_host.h"
+#include "fm_prep.cuh"
+#include "fm_rescore.cuh"
+#include "fm_score.cuh"
+
+namespace fm {
+
+// Device-side counters shared by a fm_match call (one 128-byte block, zeroed per call).
+struct DeviceCounters {
+  unsigned long long running_total;  // matches compacted so far (fm_compact.cuh)
+  unsigned long long scored_cols;    // row x column scores evaluated by score_kernel
+  RescoreCounters rescore;           // candidates, redo_rows (redo_rows is reset per batch)
+  unsigned long long redo_total;     // redo rows accumulated over batches
+  unsigned long long pad[11];
+};
+static_assert(sizeof(DeviceCounters) == 128, "DeviceCounters layout");
+
+__global__ void fold_redo_kernel(DeviceCounters* c) {
+  c->redo_total += c->rescore.redo_rows;
+  c->rescore.redo_rows = 0;
+}
+
+inline cudaError_t ensure_metas(fm_ctx* c, uint32_t n_images) {
+  if (n_images <= c->metas_cap) return cudaSuccess;
+  uint32_t cap = std::max<uint32_t>(1024, c->metas_cap * 2);
+  while (cap < n_images) cap *= 2;
+  DevBuf nb;
+  cudaError_t e = nb.ensure((size_t)cap * sizeof(ImageMeta));
+  if (e != cudaSuccess) return e;
+  if (c->metas_cap) {
+    e = cudaMemcpyAsync(nb.p, c->d_metas.p, (size_t)c->metas_cap * sizeof(ImageMeta), cudaMemcpyDeviceToDevice, c->stream);
+    if (e != cudaSuccess) return e;
+    e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) return e;
+  }
+  c->d_metas.release();
+  c->d_metas = nb;
+  c->metas_cap = cap;
+  for (size_t i = 0; i < c->h_images.size(); i++) c->h_images[i].meta = c->d_metas.as<ImageMeta>() + i;
+  c->images_dirty = true;
+  return cudaSuccess;
+}
+
+// Build the sorted / FP16 tensors of image `img` (already copied to im.desc/scale/lap).
+inline cudaError_t fast_prepare_image(fm_ctx* c, uint32_t img) {
+  Image& im = c->images[img];
+  ImageDev& v = c->h_images[img];
+  cudaError_t e = ensure_metas(c, (uint32_t)c->h_images.size());
+  if (e != cudaSuccess) return e;
+  ImageMeta* meta = c->d_metas.as<ImageMeta>() + img;
+  v.meta = meta;
+  if ((e = cudaMemsetAsync(meta, 0, sizeof(ImageMeta), c->stream)) != cudaSuccess) return e;
+  const uint32_t n = im.n;
+  const uint32_t n_pad = (n + 255u) & ~255u;  // rows are consumed 256 at a time, columns 128
+  v.n_pad = n_pad;
+  FastImageBufs& f = im.fast;
+  if ((e = f.keys.ensure((size_t)std::max(n, 1u) * 8)) != cudaSuccess) return e;
+  if ((e = f.keys_sorted.ensure((size_t)std::max(n, 1u) * 8)) != cudaSuccess) return e;
+  if ((e = f.idx.ensure((size_t)std::max(n, 1u) * 4)) != cudaSuccess) return e;
+  if ((e = f.perm.ensure((size_t)std::max(n, 1u) * 4)) != cudaSuccess) return e;  // sorted position -> original id
+  if ((e = f.scale_sorted.ensure((size_t)std::max(n, 1u) * 4)) != cudaSuccess) return e;
+  if ((e = f.norm2.ensure((size_t)std::max(n, 1u) * 4)) != cudaSuccess) return e;
+  v.perm = f.perm.as<uint32_t>();
+  v.scale_sorted = f.scale_sorted.as<float>();
+  v.rowop = nullptr;
+  v.colop = nullptr;
+  if (n == 0) {
+    ImageMeta m{};
+    for (int k = 0; k <= kMaxClasses; k++) m.class_begin[k] = 0;
+    return cudaMemcpyAsync(meta, &m, sizeof m, cudaMemcpyHostToDevice, c->stream);
+  }
+  prep_keys_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(im.desc.as<float>(), im.scale.as<float>(), im.lap.as<float>(),
+                                                          n, im.d, meta, f.keys.as<unsigned long long>(),
+                                                          f.idx.as<uint32_t>(), f.norm2.as<float>());
+  size_t tmp_bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, f.keys.as<unsigned long long>(), f.keys_sorted.as<unsigned long long>(),
+                                  f.idx.as<uint32_t>(), f.perm.as<uint32_t>(), (int)n, 0, 64, c->stream);
+  if ((e = f.sort_tmp.ensure(tmp_bytes)) != cudaSuccess) return e;
+  e = cub::DeviceRadixSort::SortPairs(f.sort_tmp.p, tmp_bytes, f.keys.as<unsigned long long>(),
+                                      f.keys_sorted.as<unsigned long long>(), f.idx.as<uint32_t>(), f.perm.as<uint32_t>(),
+                                      (int)n, 0, 64, c->stream);
+  if (e != cudaSuccess) return e;
+  prep_finish_kernel<<<1, 1024, 0, c->stream>>>(f.keys_sorted.as<unsigned long long>(), n, im.d, meta,
+                                               f.scale_sorted.as<float>());
+  if (im.d == (uint32_t)kD) {
+    const size_t op_bytes = (size_t)n_pad * kKPad * sizeof(__half);
+    if ((e = f.rowop.ensure(op_bytes)) != cudaSuccess) return e;
+    if ((e = f.colop.ensure(op_bytes)) != cudaSuccess) return e;
+    v.rowop = f.rowop.as<__half>();
+    v.colop = f.colop.as<__half>();
+    const uint32_t threads = n_pad * 8;
+    prep_pack_kernel<<<(threads + 255) / 256, 256, 0, c->stream>>>(im.desc.as<float>(), f.norm2.as<float>(),
+                                                                  f.perm.as<uint32_t>(), n, n_pad,
+                                                                  f.rowop.as<uint8_t>(), f.colop.as<uint8_t>());
+  }
+  return cudaGetLastError();
+}
+
+struct FastBatchArgs {
+  const ImageDev* images;
+  const Task* tasks;        // device, this batch
+  uint32_t n_tasks;
+  uint32_t rows;            // rows in the batch
+  const uint32_t* blk_off;  // device: 128-row blocks per task (prefix)
+  uint32_t blocks128;
+  const uint32_t* unit_off;  // device: score units per task (prefix), already multiplied by segs
+  uint32_t units;
+  uint32_t segs;
+  float thr, ratio;
+  uint32_t* rowres;
+  DeviceCounters* counters;
+};
+
+inline cudaError_t fast_match_batch(fm_ctx* c, const FastBatchArgs& a) {
+  cudaError_t e;
+  if ((e = c->d_bands.ensure((size_t)a.rows * sizeof(uint2))) != cudaSuccess) return e;
+  if ((e = c->d_cands.ensure((size_t)a.rows * a.segs * kTopK * sizeof(Cand))) != cudaSuccess) return e;
+  if ((e = c->d_redo.ensure((size_t)a.rows * sizeof(uint2))) != cudaSuccess) return e;
+  if (!c->score_attr_set) {
+    if ((e = cudaFuncSetAttribute(score_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kScoreSmemBytes)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(score_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kScoreSmemBytes)) != cudaSuccess) return e;
+    c->score_attr_set = true;
+  }
+  {
+    Span sp(&c->ev_match, c->stream, kPhBands);
+    bands_kernel<<<a.blocks128, 128, 0, c->stream>>>(a.images, a.tasks, a.blk_off, a.n_tasks, c->d_bands.as<uint2>());
+  }
+  {
+    Span sp(&c->ev_match, c->stream, kPhScore);
+    score_kernel<false><<<a.units, kScoreThreads, kScoreSmemBytes, c->stream>>>(
+        a.images, a.tasks, a.unit_off, a.n_tasks, a.segs, c->d_bands.as<uint2>(), c->d_cands.as<Cand>(),
+        &a.counters->scored_cols, nullptr, 0, 0);
+  }
+  {
+    Span sp(&c->ev_match, c->stream, kPhRescore);
+    rescore_kernel<<<a.blocks128, 128, 0, c->stream>>>(a.images, a.tasks, a.blk_off, a.n_tasks, a.segs,
+                                                       c->d_cands.as<Cand>(), a.thr, a.ratio, a.rowres,
+                                                       c->d_redo.as<uint2>(), &a.counters->rescore);
+    exact_rows_kernel<<<c->sm_count * 2, 256, 0, c->stream>>>(a.images, a.tasks, c->d_redo.as<uint2>(),
+                                                             &a.counters->rescore, a.thr, a.ratio, a.rowres);
+    fold_redo_kernel<<<1, 1, 0, c->stream>>>(a.counters);
+  }
+  c->stats.kernel_launches += 5;
+  c->stats.score_launches += 1;
+  return cudaGetLastError();
+}
+
+}  // namespace fm

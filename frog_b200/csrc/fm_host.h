@@ -1,0 +1,118 @@
+// fm_host.h -- host-side state of libfrogmatch shared by fm_api.cu and the fast-path driver.
+#pragma once
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/frogmatch.h"
+#include "fm_common.cuh"
+
+namespace fm {
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = std::max(bytes, (size_t)256);
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+enum Phase { kPhScore = 0, kPhRescore, kPhExact, kPhCompact, kPhPrep, kPhBands, kPhTotal, kNumPhases };
+
+struct EventPair {
+  cudaEvent_t a, b;
+  int phase;
+};
+
+struct EventPool {
+  std::vector<cudaEvent_t> pool;
+  size_t next = 0;
+  std::vector<EventPair> spans;
+  cudaEvent_t get() {
+    if (next == pool.size()) {
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      pool.push_back(e);
+    }
+    return pool[next++];
+  }
+  void reset() { next = 0; spans.clear(); }
+  void destroy() {
+    for (auto e : pool) cudaEventDestroy(e);
+    pool.clear();
+    reset();
+  }
+};
+
+// RAII CUDA-event bracket around a phase on the context stream.
+struct Span {
+  EventPool* pool;
+  cudaStream_t stream;
+  EventPair ep;
+  Span(EventPool* p, cudaStream_t s, int phase) : pool(p), stream(s) {
+    ep.a = pool->get();
+    ep.b = pool->get();
+    ep.phase = phase;
+    cudaEventRecord(ep.a, stream);
+  }
+  ~Span() {
+    cudaEventRecord(ep.b, stream);
+    pool->spans.push_back(ep);
+  }
+};
+
+// Device tensors of one image on the tensor-core path (see ImageDev in fm_common.cuh).
+struct FastImageBufs {
+  DevBuf keys, keys_sorted, idx, perm, scale_sorted, norm2, rowop, colop, sort_tmp;
+  void release() {
+    keys.release(); keys_sorted.release(); idx.release(); perm.release(); scale_sorted.release();
+    norm2.release(); rowop.release(); colop.release(); sort_tmp.release();
+  }
+};
+
+struct Image {
+  bool valid = false;
+  uint32_t n = 0, d = 0;
+  DevBuf desc, scale, lap;
+  FastImageBufs fast;
+};
+
+}  // namespace fm
+
+struct fm_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr, own_stream = nullptr;
+  int sm_count = 0;
+  std::vector<fm::Image> images;
+  std::vector<fm::ImageDev> h_images;
+  std::vector<fm::ImageMeta> h_metas;
+  fm::DevBuf d_images, d_metas;
+  uint32_t metas_cap = 0;
+  bool images_dirty = true;
+  uint32_t dim = 0;
+  // per-call scratch
+  fm::DevBuf d_meta_blob, d_rowres, d_chunk_count, d_chunk_out, d_totals;
+  fm::DevBuf d_bands, d_cands, d_redo, d_taskinfo;
+  // caches handed to results
+  fm::DevBuf cache_out, cache_counts;
+  void* cache_pinned = nullptr;
+  size_t cache_pinned_cap = 0;
+  unsigned long long* h_pinned = nullptr;  // 8 x u64 scratch for small D2H reads
+  fm::EventPool ev_match, ev_prep;
+  fm_stats stats{};
+  bool exact_attr_set = false, score_attr_set = false;
+  std::string err;
+};

@@ -1,0 +1,158 @@
+// fm_rescore.cuh -- exact FP32 rescoring of the tensor-core candidates + the accept decision
+// (replaces the tail of ComputeMatches, match.cpp:303-330, for rows scored by fm_score.cuh).
+//
+// Soundness.  Let t~ be the FP16-operand score and t the exact value of a.b - |b|^2/2, with
+// |t~ - t| <= eps for every pair of the task.  If A2 is the second-largest t~ of a row, every
+// column that can be the exact nearest or second-nearest neighbour (or tie with them) has
+// t~ >= A2 - 2*eps.  Each candidate list keeps the row's top-4 t~ of its column segment, so it
+// holds every such column unless its 4th entry itself is >= A2 - 2*eps -- in that (rare) case
+// the row is queued for the exact brute-force row kernel below.  Surviving candidates are
+// re-evaluated with the reference's own arithmetic (gates, sequential FP32 norm, strict compares,
+// lowest-original-index tie rule), so accepted pairs are bit-identical to the reference.
+#pragma once
+#include "fm_common.cuh"
+#include "fm_exact.cuh"
+#include "fm_score.cuh"
+
+namespace fm {
+
+struct RescoreCounters {
+  unsigned long long candidates;  // exact distances evaluated
+  unsigned long long redo_rows;   // rows handed to exact_rows_kernel
+};
+
+__device__ __forceinline__ float exact_norm48(const float (&r)[kD], const float* __restrict__ col) {
+  float acc = 0.f;
+  const float4* c4 = reinterpret_cast<const float4*>(col);
+#pragma unroll
+  for (int q = 0; q < kD / 4; q++) {
+    float4 v = __ldg(c4 + q);
+    float e;
+    e = __fsub_rn(r[4 * q], v.x);     acc = __fadd_rn(acc, __fmul_rn(e, e));
+    e = __fsub_rn(r[4 * q + 1], v.y); acc = __fadd_rn(acc, __fmul_rn(e, e));
+    e = __fsub_rn(r[4 * q + 2], v.z); acc = __fadd_rn(acc, __fmul_rn(e, e));
+    e = __fsub_rn(r[4 * q + 3], v.w); acc = __fadd_rn(acc, __fmul_rn(e, e));
+  }
+  return acc;
+}
+
+// Order-independent form of match.cpp:303-313: (d1, match, d2) = (min, lowest index attaining it,
+// second smallest of the multiset).
+__device__ __forceinline__ void top2_merge_one(float dist, uint32_t j, float& d1, float& d2, uint32_t& match) {
+  if (dist < d1) { d2 = d1; d1 = dist; match = j; }
+  else if (dist == d1) { d2 = d1; if (j < match) match = j; }
+  else if (dist < d2) { d2 = dist; }
+}
+
+// One thread per sorted row of the task.
+__global__ void __launch_bounds__(128)
+rescore_kernel(const ImageDev* __restrict__ images, const Task* __restrict__ tasks,
+               const uint32_t* __restrict__ task_blk_off, uint32_t n_tasks, uint32_t segs,
+               const Cand* __restrict__ cands, float thr, float ratio, uint32_t* __restrict__ rowres,
+               uint2* __restrict__ redo_list, RescoreCounters* __restrict__ counters) {
+  const uint32_t t = find_segment(task_blk_off, n_tasks, blockIdx.x);
+  const Task task = tasks[t];
+  if (task.flags & kTaskExact) return;
+  const ImageDev A = images[task.col_img];
+  const ImageDev B = images[task.row_img];
+  const uint32_t s = (blockIdx.x - task_blk_off[t]) * 128 + threadIdx.x;
+  if (s >= B.n) return;
+  const uint32_t row = B.perm[s];
+  const float eps = task_eps(A.meta->max_norm2, B.meta->max_norm2);
+
+  const uint32_t L = segs * kTopK;
+  const Cand* c = cands + (size_t)(task.row_off + s) * L;
+  float a1 = -INFINITY, a2 = -INFINITY;
+  for (uint32_t e = 0; e < L; e++) {
+    float v = c[e].t;
+    if (v > a1) { a2 = a1; a1 = v; } else if (v > a2) { a2 = v; }
+  }
+  const float band = a2 - 2.f * eps;  // -inf when the row has fewer than two candidates
+  bool overflow = false;
+  for (uint32_t g = 0; g < segs; g++) {
+    float last = c[g * kTopK + kTopK - 1].t;
+    if (last > -INFINITY && last >= band) overflow = true;
+  }
+
+  uint32_t match = kNone;
+  uint32_t n_eval = 0;
+  if (!overflow && a1 > -INFINITY) {
+    float r[kD];
+    const float4* src = reinterpret_cast<const float4*>(B.desc + (size_t)row * kD);
+#pragma unroll
+    for (int q = 0; q < kD / 4; q++) {
+      float4 v = __ldg(src + q);
+      r[4 * q] = v.x; r[4 * q + 1] = v.y; r[4 * q + 2] = v.z; r[4 * q + 3] = v.w;
+    }
+    const float sc = B.scale[row], lp = B.lap[row];
+    float d1 = FLT_MAX, d2 = FLT_MAX;
+    uint32_t best = 0;
+    for (uint32_t e = 0; e < L; e++) {
+      const Cand cd = c[e];
+      if (!(cd.t > -INFINITY) || !(cd.t >= band)) continue;
+      const uint32_t j = A.perm[cd.col];
+      if (lp != A.lap[j]) continue;                    // match.cpp:270
+      if (scale_gate_fails(sc, A.scale[j])) continue;  // match.cpp:273-275
+      const float dist = exact_norm48(r, A.desc + (size_t)j * kD);
+      n_eval++;
+      top2_merge_one(dist, j, d1, d2, best);
+    }
+    if (accept_rule(d1, d2, thr, ratio)) match = best;
+  }
+  rowres[task.row_off + row] = match;
+  if (overflow) {
+    unsigned long long slot = atomicAdd(&counters->redo_rows, 1ull);
+    redo_list[slot] = make_uint2(t, row);
+  }
+  // statistics: one atomic per warp
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) n_eval += __shfl_xor_sync(0xffffffffu, n_eval, o);
+  if ((threadIdx.x & 31) == 0 && n_eval) atomicAdd(&counters->candidates, (unsigned long long)n_eval);
+}
+
+// Brute-force redo of queued rows: one warp per row, lanes stride over the columns in original
+// order, per-lane sequential top-2, then a multiset merge across lanes.
+__global__ void __launch_bounds__(256)
+exact_rows_kernel(const ImageDev* __restrict__ images, const Task* __restrict__ tasks,
+                  const uint2* __restrict__ redo_list, const RescoreCounters* __restrict__ counters, float thr,
+                  float ratio, uint32_t* __restrict__ rowres) {
+  const uint32_t lane = threadIdx.x & 31;
+  const unsigned long long n = counters->redo_rows;
+  const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+  for (unsigned long long w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n; w += warps) {
+    const uint2 item = redo_list[w];
+    const Task task = tasks[item.x];
+    const ImageDev A = images[task.col_img];
+    const ImageDev B = images[task.row_img];
+    const uint32_t row = item.y;
+    float r[kD];
+    const float4* src = reinterpret_cast<const float4*>(B.desc + (size_t)row * kD);
+#pragma unroll
+    for (int q = 0; q < kD / 4; q++) {
+      float4 v = __ldg(src + q);
+      r[4 * q] = v.x; r[4 * q + 1] = v.y; r[4 * q + 2] = v.z; r[4 * q + 3] = v.w;
+    }
+    const float sc = B.scale[row], lp = B.lap[row];
+    float d1 = FLT_MAX, d2 = FLT_MAX;
+    uint32_t match = 0;
+    for (uint32_t j = lane; j < A.n; j += 32) {
+      if (lp != A.lap[j]) continue;
+      if (scale_gate_fails(sc, A.scale[j])) continue;
+      const float dist = exact_norm48(r, A.desc + (size_t)j * kD);
+      if (dist < d1) { d2 = d1; d1 = dist; match = j; } else if (dist < d2) { d2 = dist; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float od1 = __shfl_xor_sync(0xffffffffu, d1, o);
+      const float od2 = __shfl_xor_sync(0xffffffffu, d2, o);
+      const uint32_t om = __shfl_xor_sync(0xffffffffu, match, o);
+      const bool other_wins = od1 < d1 || (od1 == d1 && om < match);
+      const float hi_d1 = fmaxf(d1, od1);  // the larger of the two minima is a second-smallest candidate
+      d2 = fminf(hi_d1, fminf(d2, od2));
+      if (other_wins) { d1 = od1; match = om; }
+    }
+    if (lane == 0) rowres[task.row_off + row] = accept_rule(d1, d2, thr, ratio) ? match : kNone;
+  }
+}
+
+}  // namespace fm

@@ -1,0 +1,350 @@
+// fm_score.cuh -- the tensor-core scoring kernel (replaces norm() + the inner loop of
+// ComputeMatches, match.cpp:243-251 and :267-317) and the band kernel that feeds it.
+//
+// One CTA scores a "unit": 256 consecutive (laplacian, scale)-sorted rows of image `second`
+// against one contiguous range of 128-column tiles of image `first`.
+//   warp 0      TMA producer: cp.async.bulk 16 KB pre-swizzled FP16 tiles -> smem ring (mbarrier tx)
+//   warp 1      MMA issuer  : tcgen05.mma kind::f16, M=128 N=128 K=16, 4 K-steps x 2 row halves per
+//                             tile, FP32 accumulators double-buffered in TMEM (4 x 128 columns)
+//   warp 2      TMEM allocator
+//   warps 4..11 epilogue    : tcgen05.ld (TMEM lane == row, so a row's scan over columns is
+//                             thread-local), gate mask on band-edge tiles only, running top-4
+//                             (value, column) per row kept in registers
+// Scores never touch HBM: per row only the 4 best (t, column) candidates leave the SM.
+// t = a.b - |b|^2/2 comes straight out of the MMA (K slots 48,49, see fm_prep.cuh), so
+// larger t <=> smaller squared distance.
+#pragma once
+#include "fm_common.cuh"
+#include "fm_exact.cuh"
+#include "fm_ptx.cuh"
+
+namespace fm {
+
+constexpr int kTileBytes = 16384;  // 128 rows x 64 halves
+constexpr int kTileCols = 128;
+constexpr int kUnitRows = 256;
+constexpr int kStages = 6;
+constexpr int kTopK = 4;
+constexpr int kEpiWarps = 8;
+constexpr int kScoreThreads = (4 + kEpiWarps) * 32;
+
+struct Cand {
+  float t;       // approximate score, -inf for an empty slot
+  uint32_t col;  // sorted column position in image `first`
+};
+
+struct alignas(1024) ScoreSmem {
+  uint8_t a[2][kTileBytes];
+  uint8_t b[kStages][kTileBytes];
+  uint64_t bar_a;
+  uint64_t bar_bfull[kStages];
+  uint64_t bar_bempty[kStages];
+  uint64_t bar_accfull[2];
+  uint64_t bar_accempty[2];
+  uint32_t tmem_base;
+  uint32_t cmin, cmax;
+};
+constexpr size_t kScoreSmemBytes = sizeof(ScoreSmem) + 1024;
+
+// ------------------------------------------------------------------------------------------------
+// Band kernel: for every sorted row of image `second`, the interval [lo, hi) of sorted columns of
+// image `first` that pass BOTH reference gates.  Within one laplacian class columns are sorted
+// by scale and float division is monotone, so
+//   lo = first column with !(s_row / s_col > 1.3f)      (match.cpp:273)
+//   hi = first column with  (s_col / s_row > 1.3f)      (match.cpp:274)
+// found by binary search with the reference's own float predicate.
+__global__ void __launch_bounds__(128)
+bands_kernel(const ImageDev* __restrict__ images, const Task* __restrict__ tasks,
+             const uint32_t* __restrict__ task_blk_off, uint32_t n_tasks, uint2* __restrict__ bands) {
+  const uint32_t t = find_segment(task_blk_off, n_tasks, blockIdx.x);
+  const Task task = tasks[t];
+  if (task.flags & kTaskExact) return;
+  const ImageDev A = images[task.col_img];
+  const ImageDev B = images[task.row_img];
+  const uint32_t s = (blockIdx.x - task_blk_off[t]) * 128 + threadIdx.x;
+  if (s >= B.n) return;
+  const ImageMeta* mb = B.meta;
+  const ImageMeta* ma = A.meta;
+  // class of this row in B, then the class with the same laplacian value in A
+  uint32_t cb = 0;
+  while (cb + 1 < mb->n_classes && mb->class_begin[cb + 1] <= s) cb++;
+  const float lap = mb->class_lap[cb];
+  uint32_t lo = 0, hi = 0;
+  for (uint32_t ca = 0; ca < ma->n_classes; ca++) {
+    if (ma->class_lap[ca] == lap) {
+      const uint32_t beg = ma->class_begin[ca], end = ma->class_begin[ca + 1];
+      const float sr = B.scale_sorted[s];
+      const float* sc = A.scale_sorted;
+      uint32_t l = beg, h = end;
+      while (l < h) {  // first col with !(sr / sc > 1.3f)
+        uint32_t m = (l + h) >> 1;
+        if (__fdiv_rn(sr, sc[m]) > 1.3f) l = m + 1; else h = m;
+      }
+      lo = l;
+      h = end;
+      while (l < h) {  // first col >= lo with (sc / sr > 1.3f)
+        uint32_t m = (l + h) >> 1;
+        if (__fdiv_rn(sc[m], sr) > 1.3f) h = m; else l = m + 1;
+      }
+      hi = l;
+      break;
+    }
+  }
+  if (hi < lo) hi = lo;
+  bands[task.row_off + s] = make_uint2(lo, hi);
+}
+
+// ------------------------------------------------------------------------------------------------
+
+struct TopK {
+  float v[kTopK];
+  uint32_t i[kTopK];
+};
+
+// Insert (v, idx) into the descending list; caller guarantees v > t.v[3].
+__device__ __forceinline__ void topk_insert(TopK& t, float v, uint32_t idx) {
+  if (v > t.v[1]) {
+    t.v[3] = t.v[2]; t.i[3] = t.i[2];
+    t.v[2] = t.v[1]; t.i[2] = t.i[1];
+    if (v > t.v[0]) { t.v[1] = t.v[0]; t.i[1] = t.i[0]; t.v[0] = v; t.i[0] = idx; }
+    else            { t.v[1] = v; t.i[1] = idx; }
+  } else {
+    if (v > t.v[2]) { t.v[3] = t.v[2]; t.i[3] = t.i[2]; t.v[2] = v; t.i[2] = idx; }
+    else            { t.v[3] = v; t.i[3] = idx; }
+  }
+}
+
+__device__ __forceinline__ float max3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
+
+// Bound on |t~ - t| (FP16-operand score vs exact a.b - |b|^2/2) for a task, from the two images'
+// maximum squared norms:
+//   FP16 rounding of both operands   <= (2^-10 + 2^-22) |a||b|
+//   hi/lo split of -|b|^2/2, FP32 accumulation inside the tensor core, FP32 evaluation of |b|^2,
+//   FP16 subnormal flush and the reference's own FP32 rounding of d^2  -> the second term.
+__device__ __forceinline__ float task_eps(float max_n2_a, float max_n2_b) {
+  return 1.05e-3f * sqrtf(max_n2_a * max_n2_b) + 3e-5f * fmaxf(1.f, fmaxf(max_n2_a, max_n2_b));
+}
+
+// 16 consecutive columns of one row.  kMasked: columns outside [lo, hi) are gated out.
+// Fast path: a 3-input max tree and one compare against the capture threshold
+//   thr = max(4th best so far, 2nd best so far - 2 eps).
+// Only columns above thr can be (or tie with) the exact nearest / second-nearest neighbour, or
+// must be kept so the rescoring pass can certify the list (fm_rescore.cuh); that happens for
+// about 2 ln N columns per row, so the insert stays an out-of-line branch.
+template <bool kMasked>
+__device__ __forceinline__ void score_chunk(const uint32_t (&r)[16], uint32_t col0, uint32_t lo, uint32_t width,
+                                            TopK& tk, float& thr, float two_eps) {
+  float f[16];
+#pragma unroll
+  for (int e = 0; e < 16; e++) {
+    f[e] = __uint_as_float(r[e]);
+    if (kMasked) f[e] = ((col0 + e) - lo < width) ? f[e] : -INFINITY;
+  }
+  const float m0 = max3(f[0], f[1], f[2]), m1 = max3(f[3], f[4], f[5]), m2 = max3(f[6], f[7], f[8]);
+  const float m3 = max3(f[9], f[10], f[11]), m4 = max3(f[12], f[13], f[14]);
+  const float m = fmaxf(max3(m0, m1, m2), max3(m3, m4, f[15]));
+  if (m > thr) {
+#pragma unroll
+    for (int e = 0; e < 16; e++) {
+      if (f[e] > thr) {
+        asm volatile("" ::: "memory");  // keep a real branch (no if-conversion into 30 selects per column)
+        topk_insert(tk, f[e], col0 + e);
+        thr = fmaxf(tk.v[kTopK - 1], tk.v[1] - two_eps);
+      }
+    }
+  }
+}
+
+template <bool kMasked, bool kDump>
+__device__ __forceinline__ void score_tile(uint32_t taddr, uint32_t cb, uint32_t lo, uint32_t width, TopK& tk,
+                                           float& thr, float two_eps, uint64_t* bar_release, float* dump_row) {
+  uint32_t ra[16], rb[16];
+  ptx::tmem_ld16(ra, taddr);
+  ptx::tmem_ld_wait(ra);
+  // Rolled on purpose: the insert branches make the body large, and one copy of it must stay
+  // resident in the instruction cache.
+#pragma unroll 1
+  for (int c = 0; c < kTileCols / 16; c += 2) {
+    ptx::tmem_ld16(rb, taddr + (c + 1) * 16);  // next 16 columns in flight while these are scanned
+    if (kDump) {
+#pragma unroll
+      for (int e = 0; e < 16; e++) dump_row[cb + c * 16 + e] = __uint_as_float(ra[e]);
+    }
+    score_chunk<kMasked>(ra, cb + c * 16, lo, width, tk, thr, two_eps);
+    ptx::tmem_ld_wait(rb);
+    if (c + 2 < kTileCols / 16) {
+      ptx::tmem_ld16(ra, taddr + (c + 2) * 16);
+    } else {
+      // every column of this accumulator is now in registers: hand it back to the MMA warp
+      ptx::tc_fence_before();
+      __syncwarp();
+      if ((threadIdx.x & 31) == 0) ptx::mbar_arrive(bar_release);
+    }
+    if (kDump) {
+#pragma unroll
+      for (int e = 0; e < 16; e++) dump_row[cb + (c + 1) * 16 + e] = __uint_as_float(rb[e]);
+    }
+    score_chunk<kMasked>(rb, cb + (c + 1) * 16, lo, width, tk, thr, two_eps);
+    if (c + 2 < kTileCols / 16) ptx::tmem_ld_wait(ra);
+  }
+}
+
+// unit_off: exclusive prefix of units per task (n_tasks + 1 entries).  A task with n rows has
+// ceil(n / 256) * segs units; unit = row_block * segs + seg.
+// cands: [batch rows][segs][kTopK].   dump (kDump only): [256][dump_ld] raw t of unit 0.
+template <bool kDump>
+__global__ void __launch_bounds__(kScoreThreads, 1)
+score_kernel(const ImageDev* __restrict__ images, const Task* __restrict__ tasks,
+             const uint32_t* __restrict__ unit_off, uint32_t n_tasks, uint32_t segs,
+             const uint2* __restrict__ bands, Cand* __restrict__ cands, unsigned long long* __restrict__ scored_cols,
+             float* __restrict__ dump, uint32_t dump_ld, uint32_t unit_base) {
+  extern __shared__ uint8_t smem_raw[];
+  ScoreSmem& sm = *reinterpret_cast<ScoreSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+
+  const uint32_t unit = blockIdx.x + unit_base;  // unit_base != 0 only for single-unit debug launches
+  const uint32_t t = find_segment(unit_off, n_tasks, unit);
+  const Task task = tasks[t];
+  if (task.flags & kTaskExact) return;
+  const ImageDev A = images[task.col_img];
+  const ImageDev B = images[task.row_img];
+  const uint32_t local = unit - unit_off[t];
+  const uint32_t rb = local / segs, seg = local - rb * segs;
+
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool is_epi = warp >= 4;
+  // epilogue thread -> row: TMEM sub-partition = warp % 4, accumulator half = (warp - 4) / 4
+  const uint32_t half = is_epi ? (warp - 4) >> 2 : 0;
+  const uint32_t row_in_unit = half * 128 + (warp & 3) * 32 + lane;
+  const uint32_t s = rb * kUnitRows + row_in_unit;
+  uint32_t lo = 0, hi = 0;
+  if (is_epi && s < B.n) {
+    uint2 bd = bands[task.row_off + s];
+    lo = bd.x;
+    hi = bd.y;
+  }
+  // warp-level and CTA-level column ranges
+  uint32_t w_cmin = (hi > lo) ? lo : 0xFFFFFFFFu, w_cmax = (hi > lo) ? hi : 0u;
+  uint32_t w_imin = lo, w_imax = hi;  // interior: columns every row of the warp accepts
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    w_cmin = min(w_cmin, __shfl_xor_sync(0xffffffffu, w_cmin, o));
+    w_cmax = max(w_cmax, __shfl_xor_sync(0xffffffffu, w_cmax, o));
+    w_imin = max(w_imin, __shfl_xor_sync(0xffffffffu, w_imin, o));
+    w_imax = min(w_imax, __shfl_xor_sync(0xffffffffu, w_imax, o));
+  }
+  if (threadIdx.x == 0) { sm.cmin = 0xFFFFFFFFu; sm.cmax = 0u; }
+  __syncthreads();
+  if (is_epi && lane == 0 && w_cmax > w_cmin) { atomicMin(&sm.cmin, w_cmin); atomicMax(&sm.cmax, w_cmax); }
+  __syncthreads();
+  const uint32_t cmin = sm.cmin, cmax = sm.cmax;
+  uint32_t tile0 = 0, n_tiles = 0;
+  if (cmax > cmin) {
+    const uint32_t tb = cmin / kTileCols, te = (cmax + kTileCols - 1) / kTileCols;
+    const uint32_t nt = te - tb;
+    tile0 = tb + (uint32_t)(((uint64_t)nt * seg) / segs);
+    n_tiles = tb + (uint32_t)(((uint64_t)nt * (seg + 1)) / segs) - tile0;
+  }
+
+  TopK tk;
+#pragma unroll
+  for (int k = 0; k < kTopK; k++) { tk.v[k] = -INFINITY; tk.i[k] = 0; }
+
+  if (n_tiles > 0) {  // CTA-uniform
+    if (warp == 1 && lane == 0) {
+      ptx::mbar_init(&sm.bar_a, 1);
+      for (int i = 0; i < kStages; i++) { ptx::mbar_init(&sm.bar_bfull[i], 1); ptx::mbar_init(&sm.bar_bempty[i], 1); }
+      for (int i = 0; i < 2; i++) { ptx::mbar_init(&sm.bar_accfull[i], 1); ptx::mbar_init(&sm.bar_accempty[i], kEpiWarps); }
+      ptx::fence_mbar_init();
+    }
+    if (warp == 2) ptx::tmem_alloc_512(&sm.tmem_base);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem = sm.tmem_base;
+
+    if (warp == 0) {
+      if (lane == 0) {
+        // ---- TMA producer ------------------------------------------------------------------
+        const uint8_t* rowop = reinterpret_cast<const uint8_t*>(B.rowop) + (size_t)rb * 2 * kTileBytes;
+        ptx::mbar_expect_tx(&sm.bar_a, 2 * kTileBytes);
+        ptx::bulk_g2s(sm.a[0], rowop, kTileBytes, &sm.bar_a);
+        ptx::bulk_g2s(sm.a[1], rowop + kTileBytes, kTileBytes, &sm.bar_a);
+        const uint8_t* colop = reinterpret_cast<const uint8_t*>(A.colop);
+        for (uint32_t i = 0; i < n_tiles; i++) {
+          const uint32_t st = i % kStages, use = i / kStages;
+          if (use > 0) ptx::mbar_wait(&sm.bar_bempty[st], (use - 1) & 1);
+          ptx::mbar_expect_tx(&sm.bar_bfull[st], kTileBytes);
+          ptx::bulk_g2s(sm.b[st], colop + (size_t)(tile0 + i) * kTileBytes, kTileBytes, &sm.bar_bfull[st]);
+        }
+      }
+    } else if (warp == 1) {
+      if (lane == 0) {
+        // ---- MMA issuer ----------------------------------------------------------------------
+        constexpr uint32_t idesc = ptx::umma_idesc_f16_f32(128, kTileCols);
+        const uint64_t adesc0 = ptx::umma_desc_sw128(ptx::smem_u32(sm.a[0]));
+        const uint64_t adesc1 = ptx::umma_desc_sw128(ptx::smem_u32(sm.a[1]));
+        ptx::mbar_wait(&sm.bar_a, 0);
+        for (uint32_t i = 0; i < n_tiles; i++) {
+          const uint32_t st = i % kStages, acc = i & 1, use = i >> 1;
+          if (use > 0) ptx::mbar_wait(&sm.bar_accempty[acc], (use - 1) & 1);
+          ptx::mbar_wait(&sm.bar_bfull[st], (i / kStages) & 1);
+          ptx::tc_fence_after();
+          const uint64_t bdesc = ptx::umma_desc_sw128(ptx::smem_u32(sm.b[st]));
+#pragma unroll
+          for (int k = 0; k < kKPad / 16; k++)  // +32 B per K step inside the 128 B swizzle row
+            ptx::mma_f16_ss(tmem + acc * 256, adesc0 + 2 * k, bdesc + 2 * k, idesc, k > 0);
+#pragma unroll
+          for (int k = 0; k < kKPad / 16; k++)
+            ptx::mma_f16_ss(tmem + acc * 256 + 128, adesc1 + 2 * k, bdesc + 2 * k, idesc, k > 0);
+          ptx::mma_commit(&sm.bar_bempty[st]);
+          ptx::mma_commit(&sm.bar_accfull[acc]);
+        }
+      }
+    } else if (is_epi) {
+      // ---- epilogue ------------------------------------------------------------------------------
+      const uint32_t width = hi - lo;
+      const float two_eps = 2.f * task_eps(A.meta->max_norm2, B.meta->max_norm2);
+      float thr = -INFINITY;
+      float* dump_row = kDump ? dump + (size_t)row_in_unit * dump_ld : nullptr;
+      unsigned long long scored = 0;
+      for (uint32_t i = 0; i < n_tiles; i++) {
+        const uint32_t acc = i & 1;
+        const uint32_t cb = (tile0 + i) * kTileCols;
+        ptx::mbar_wait(&sm.bar_accfull[acc], (i >> 1) & 1);
+        ptx::tc_fence_after();
+        const uint32_t taddr = tmem + (((warp & 3) * 32) << 16) + acc * 256 + half * 128;
+        const bool needed = kDump || (cb < w_cmax && cb + kTileCols > w_cmin);  // warp-uniform
+        if (!needed) {
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&sm.bar_accempty[acc]);
+        } else if (!kDump && cb >= w_imin && cb + kTileCols <= w_imax) {
+          score_tile<false, kDump>(taddr, cb, lo, width, tk, thr, two_eps, &sm.bar_accempty[acc], dump_row);
+          scored += kTileCols;
+        } else {
+          score_tile<true, kDump>(taddr, cb, lo, width, tk, thr, two_eps, &sm.bar_accempty[acc], dump_row);
+          scored += kTileCols;
+        }
+      }
+      if (scored_cols != nullptr) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) scored += __shfl_xor_sync(0xffffffffu, scored, o);
+        if (lane == 0) atomicAdd(scored_cols, scored);
+      }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+      ptx::tc_fence_after();
+      ptx::tmem_dealloc_512(tmem);
+    }
+  }
+
+  if (is_epi && s < B.n) {
+    Cand* out = cands + ((size_t)(task.row_off + s) * segs + seg) * kTopK;
+#pragma unroll
+    for (int k = 0; k < kTopK; k++) out[k] = Cand{tk.v[k], tk.i[k]};
+  }
+}
+
+}  // namespace fm

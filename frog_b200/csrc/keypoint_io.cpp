@@ -1,0 +1,249 @@
+// keypoint_io.cpp -- see keypoint_io.h.
+#include "keypoint_io.h"
+
+#include <zlib.h>
+
+#include <algorithm>
+#include <cerrno>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+namespace fmio {
+
+namespace {
+
+bool slurp(const std::string& path, std::vector<char>& buf, std::string& err) {
+  FILE* f = fopen(path.c_str(), "rb");
+  if (!f) { err = "cannot open " + path; return false; }
+  fseek(f, 0, SEEK_END);
+  long sz = ftell(f);
+  fseek(f, 0, SEEK_SET);
+  buf.resize((size_t)std::max(sz, 0L) + 1);
+  size_t got = sz > 0 ? fread(buf.data(), 1, (size_t)sz, f) : 0;
+  fclose(f);
+  buf.resize(got + 1);
+  buf[got] = 0;
+  return true;
+}
+
+// std::stof semantics (match.cpp:69,152) on the cell [c, ce): strtof after leading blanks, longest
+// valid prefix, trailing junk ignored; no conversion or ERANGE make std::stof throw, which
+// terminates the reference -- reported here as an error.
+inline bool cell_to_float(const char* c, const char* ce, float& v) {
+  while (c < ce && (*c == ' ' || (*c >= '\t' && *c <= '\r'))) c++;
+  if (c == ce) return false;
+  char* endp = nullptr;
+  errno = 0;
+  v = strtof(c, &endp);  // stops at ',' '\n' or NUL at the latest: none can continue a number
+  if (endp == c || errno == ERANGE) return false;
+  return true;
+}
+
+}  // namespace
+
+bool parse_csv_text(const char* text, size_t len, KeypointSet& out, std::string& err) {
+  out = KeypointSet{};
+  const char* p = text;
+  const char* const end_all = text + len;
+  std::vector<float> row;
+  row.reserve(64);
+  size_t line_no = 0;
+  while (p < end_all) {
+    const char* eol = static_cast<const char*>(memchr(p, '\n', (size_t)(end_all - p)));
+    const char* end = eol ? eol : end_all;
+    line_no++;
+    row.clear();
+    const char* c = p;
+    // std::getline(lineStream, cell, ',') loop of match.cpp:150: an exhausted stream yields no
+    // further (empty) cell, a cell starting with CR ends the row.
+    while (c < end) {
+      const char* comma = static_cast<const char*>(memchr(c, ',', (size_t)(end - c)));
+      const char* ce = comma ? comma : end;
+      if (*c == 13) break;
+      float v;
+      if (!cell_to_float(c, ce, v)) {
+        err = "stof failed at line " + std::to_string(line_no) + " cell " + std::to_string(row.size());
+        return false;
+      }
+      row.push_back(v);
+      if (!comma) break;
+      c = comma + 1;
+    }
+    if (row.size() > 6) {  // match.cpp:170
+      const uint32_t d = (uint32_t)row.size() - 6;
+      if (out.n == 0) out.d = d;
+      if (d != out.d) {
+        err = "descriptor length changes inside the file (line " + std::to_string(line_no) + ")";
+        return false;
+      }
+      out.head.insert(out.head.end(), row.begin(), row.begin() + 6);
+      out.desc.insert(out.desc.end(), row.begin() + 6, row.end());
+      out.n++;
+    }
+    if (!eol) break;
+    p = eol + 1;
+  }
+  return true;
+}
+
+bool read_csv(const std::string& path, KeypointSet& out, std::string& err) {
+  std::vector<char> buf;
+  if (!slurp(path, buf, err)) return false;
+  return parse_csv_text(buf.data(), buf.size() - 1, out, err);
+}
+
+bool read_csv_gz(const std::string& path, KeypointSet& out, std::string& err) {
+  std::vector<char> raw;
+  if (!slurp(path, raw, err)) return false;
+  std::vector<char> text;
+  z_stream zs{};
+  if (inflateInit2(&zs, 15 + 32) != Z_OK) { err = "zlib init failed"; return false; }
+  zs.next_in = reinterpret_cast<Bytef*>(raw.data());
+  zs.avail_in = (uInt)(raw.size() - 1);
+  size_t produced = 0;
+  text.resize(std::max<size_t>(raw.size() * 4, 1 << 16));
+  int rc = Z_OK;
+  while (rc != Z_STREAM_END) {
+    if (produced == text.size()) text.resize(text.size() * 2);
+    const size_t chunk = std::min<size_t>(text.size() - produced, 1u << 30);
+    zs.next_out = reinterpret_cast<Bytef*>(text.data() + produced);
+    zs.avail_out = (uInt)chunk;
+    rc = inflate(&zs, Z_NO_FLUSH);
+    produced += chunk - zs.avail_out;
+    if (rc != Z_OK && rc != Z_STREAM_END) break;  // truncated / corrupt: keep what was inflated
+    if (rc == Z_OK && zs.avail_in == 0 && zs.avail_out != 0) break;
+  }
+  inflateEnd(&zs);
+  text.resize(produced + 1);
+  text[produced] = 0;
+  return parse_csv_text(text.data(), produced, out, err);
+}
+
+bool read_bin(const std::string& path, KeypointSet& out, std::string& err) {
+  std::vector<char> buf;
+  if (!slurp(path, buf, err)) return false;
+  const size_t len = buf.size() - 1;
+  out = KeypointSet{};
+  out.d = 48;  // match.cpp:201
+  // Replay of `while(!feof(file))` (match.cpp:184-205) over an in-memory image of the file:
+  // fread(&valF,4,1) returns 0 at EOF and leaves valF as it was (a short tail is copied
+  // partially, as glibc does), so after the last full record one more iteration runs whose six
+  // header fields all equal the last response and whose descriptor is 48 zeros.
+  size_t pos = 0;
+  bool eof = false;
+  float valF = 0.f;
+  auto read_float = [&]() {
+    size_t avail = len - pos;
+    if (avail >= 4) { memcpy(&valF, buf.data() + pos, 4); pos += 4; }
+    else { if (avail) memcpy(&valF, buf.data() + pos, avail); pos = len; eof = true; }
+  };
+  while (!eof) {
+    float h[6];
+    for (int k = 0; k < 6; k++) { read_float(); h[k] = valF; }
+    float desc[48] = {0};
+    size_t avail = len - pos;
+    if (avail >= sizeof desc) { memcpy(desc, buf.data() + pos, sizeof desc); pos += sizeof desc; }
+    else { if (avail) memcpy(desc, buf.data() + pos, avail); pos = len; eof = true; }
+    out.head.insert(out.head.end(), h, h + 6);
+    out.desc.insert(out.desc.end(), desc, desc + 48);
+    out.n++;
+  }
+  return true;
+}
+
+bool read_keypoints(const std::string& path, KeypointSet& out, std::string& err) {
+  const std::string ext = path.substr(path.find_last_of('.') + 1);  // match.cpp:514
+  if (ext == "csv") return read_csv(path, out, err);
+  if (ext == "bin") return read_bin(path, out, err);
+  if (ext == "gz") return read_csv_gz(path, out, err);
+  err = "Bad file format : " + ext;  // match.cpp:535 (the reference then dereferences garbage)
+  return false;
+}
+
+static void keep_rows(KeypointSet& k, const std::vector<uint32_t>& rows) {
+  KeypointSet o;
+  o.d = k.d;
+  o.n = (uint32_t)rows.size();
+  o.head.resize((size_t)o.n * 6);
+  o.desc.resize((size_t)o.n * k.d);
+  for (uint32_t i = 0; i < o.n; i++) {
+    memcpy(o.head.data() + (size_t)i * 6, k.head.data() + (size_t)rows[i] * 6, 6 * sizeof(float));
+    if (k.d) memcpy(o.desc.data() + (size_t)i * k.d, k.desc.data() + (size_t)rows[i] * k.d, k.d * sizeof(float));
+  }
+  k = std::move(o);
+}
+
+void filter_z(KeypointSet& k, float zT, float zmin, float zmax) {
+  std::vector<uint32_t> rows;
+  rows.reserve(k.n);
+  for (uint32_t i = 0; i < k.n; i++) {
+    float z = k.row_head(i)[2] + zT;  // match.cpp:542
+    if (!(z < zmin || z > zmax)) rows.push_back(i);
+  }
+  if (rows.size() != k.n) keep_rows(k, rows);
+}
+
+namespace {
+struct RespIdx {
+  float response;
+  uint32_t idx;
+};
+// match.cpp:338 compareCSVrow: by-value compare on response, descending
+bool by_response_desc(RespIdx i, RespIdx j) { return i.response > j.response; }
+}  // namespace
+
+void prune(KeypointSet& k, float sp, int np) {
+  std::vector<RespIdx> v;
+  v.reserve(k.n);
+  for (uint32_t i = 0; i < k.n; i++) {
+    float resp = k.row_head(i)[5];
+    if (!(resp < sp)) v.push_back(RespIdx{resp, i});  // remove_if(response < sp), match.cpp:585-589
+  }
+  bool changed = v.size() != k.n;
+  if (np >= 0 && v.size() > (size_t)np) {  // match.cpp:592-594
+    std::partial_sort(v.begin(), v.begin() + np, v.end(), by_response_desc);
+    v.resize((size_t)np);
+    changed = true;
+  }
+  if (changed) {
+    std::vector<uint32_t> rows(v.size());
+    for (size_t i = 0; i < v.size(); i++) rows[i] = v[i].idx;
+    keep_rows(k, rows);
+  }
+}
+
+bool write_pairs_bin(const std::string& path, const std::vector<std::string>& filenames,
+                     const std::vector<std::array<double, 3>>& rigids, const std::vector<KeypointSet>& images,
+                     const std::vector<PairBlock>& blocks) {
+  FILE* file = fopen(path.c_str(), "wb");
+  if (!file) return false;
+  static char iobuf[1 << 22];
+  setvbuf(file, iobuf, _IOFBF, sizeof iobuf);
+  unsigned short nbAcq = (unsigned short)filenames.size();  // match.cpp:684
+  fwrite(&nbAcq, sizeof nbAcq, 1, file);
+  for (size_t it = 0; it < images.size(); it++) {
+    size_t found = filenames[it].find_last_of("/\\");  // match.cpp:690-694
+    std::string cur = filenames[it].substr(found + 1);
+    unsigned short len = (unsigned short)cur.size();
+    fwrite(&len, sizeof len, 1, file);
+    fwrite(cur.c_str(), 1, cur.size(), file);
+    std::array<double, 3> tmp = {0.0, 0.0, 0.0};  // match.cpp:697-708
+    if (!rigids.empty()) tmp = rigids[it];
+    fwrite(tmp.data(), sizeof(double), 3, file);
+    uint32_t nbPoints = images[it].n;  // pointIdType = unsigned int (INT_PTIDS), match.cpp:711-713
+    fwrite(&nbPoints, sizeof nbPoints, 1, file);
+    if (nbPoints) fwrite(images[it].head.data(), sizeof(float), (size_t)nbPoints * 6, file);  // :715-723
+  }
+  for (const PairBlock& b : blocks) {  // match.cpp:727-742
+    fwrite(&b.first, sizeof(unsigned short), 1, file);
+    fwrite(&b.second, sizeof(unsigned short), 1, file);
+    unsigned int size = b.count;
+    fwrite(&size, sizeof size, 1, file);
+    if (size) fwrite(b.pairs, 8, size, file);
+  }
+  fclose(file);
+  return true;
+}
+
+}  // namespace fmio

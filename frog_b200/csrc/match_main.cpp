@@ -1,0 +1,338 @@
+// match_main.cpp -- drop-in replacement for valette/FROG's `bin/match` (match/match.cpp:340-747).
+//
+//   match <listfile-or-directory> [-o out] [-d dist] [-d2 ratio] [-n N] [-sp thr] [-np n] [-nt threads]
+//         [-zmin z] [-zmax z] [-sym] [-targ k]            (reference keys, same meaning)
+//         [-gpus G] [-exact 1] [-stats file.json]         (new keys; unknown to the reference)
+//
+// Same argv quirks (every key consumes two tokens except -sym, match.cpp:365-431), same keypoint
+// readers, same stdout protocol, byte-identical pairs.bin.  The pairing phase (match.cpp:638-652)
+// runs on B200s through the C ABI of libfrogmatch.so; there is no CPU fallback.
+#include <omp.h>
+
+#include <algorithm>
+#include <array>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <filesystem>
+#include <fstream>
+#include <iostream>
+#include <numeric>
+#include <sstream>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "frogmatch.h"
+#include "keypoint_io.h"
+
+namespace fs = std::filesystem;
+using std::cerr;
+using std::cout;
+using std::endl;
+using std::string;
+
+namespace {
+
+struct GpuJob {
+  int device = 0;
+  std::vector<size_t> pair_ids;  // indices into the global pair list
+  fm_ctx* ctx = nullptr;
+  fm_result* res = nullptr;
+  fm_stats stats{};
+  string error;
+};
+
+void run_gpu_job(GpuJob& job, const std::vector<fmio::KeypointSet>& images, const std::vector<std::pair<int, int>>& indices,
+                 float dist, float ratio, uint32_t flags) {
+  if (fm_create(job.device, &job.ctx) != FM_OK) { job.error = fm_last_error(nullptr); return; }
+  std::vector<char> needed(images.size(), 0);
+  for (size_t id : job.pair_ids) { needed[indices[id].first] = 1; needed[indices[id].second] = 1; }
+  for (size_t i = 0; i < images.size(); i++) {
+    if (!needed[i]) continue;
+    const fmio::KeypointSet& k = images[i];
+    std::vector<float> scale(k.n), lap(k.n);
+    for (uint32_t r = 0; r < k.n; r++) { scale[r] = k.row_head(r)[3]; lap[r] = k.row_head(r)[4]; }
+    const uint32_t d = k.d ? k.d : 48;
+    if (fm_upload_image(job.ctx, (uint32_t)i, k.desc.data(), scale.data(), lap.data(), k.n, d) != FM_OK ||
+        fm_synchronize(job.ctx) != FM_OK) {  // scale/lap are temporaries: finish the copy before they die
+      job.error = fm_last_error(job.ctx);
+      return;
+    }
+  }
+  std::vector<uint32_t> pf(job.pair_ids.size()), ps(job.pair_ids.size());
+  for (size_t k = 0; k < job.pair_ids.size(); k++) {
+    pf[k] = (uint32_t)indices[job.pair_ids[k]].first;
+    ps[k] = (uint32_t)indices[job.pair_ids[k]].second;
+  }
+  if (fm_match(job.ctx, pf.data(), ps.data(), pf.size(), dist, ratio, flags, &job.res) != FM_OK) {
+    job.error = fm_last_error(job.ctx);
+    return;
+  }
+  fm_get_stats(job.ctx, &job.stats);
+}
+
+}  // namespace
+
+int main(int argc, char* argv[]) {
+  std::chrono::time_point<std::chrono::system_clock> start, end;
+  int N = 1000000;
+  float sp = 0;
+  int np = 1000000;
+  int nt = (int)std::thread::hardware_concurrency();
+  if (argc < 2) {
+    cout << "Usage : match pointFiles.txt [options] " << endl;  // match.cpp:347-350
+    return 1;
+  }
+  fs::path full_path = fs::absolute(fs::path(argv[1]));
+  float dist = 0.22f;  // match.cpp:352 `float dist = 0.22`
+  float dist2second = 1;
+  float zmin = -1e20f, zmax = 1e20f;
+  bool matchAll = false, writePoints = false, symFlag = false, forceExact = false;
+  char* outputFileName = nullptr;
+  float anatVal = 0.0f;
+  int target = -1;
+  int gpus = -1;
+  const char* statsFile = nullptr;
+
+  // match.cpp:365-431: key = argv[k], value = argv[k+1]; advance by 2, by 1 for -sym.
+  for (int k = 2; k < argc;) {
+    const char* key = argv[k];
+    const char* value = (k + 1 < argc) ? argv[k + 1] : nullptr;
+    auto has = [&](const char* name) { return strcmp(key, name) == 0; };
+    if (value) {
+      if (has("-n")) N = atoi(value);
+      if (has("-sp")) sp = (float)atof(value);
+      if (has("-np")) np = atoi(value);
+      if (has("-nt")) nt = atoi(value);
+      if (has("-d")) dist = (float)atof(value);
+      if (has("-d2")) dist2second = (float)atof(value);
+      if (has("-zmin")) zmin = (float)atof(value);
+      if (has("-zmax")) zmax = (float)atof(value);
+      if (has("-o")) outputFileName = argv[k + 1];
+      if (has("-anat")) anatVal = (float)atof(value);
+      if (has("-targ")) target = atoi(value);
+      if (has("-gpus")) gpus = atoi(value);
+      if (has("-exact")) forceExact = atoi(value) != 0;
+      if (has("-stats")) statsFile = value;
+    }
+    if (has("-all")) matchAll = true;
+    if (has("-p")) writePoints = true;
+    if (has("-sym")) { symFlag = true; k -= 1; }
+    k += 2;
+  }
+  if (matchAll) {
+    cerr << "match: -all is not supported by the B200 build (the reference emits stale column ids in this "
+            "mode, match.cpp:295-300)" << endl;
+    return 1;
+  }
+  if (anatVal != 0.0f) {
+    cerr << "match: -anat is not supported (the reference reads uninitialised transformedCoordinates, "
+            "match.cpp:548-559)" << endl;
+    return 1;
+  }
+  if (writePoints) cerr << "match: -p (debug CSV dump) is ignored by the B200 build" << endl;
+
+  std::vector<std::array<double, 3>> rigids;
+  std::vector<string> filenames;
+  if (fs::is_directory(full_path)) {  // match.cpp:439-452
+    for (fs::directory_iterator it(full_path), e; it != e; ++it)
+      if (fs::is_regular_file(it->status())) filenames.push_back(it->path().native());
+  } else if (fs::is_regular_file(full_path)) {  // match.cpp:454-492
+    std::ifstream file(full_path.native());
+    string line;
+    while (std::getline(file, line)) {
+      std::stringstream lineStream(line);
+      string cell;
+      std::getline(lineStream, cell, ',');
+      if (cell.find("/") == 0) {
+        filenames.push_back(cell);
+        cout << cell << endl;
+      } else {
+        filenames.push_back(full_path.parent_path().native() + "/" + cell + ".csv");
+        cout << full_path.parent_path().native() + cell << endl;
+      }
+      std::array<double, 3> point = {0, 0, 0};
+      try {
+        std::getline(lineStream, cell, ',');
+        point[0] = std::stof(cell);
+        std::getline(lineStream, cell, ',');
+        point[1] = std::stof(cell);
+        std::getline(lineStream, cell, ',');
+        point[2] = std::stof(cell);
+      } catch (...) {
+      }
+      rigids.push_back(point);
+    }
+  } else {
+    cerr << "Bad argument, first arg must be a valid file or a directory" << endl;  // match.cpp:496
+    return 1;
+  }
+
+  cout << "Found " << filenames.size() << " files, loading : " << fmin(N, filenames.size()) << endl;
+  start = std::chrono::system_clock::now();
+  if (filenames.size() > (size_t)N) filenames.resize(N);
+  if (nt > 0) omp_set_num_threads(nt);
+  int nb = (int)filenames.size();
+  if (nb > 65535) { cerr << "match: more than 65535 images cannot be described by pairs.bin (u16 ids)" << endl; return 1; }
+  std::vector<fmio::KeypointSet> images(nb);
+  int load_failed = 0;
+
+#pragma omp parallel for schedule(dynamic)
+  for (int it = 0; it < nb; ++it) {  // match.cpp:508-570
+    string err;
+    if (!fmio::read_keypoints(filenames[it], images[it], err)) {
+#pragma omp critical
+      { cerr << err << " (" << filenames[it] << ")" << endl; load_failed = 1; }
+      continue;
+    }
+    const uint32_t before = images[it].n;
+    float zT = rigids.size() ? (float)rigids[it][2] : 0;
+    fmio::filter_z(images[it], zT, zmin, zmax);
+    std::array<double, 3> rg = rigids.size() ? rigids[it] : std::array<double, 3>{0, 0, 0};
+#pragma omp critical
+    cout << "image " << it << " rigid : " << rg[0] << ", " << rg[1] << ", " << rg[2] << " before : " << images[it].n
+         << " points, after : " << images[it].n << endl << std::flush;  // the reference prints the post-filter size twice
+    (void)before;
+  }
+  if (load_failed) return 1;
+  if (nb == 0) { cerr << "match: no keypoint files" << endl; return 1; }
+
+  end = std::chrono::system_clock::now();
+  cout << " : " << std::chrono::duration<float>(end - start).count() << "s" << endl;
+  start = end;
+  cout << (images[0].n ? images[0].d : 0) << " values per descriptor" << endl;  // match.cpp:575
+  cout << "Sorting and pruning..." << endl;
+
+#pragma omp parallel for schedule(dynamic)
+  for (int it = 0; it < nb; ++it) {  // match.cpp:579-609
+    fmio::prune(images[it], sp, np);
+#pragma omp critical
+    cout << ". (" << images[it].n << ")" << std::flush;
+  }
+  end = std::chrono::system_clock::now();
+  cout << " : " << std::chrono::duration<float>(end - start).count() << "s" << endl;
+  start = end;
+
+  uint32_t dim = 0;
+  for (auto& k : images)
+    if (k.n) {
+      if (dim == 0) dim = k.d;
+      if (k.d != dim) { cerr << "match: images disagree on the descriptor length" << endl; return 1; }
+    }
+
+  // match.cpp:617-628
+  std::vector<std::pair<int, int>> indices;
+  for (int i = 0; i < nb - 1; i++) {
+    if (target >= 0) {
+      if (i != target) indices.push_back(std::make_pair(i, target));
+    } else {
+      for (int j = i + 1; j < nb; j++) indices.push_back(std::make_pair(i, j));
+    }
+  }
+  if (target >= nb) { cerr << "match: -targ " << target << " is not a valid image index" << endl; return 1; }
+
+  cout << "Pairing... " << endl;
+  int n_dev = 0;
+  if (fm_device_count(&n_dev) != FM_OK || n_dev == 0) {
+    cerr << "match: no CUDA device available (" << fm_last_error(nullptr) << "); this build has no CPU path" << endl;
+    return 1;
+  }
+  int G = gpus > 0 ? std::min(gpus, n_dev) : n_dev;
+  G = std::max(1, std::min<int>(G, std::max<size_t>(indices.size(), 1)));
+  std::vector<GpuJob> jobs(G);
+  {
+    // longest-processing-time-first sharding of image pairs (independent units, match.cpp:638-652)
+    std::vector<size_t> order(indices.size());
+    std::iota(order.begin(), order.end(), 0);
+    auto weight = [&](size_t id) { return (double)images[indices[id].first].n * (double)images[indices[id].second].n; };
+    std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return weight(a) > weight(b); });
+    std::vector<double> load(G, 0.0);
+    for (size_t id : order) {
+      int g = (int)(std::min_element(load.begin(), load.end()) - load.begin());
+      jobs[g].pair_ids.push_back(id);
+      load[g] += weight(id);
+    }
+    for (int g = 0; g < G; g++) {
+      jobs[g].device = g;
+      std::sort(jobs[g].pair_ids.begin(), jobs[g].pair_ids.end());  // consecutive pairs share the first image
+    }
+  }
+  const uint32_t flags = (symFlag ? FM_FLAG_SYM : 0u) | (forceExact ? FM_FLAG_FORCE_EXACT : 0u);
+  {
+    std::vector<std::thread> threads;
+    for (int g = 1; g < G; g++)
+      threads.emplace_back(run_gpu_job, std::ref(jobs[g]), std::cref(images), std::cref(indices), dist, dist2second, flags);
+    run_gpu_job(jobs[0], images, indices, dist, dist2second, flags);
+    for (auto& t : threads) t.join();
+  }
+  for (auto& j : jobs)
+    if (!j.error.empty()) { cerr << "match: GPU " << j.device << ": " << j.error << endl; return 1; }
+
+  // gather: per pair, where its list lives
+  std::vector<fmio::PairBlock> by_pair(indices.size());
+  long long sum = 0;
+  for (auto& j : jobs)
+    for (size_t k = 0; k < j.pair_ids.size(); k++) {
+      const size_t id = j.pair_ids[k];
+      fmio::PairBlock b;
+      b.first = indices[id].first;
+      b.second = indices[id].second;
+      b.count = fm_result_count(j.res, k);
+      b.pairs = fm_result_pairs(j.res, k);
+      by_pair[id] = b;
+      sum += b.count;
+      cout << "." << std::flush;  // match.cpp:650
+    }
+  end = std::chrono::system_clock::now();
+  const float pairing_s = std::chrono::duration<float>(end - start).count();
+  cout << " : " << pairing_s << "s" << endl;
+  start = end;
+  cout << "Nb Match : " << (int)sum << endl;  // `int sum`, match.cpp:615,658
+
+  // match.cpp:660-673
+  std::stringstream outfilename;
+  if (outputFileName) outfilename << string(outputFileName);
+  else outfilename << "out_" << full_path.stem().string() << "_" << filenames.size() << ".bin";
+
+  // match.cpp:727-742 walks pairs[i][j] row-major over a matrix in which a later store to the same
+  // cell replaces an earlier one (only possible with -targ); reproduce that order.
+  std::vector<size_t> order(indices.size());
+  std::iota(order.begin(), order.end(), 0);
+  std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return indices[a] < indices[b]; });
+  std::vector<fmio::PairBlock> blocks;
+  blocks.reserve(order.size());
+  for (size_t id : order) blocks.push_back(by_pair[id]);
+
+  if (!fmio::write_pairs_bin(outfilename.str(), filenames, rigids, images, blocks)) {
+    cout << "write error : " << outfilename.str() << endl;  // match.cpp:677-682
+    exit(1);
+  }
+  cout << "Output file : " << outfilename.str() << endl;
+
+  if (statsFile) {
+    fm_stats tot{};
+    float ms_max = 0;
+    for (auto& j : jobs) {
+      tot.descriptor_pairs += j.stats.descriptor_pairs;
+      tot.scored_pairs += j.stats.scored_pairs;
+      tot.rows += j.stats.rows;
+      tot.rows_exact += j.stats.rows_exact;
+      tot.candidates += j.stats.candidates;
+      tot.kernel_launches += j.stats.kernel_launches;
+      ms_max = std::max(ms_max, j.stats.ms_total);
+    }
+    std::ofstream sf(statsFile);
+    sf << "{\"gpus\": " << G << ", \"image_pairs\": " << indices.size() << ", \"descriptor_pairs\": " << tot.descriptor_pairs
+       << ", \"scored_pairs\": " << tot.scored_pairs << ", \"rows\": " << tot.rows << ", \"rows_exact\": " << tot.rows_exact
+       << ", \"candidates\": " << tot.candidates << ", \"kernel_launches\": " << tot.kernel_launches
+       << ", \"gpu_ms_max\": " << ms_max << ", \"pairing_s\": " << pairing_s << ", \"matches\": " << sum << "}" << endl;
+  }
+  for (auto& j : jobs) {
+    fm_result_free(j.res);
+    fm_destroy(j.ctx);
+  }
+  return 0;
+}
