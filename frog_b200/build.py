@@ -15,6 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "frog_b200", "csrc")
 LIB = os.path.join(ROOT, "frog_b200", "libfrogmatch.so")
 BIN = os.path.join(ROOT, "bin", "match")
+FMIO = os.path.join(ROOT, "frog_b200", "libfmio.so")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -58,9 +59,21 @@ def build_cli(force: bool = False) -> str:
     return BIN
 
 
+def build_fmio(force: bool = False) -> str:
+    """Host-side readers / pruning / pairs.bin writer as a small C library (no CUDA)."""
+    srcs = _sources((".cpp", ".h"))
+    if not force and _newer(FMIO, srcs):
+        return FMIO
+    cmd = ["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-I", os.path.join(ROOT, "include"),
+           os.path.join(CSRC, "fmio_capi.cpp"), os.path.join(CSRC, "keypoint_io.cpp"), "-o", FMIO, "-lz"]
+    subprocess.run(cmd, check=True, cwd=ROOT)
+    return FMIO
+
+
 def build_all(force: bool = False) -> None:
     build_lib(force)
     build_cli(force)
+    build_fmio(force)
 
 
 if __name__ == "__main__":

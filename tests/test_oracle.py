@@ -1,0 +1,112 @@
+"""CPU: the three statements of the reference hot path pin each other, and the golden pairs.bin
+files written by the unmodified reference binary pin all of them (oracle parity = PINNED)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import helpers
+from frog_b200 import pairsbin, synth
+from oracle import oracle as O
+
+CASES = sorted(json.load(open(os.path.join(os.path.dirname(__file__), "golden", "manifest.json"))).items())
+
+
+@pytest.fixture(scope="module")
+def libs(built):
+    port = O.PortLib()
+    ref = O.RefLib() if os.path.exists(O.REF_LIB) else None
+    return port, ref
+
+
+PARAMS = [(0.22, 1.0, False), (1.0, 0.8, False), (1e10, 1.0, False), (0.5, 0.998, True), (1.0, 1.01, False)]
+
+
+@pytest.mark.parametrize("kind", ["bank", "iid"])
+def test_numpy_port_reference_agree(libs, kind):
+    port, ref = libs
+    a, b = synth.make(kind, 310, 0), synth.make(kind, 257, 1)
+    fa, fb = (a.desc, a.scale, a.lap), (b.desc, b.scale, b.lap)
+    for thr, rat, sym in PARAMS:
+        p = port.compute_matches(fa, fb, thr, rat, sym)
+        n = O.compute_matches_numpy(fa, fb, thr, rat, sym)
+        assert np.array_equal(p, n)
+        if ref is not None:
+            assert np.array_equal(ref.compute_matches(fa, fb, thr, rat, sym), p)
+
+
+def test_norm_is_sequential_fp32(libs):
+    port, ref = libs
+    rng = np.random.default_rng(3)
+    a = rng.standard_normal(48).astype(np.float32)
+    b = rng.standard_normal(48).astype(np.float32)
+    acc = np.float32(0)
+    for k in range(48):
+        d = np.float32(a[k] - b[k])
+        acc = np.float32(acc + np.float32(d * d))
+    assert port.norm(a, b) == acc
+    assert O.norm_matrix_numpy(a[None], b[None])[0, 0] == acc
+    if ref is not None:
+        assert ref.norm(a, b) == acc
+
+
+def test_known_answers(libs):
+    """Edge cases of match.cpp:264-330 (SURVEY.md 8c KAT list)."""
+    port, _ = libs
+    e = np.eye(48, dtype=np.float32)
+    one = np.ones(1, np.float32)
+
+    def cm(first, second, thr=1.0, rat=1.0):
+        return port.compute_matches(first, second, thr, rat).tolist()
+
+    row = (0.6 * e[:1] + 0.0, one, one * 0)
+    # single surviving column: d2 stays FLT_MAX -> ratio test bypassed (match.cpp:320)
+    assert cm((e[:1] * 0.5, one, one * 0), row) == [[0, 0]]
+    # laplacian mismatch (match.cpp:270) and scale ratio beyond 1.3 (match.cpp:273-275)
+    assert cm((e[:1] * 0.5, one, one * 1), row) == []
+    assert cm((e[:1] * 0.5, one * 1.31, one * 0), row) == []
+    # scale ratio exactly representable at the boundary: 1.3f/1 == 1.3f is NOT > 1.3 (double)
+    assert cm((e[:1] * 0.5, one * np.float32(1.3), one * 0), row) == [[0, 0]]
+    assert cm((e[:1] * 0.5, one * np.nextafter(np.float32(1.3), np.float32(2)), one * 0), row) == []
+    # exact tie d1 == d2: rejected at -d2 1, accepted at -d2 1.01; lowest column index wins
+    two = (np.stack([e[1] * 0.5, e[2] * 0.5]), np.ones(2, np.float32), np.zeros(2, np.float32))
+    assert cm(two, row, rat=1.0) == []
+    assert cm(two, row, rat=1.01) == [[0, 0]]
+    # duplicate of the row itself twice: d1 = d2 = 0 -> sqrt(0/0) is NaN -> rejected even at 1.01
+    dup = (np.stack([row[0][0], row[0][0]]), np.ones(2, np.float32), np.zeros(2, np.float32))
+    assert cm(dup, row, rat=1.01) == []
+    # no surviving column: d1 = FLT_MAX, sqrt(FLT_MAX) = 1.8e19 > 1e10 -> no emit (FROG.py's -d)
+    assert cm((e[:1] * 0.5, one, one * 1), row, thr=1e10) == []
+    # distance threshold is strict: sqrt(d1) < thr
+    d = float(np.sqrt(O.norm_matrix_numpy(row[0], e[:1] * 0.5)[0, 0]))
+    assert cm((e[:1] * 0.5, one, one * 0), row, thr=d) == []
+    assert cm((e[:1] * 0.5, one, one * 0), row, thr=float(np.nextafter(np.float32(d), np.float32(9)))) == [[0, 0]]
+
+
+@pytest.mark.parametrize("name,case", CASES)
+def test_golden_pairs_bin(libs, golden_dir, tmp_path, name, case):
+    """host readers/pruning/writer (the C++ bin/match runs) + oracle port == reference bytes."""
+    port, _ = libs
+    opts = helpers.parse_args(case["args"])
+    filenames, rigids, heads, descs = helpers.load_group(os.path.join(golden_dir, case["list"]), opts)
+    sched = helpers.pair_schedule(len(filenames), opts["target"])
+    lists = port.match_pairs(helpers.images_of(heads, descs), [s[0] for s in sched], [s[1] for s in sched],
+                             opts["dist"], opts["ratio"], opts["sym"])
+    assert sum(len(l) for l in lists) == case["nb_match"]
+    out = str(tmp_path / "pairs.bin")
+    helpers.write_pairs(out, filenames, rigids, heads, sched, lists)
+    golden = open(os.path.join(golden_dir, name + ".pairs.bin"), "rb").read()
+    mine = open(out, "rb").read()
+    if mine != golden:
+        d = pairsbin.diff(pairsbin.parse(golden), pairsbin.parse(mine))
+        pytest.fail(f"pairs.bin differs from the reference: {d}")
+
+
+def test_reference_binary_regenerates_golden(golden_dir, tmp_path, built):
+    """Where the reference binary exists, it must still reproduce a committed fixture."""
+    if not os.path.exists(O.REF_BIN):
+        pytest.skip("oracle/_ref/match_ref not built here")
+    out = str(tmp_path / "o.bin")
+    O.run_ref_binary([os.path.join(golden_dir, "list_bin.txt"), "-o", out, "-d", "1", "-d2", "0.8"])
+    assert open(out, "rb").read() == open(os.path.join(golden_dir, "bin_ratio.pairs.bin"), "rb").read()
