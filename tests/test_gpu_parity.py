@@ -1,0 +1,179 @@
+"""GPU: libfrogmatch (through the C ABI) against the oracle on seeded inputs -- bit-exact."""
+import numpy as np
+import pytest
+
+import helpers
+from frog_b200 import capi, synth
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def env(built):
+    m = capi.Matcher(0)
+    yield m, O.PortLib()
+    m.close()
+
+
+def run_both(m, port, images, pf, ps, thr, rat, sym=False, engines=(False, True)):
+    want = port.match_pairs(images, pf, ps, thr, rat, sym)
+    m.clear()
+    for i, (d, s, l) in enumerate(images):
+        m.upload(i, d, s, l)
+    stats = {}
+    for force_exact in engines:
+        res = m.match(pf, ps, thr, rat, sym=sym, force_exact=force_exact)
+        got = res.all_pairs()
+        stats[force_exact] = m.stats()
+        res.free()
+        assert len(got) == len(want)
+        for p, (g, w) in enumerate(zip(got, want)):
+            assert np.array_equal(g, w), f"pair {p} engine={'exact' if force_exact else 'tensor'}: {len(g)} vs {len(w)}"
+    return stats
+
+
+PARAMS = [(0.22, 1.0), (1.0, 1.0), (1.0, 0.8), (1e10, 1.0), (0.5, 0.998), (1.0, 1.01)]
+
+
+@pytest.mark.parametrize("kind", ["bank", "iid"])
+@pytest.mark.parametrize("thr,rat", PARAMS)
+def test_group_parity(env, kind, thr, rat):
+    m, port = env
+    images = helpers.random_group(kind, 4, 1100)
+    images[2] = tuple(x[:777] for x in images[2])  # ragged sizes, not multiples of any tile
+    sched = helpers.pair_schedule(4, -1)
+    st = run_both(m, port, images, [s[0] for s in sched], [s[1] for s in sched], thr, rat)
+    assert st[False]["score_launches"] >= 1 and st[False]["scored_pairs"] > 0  # the tensor path really ran
+    assert st[False]["rows_exact"] < 0.02 * st[False]["rows"]
+
+
+def test_sym_and_repeated_pairs(env):
+    m, port = env
+    images = helpers.random_group("bank", 3, 900)
+    run_both(m, port, images, [0, 0, 2, 1, 1], [1, 1, 0, 2, 1], 1.0, 0.9, sym=True)
+
+
+def test_sizes_edge(env):
+    m, port = env
+    base = helpers.random_group("bank", 1, 600)[0]
+    images = [base, tuple(x[:1] for x in base), tuple(x[:0] for x in base), tuple(x[:256] for x in base),
+              tuple(x[:257] for x in base), tuple(x[:128] for x in base)]
+    sched = [(i, j) for i in range(6) for j in range(6) if i != j]
+    run_both(m, port, images, [s[0] for s in sched], [s[1] for s in sched], 1.0, 1.0)
+
+
+def test_known_answers_on_gpu(env):
+    m, port = env
+    e = np.eye(48, dtype=np.float32)
+    o = np.ones
+    row = (0.6 * e[:1], o(1, np.float32), np.zeros(1, np.float32))
+    cases = [
+        (e[:1] * 0.5, o(1), np.zeros(1)),
+        (e[:1] * 0.5, o(1), o(1)),
+        (e[:1] * 0.5, o(1) * 1.31, np.zeros(1)),
+        (e[:1] * 0.5, o(1) * np.float32(1.3), np.zeros(1)),
+        (e[:1] * 0.5, o(1) * np.nextafter(np.float32(1.3), np.float32(2)), np.zeros(1)),
+        (np.stack([e[1] * 0.5, e[2] * 0.5]), o(2), np.zeros(2)),
+        (np.stack([row[0][0], row[0][0]]), o(2), np.zeros(2)),
+        (np.stack([row[0][0], e[3], row[0][0] * 0.999]), o(3), np.zeros(3)),
+    ]
+    images = [row] + [tuple(np.asarray(x, np.float32) for x in c) for c in cases]
+    pf = list(range(1, len(images)))
+    ps = [0] * len(pf)
+    for thr, rat in [(1.0, 1.0), (1.0, 1.01), (1e10, 1.0), (0.1, 1.0), (1.0, 0.5)]:
+        run_both(m, port, images, pf, ps, thr, rat)
+        run_both(m, port, images, ps, pf, thr, rat)
+
+
+def test_many_duplicates_overflow_to_exact_rows(env):
+    """Rows with more than 4 near-tied candidates cannot be certified from the top-4 list: they
+    must be redone by the exact row kernel and still come out identical."""
+    m, port = env
+    a, b = helpers.random_group("iid", 2, 800)
+    ad = a[0].copy()
+    ad[100:140] = ad[100]  # 40 identical columns
+    bd = b[0].copy()
+    bd[:50] = ad[100] * np.float32(0.999)
+    images = [(ad, np.full(800, 1.5, np.float32), np.zeros(800, np.float32)),
+              (bd, np.full(800, 1.6, np.float32), np.zeros(800, np.float32))]
+    for thr, rat in [(1.0, 1.0), (1.0, 1.01)]:
+        st = run_both(m, port, images, [0], [1], thr, rat)
+        assert st[False]["rows_exact"] >= 50
+
+
+def test_uncertified_images_route_to_exact(env):
+    m, port = env
+    base = helpers.random_group("bank", 4, 500)
+    nan_img = (base[1][0].copy(), base[1][1].copy(), base[1][2].copy())
+    nan_img[0][7, 3] = np.nan
+    neg_scale = (base[2][0], base[2][1].copy(), base[2][2])
+    neg_scale[1][11] = -1.0
+    big = (base[3][0] * np.float32(9.0), base[3][1], base[3][2])
+    laps = (base[0][0], base[0][1], (np.arange(500) % 11).astype(np.float32))
+    phantom = (np.concatenate([base[0][0], np.zeros((1, 48), np.float32)]),
+               np.concatenate([base[0][1], [np.float32(321.5)]]).astype(np.float32),
+               np.concatenate([base[0][2], [np.float32(321.5)]]).astype(np.float32))
+    images = [base[0], nan_img, neg_scale, big, laps, phantom]
+    sched = helpers.pair_schedule(6, -1)
+    st = run_both(m, port, images, [s[0] for s in sched], [s[1] for s in sched], 1.0, 1.0)
+    assert st[False]["rows_exact"] > 0
+
+
+def test_other_descriptor_lengths(env):
+    """d != 48 (surf3d descriptor types 1/2, vtkOpenSURF3D/surf3d.cxx:36-39) runs on the generic exact kernel."""
+    m, port = env
+    rng = np.random.default_rng(5)
+    for d in (24, 64, 192):
+        images = []
+        for i in range(3):
+            x = rng.standard_normal((300 + 7 * i, d)).astype(np.float32)
+            x /= np.linalg.norm(x, axis=1, keepdims=True)
+            images.append((x, rng.uniform(1, 2, x.shape[0]).astype(np.float32), rng.integers(0, 2, x.shape[0]).astype(np.float32)))
+        run_both(m, port, images, [0, 0, 1], [1, 2, 2], 1.2, 0.95, engines=(False,))
+
+
+def test_api_errors(env):
+    m, _ = env
+    m.clear()
+    d, s, l = helpers.random_group("iid", 1, 10)[0]
+    m.upload(0, d, s, l)
+    with pytest.raises(capi.FrogMatchError):
+        m.match([0], [3])  # image 3 was never uploaded
+    with pytest.raises(capi.FrogMatchError):
+        m.match([0], [0], dist=3e19)  # would need the reference's stale-index leak (match.cpp:320-321)
+    with pytest.raises(capi.FrogMatchError):
+        m.upload(1, d[:, :24], s, l)  # mixed descriptor lengths
+
+
+def test_full_size_engines_agree(env):
+    """BASELINE config 2 scale (10 x 20k, iid): tensor-core path == exact CUDA path on every pair,
+    and sampled pairs == oracle."""
+    m, port = env
+    n_img, n_pts = 10, 20000
+    kps = [synth.make("iid", n_pts, i) for i in range(n_img)]
+    m.clear()
+    for i, k in enumerate(kps):
+        m.upload(i, k.desc, k.scale, k.lap)
+    sched = helpers.pair_schedule(n_img, -1)
+    pf, ps = [s[0] for s in sched], [s[1] for s in sched]
+    for thr, rat in [(1.0, 1.0), (1.0, 0.8)]:
+        fast = m.match(pf, ps, thr, rat)
+        lf = fast.all_pairs()
+        st = m.stats()
+        fast.free()
+        ex = m.match(pf[:6], ps[:6], thr, rat, force_exact=True)
+        le = ex.all_pairs()
+        ex.free()
+        for p in range(6):
+            assert np.array_equal(lf[p], le[p])
+        assert st["descriptor_pairs"] == 45 * n_pts * n_pts
+        assert st["rows_exact"] < 0.02 * st["rows"]
+        # size-independent properties: one match per row at most, sorted by second index, ids in range
+        for l in lf:
+            assert np.all(np.diff(l[:, 1].astype(np.int64)) > 0) and l[:, 0].max(initial=0) < n_pts
+    img = [(k.desc, k.scale, k.lap) for k in kps[:2]]
+    sub = (img[1][0][:1500], img[1][1][:1500], img[1][2][:1500])
+    want = port.compute_matches(img[0], sub, 1.0, 0.8)
+    got = lf[0][lf[0][:, 1] < 1500]
+    assert np.array_equal(got, want)
