@@ -26,6 +26,7 @@ struct ImageMeta {
   uint32_t flags;
   uint32_t n_classes;
   float max_norm2;                    // max squared L2 norm over the image's descriptors
+  float max_delta2;                   // max squared L2 norm of (fp16(desc) - desc): actual FP16 rounding residual
   float class_lap[kMaxClasses];       // laplacian value of each class, ascending bit pattern order
   uint32_t class_begin[kMaxClasses + 1];  // class c occupies sorted positions [begin[c], begin[c+1])
 };

@@ -1,6 +1,8 @@
 // fm_fast.cuh -- host-side driver of the tensor-core path: per-image preparation at upload and
 // the bands -> score -> rescore -> redo kernel sequence for one batch of tasks.
 #pragma once
+#include <cstdlib>
+
 #include "fm_host.h"
 #include "fm_prep.cuh"
 #include "fm_rescore.cuh"
@@ -121,6 +123,8 @@ inline cudaError_t fast_match_batch(fm_ctx* c, const FastBatchArgs& a) {
   if ((e = c->d_redo.ensure((size_t)a.rows * sizeof(uint2))) != cudaSuccess) return e;
   if (!c->score_attr_set) {
     if ((e = cudaFuncSetAttribute(score_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kScoreSmemBytes)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(score_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kScoreSmemBytes)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(score_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kScoreSmemBytes)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(score_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kScoreSmemBytes)) != cudaSuccess) return e;
     c->score_attr_set = true;
   }
@@ -130,7 +134,10 @@ inline cudaError_t fast_match_batch(fm_ctx* c, const FastBatchArgs& a) {
   }
   {
     Span sp(&c->ev_match, c->stream, kPhScore);
-    score_kernel<false><<<a.units, kScoreThreads, kScoreSmemBytes, c->stream>>>(
+    // FM_PROBE=1|2 selects a timing-attribution variant of the kernel (wrong results, see fm_score.cuh)
+    static const int probe = getenv("FM_PROBE") ? atoi(getenv("FM_PROBE")) : 0;
+    auto kern = probe == 1 ? score_kernel<false, 1> : probe == 2 ? score_kernel<false, 2> : score_kernel<false, 0>;
+    kern<<<a.units, kScoreThreads, kScoreSmemBytes, c->stream>>>(
         a.images, a.tasks, a.unit_off, a.n_tasks, a.segs, c->d_bands.as<uint2>(), c->d_cands.as<Cand>(),
         &a.counters->scored_cols, nullptr, 0, 0);
   }
@@ -139,7 +146,7 @@ inline cudaError_t fast_match_batch(fm_ctx* c, const FastBatchArgs& a) {
     rescore_kernel<<<a.blocks128, 128, 0, c->stream>>>(a.images, a.tasks, a.blk_off, a.n_tasks, a.segs,
                                                        c->d_cands.as<Cand>(), a.thr, a.ratio, a.rowres,
                                                        c->d_redo.as<uint2>(), &a.counters->rescore);
-    exact_rows_kernel<<<c->sm_count * 2, 256, 0, c->stream>>>(a.images, a.tasks, c->d_redo.as<uint2>(),
+    exact_rows_kernel<<<c->sm_count * 2, 256, 0, c->stream>>>(a.images, a.tasks, c->d_bands.as<uint2>(), c->d_redo.as<uint2>(),
                                                              &a.counters->rescore, a.thr, a.ratio, a.rowres);
     fold_redo_kernel<<<1, 1, 0, c->stream>>>(a.counters);
   }

@@ -34,13 +34,15 @@ prep_keys_kernel(const float* __restrict__ desc, const float* __restrict__ scale
                  uint32_t* __restrict__ idx, float* __restrict__ norm2) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t flags = 0;
-  float n2 = 0.f;
+  float n2 = 0.f, dl2 = 0.f;
   if (i < n) {
     const float* p = desc + (size_t)i * d;
     for (uint32_t k = 0; k < d; k++) {
       float v = __ldg(p + k);
       if (!isfinite(v)) flags |= kImgNotFinite;
       n2 = fmaf(v, v, n2);
+      const float r = __half2float(__float2half_rn(v)) - v;  // exact: the operand's FP16 rounding residual
+      dl2 = fmaf(r, r, dl2);
     }
     float s = scale[i], l = lap[i];
     if (!isfinite(s) || !isfinite(l)) flags |= kImgNotFinite;
@@ -53,14 +55,17 @@ prep_keys_kernel(const float* __restrict__ desc, const float* __restrict__ scale
   }
   // warp-aggregate then one atomic per warp
   float m = isfinite(n2) ? n2 : 0.f;
+  float md = isfinite(dl2) ? dl2 : 0.f;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    md = fmaxf(md, __shfl_xor_sync(0xffffffffu, md, o));
     flags |= __shfl_xor_sync(0xffffffffu, flags, o);
   }
   if ((threadIdx.x & 31) == 0) {
     if (flags) atomicOr(&meta->flags, flags);
-    atomicMax(reinterpret_cast<unsigned int*>(&meta->max_norm2), __float_as_uint(m));
+    atomicMax(reinterpret_cast<unsigned int*>(&meta->max_norm2), __float_as_uint(m));   // non-negative floats
+    atomicMax(reinterpret_cast<unsigned int*>(&meta->max_delta2), __float_as_uint(md));  // order like uints
   }
 }
 

@@ -58,7 +58,7 @@ rescore_kernel(const ImageDev* __restrict__ images, const Task* __restrict__ tas
   const uint32_t s = (blockIdx.x - task_blk_off[t]) * 128 + threadIdx.x;
   if (s >= B.n) return;
   const uint32_t row = B.perm[s];
-  const float eps = task_eps(A.meta->max_norm2, B.meta->max_norm2);
+  const float eps = task_eps(A.meta, B.meta);
 
   const uint32_t L = segs * kTopK;
   const Cand* c = cands + (size_t)(task.row_off + s) * L;
@@ -102,7 +102,7 @@ rescore_kernel(const ImageDev* __restrict__ images, const Task* __restrict__ tas
   rowres[task.row_off + row] = match;
   if (overflow) {
     unsigned long long slot = atomicAdd(&counters->redo_rows, 1ull);
-    redo_list[slot] = make_uint2(t, row);
+    redo_list[slot] = make_uint2(t, s);
   }
   // statistics: one atomic per warp
 #pragma unroll
@@ -110,12 +110,15 @@ rescore_kernel(const ImageDev* __restrict__ images, const Task* __restrict__ tas
   if ((threadIdx.x & 31) == 0 && n_eval) atomicAdd(&counters->candidates, (unsigned long long)n_eval);
 }
 
-// Brute-force redo of queued rows: one warp per row, lanes stride over the columns in original
-// order, per-lane sequential top-2, then a multiset merge across lanes.
+// Exact redo of queued rows: one warp per row.  Lanes stride over the row's gate interval
+// [lo, hi) of sorted columns (every column outside it fails a reference gate, fm_score.cuh
+// bands_kernel), evaluate the reference's gates and FP32 distance on each, keep an
+// order-independent (d1, lowest original index, d2) and merge across lanes as multisets.
 __global__ void __launch_bounds__(256)
 exact_rows_kernel(const ImageDev* __restrict__ images, const Task* __restrict__ tasks,
-                  const uint2* __restrict__ redo_list, const RescoreCounters* __restrict__ counters, float thr,
-                  float ratio, uint32_t* __restrict__ rowres) {
+                  const uint2* __restrict__ bands, const uint2* __restrict__ redo_list,
+                  const RescoreCounters* __restrict__ counters, float thr, float ratio,
+                  uint32_t* __restrict__ rowres) {
   const uint32_t lane = threadIdx.x & 31;
   const unsigned long long n = counters->redo_rows;
   const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
@@ -124,7 +127,8 @@ exact_rows_kernel(const ImageDev* __restrict__ images, const Task* __restrict__ 
     const Task task = tasks[item.x];
     const ImageDev A = images[task.col_img];
     const ImageDev B = images[task.row_img];
-    const uint32_t row = item.y;
+    const uint32_t row = B.perm[item.y];
+    const uint2 band = bands[task.row_off + item.y];
     float r[kD];
     const float4* src = reinterpret_cast<const float4*>(B.desc + (size_t)row * kD);
 #pragma unroll
@@ -135,11 +139,12 @@ exact_rows_kernel(const ImageDev* __restrict__ images, const Task* __restrict__ 
     const float sc = B.scale[row], lp = B.lap[row];
     float d1 = FLT_MAX, d2 = FLT_MAX;
     uint32_t match = 0;
-    for (uint32_t j = lane; j < A.n; j += 32) {
-      if (lp != A.lap[j]) continue;
-      if (scale_gate_fails(sc, A.scale[j])) continue;
+    for (uint32_t c = band.x + lane; c < band.y; c += 32) {
+      const uint32_t j = A.perm[c];
+      if (lp != A.lap[j]) continue;                    // match.cpp:270
+      if (scale_gate_fails(sc, A.scale[j])) continue;  // match.cpp:273-275
       const float dist = exact_norm48(r, A.desc + (size_t)j * kD);
-      if (dist < d1) { d2 = d1; d1 = dist; match = j; } else if (dist < d2) { d2 = dist; }
+      top2_merge_one(dist, j, d1, d2, match);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {

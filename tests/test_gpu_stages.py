@@ -17,8 +17,15 @@ def matcher(built):
     m.close()
 
 
-def eps_bound(n2a, n2b):
-    return 1.05e-3 * np.sqrt(n2a * n2b) + 3e-5 * max(1.0, n2a, n2b)
+def eps_bound(desc_a, desc_b):
+    """task_eps of fm_score.cuh: Cauchy-Schwarz on the actual FP16 rounding residuals."""
+    def stats(d):
+        d = d.astype(np.float64)
+        r = d.astype(np.float16).astype(np.float64) - d
+        return np.sqrt((d ** 2).sum(1).max()), np.sqrt((r ** 2).sum(1).max())
+    na, da = stats(desc_a)
+    nb, db = stats(desc_b)
+    return 1.01 * (na * db + da * nb + da * db) + 3e-5 * max(1.0, na * na, nb * nb)
 
 
 def test_prep_sort_classes_operands(matcher):
@@ -62,7 +69,7 @@ def test_bands_score_tile_and_candidates(matcher, kind, n_first, n_second):
     n2a = (a.desc[pa].astype(np.float64) ** 2).sum(1)
     n2b = (b.desc[pb].astype(np.float64) ** 2).sum(1)
     t_exact = 0.5 * (n2b[:, None] - exact)  # = a.b - |col|^2/2 up to the reference's own rounding
-    eps = eps_bound(n2a.max(), n2b.max())
+    eps = eps_bound(a.desc, b.desc)
     rowop = db["rowop"].astype(np.float64)
     colop = da["colop"].astype(np.float64)
     worst = 0.0
@@ -90,7 +97,7 @@ def test_bands_score_tile_and_candidates(matcher, kind, n_first, n_second):
         for r in range(nr):
             order = np.sort(tm[r])[::-1]
             a2 = order[1] if len(order) > 1 else -np.inf
-            need = set(np.nonzero(tm[r] >= a2 - 2 * eps)[0].tolist()) if np.isfinite(order[0]) else set()
+            need = set(np.nonzero(np.isfinite(tm[r]) & (tm[r] >= a2 - 2 * eps))[0].tolist())
             got = {int(c) for c, v in zip(u["cand_col"][r], u["cand_t"][r]) if np.isfinite(v)}
             overflow = np.isfinite(u["cand_t"][r][3]) and u["cand_t"][r][3] >= a2 - 2 * eps
             if not overflow:
