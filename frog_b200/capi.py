@@ -226,8 +226,8 @@ class Matcher:
         t = np.zeros((256, ld), np.float32)
         nr = min(256, n_second - row_block * 256)
         bands = np.zeros((nr, 2), np.uint32)
-        ct = np.zeros((nr, 4), np.float32)
-        cc = np.zeros((nr, 4), np.uint32)
+        ct = np.zeros((nr, 8), np.float32)
+        cc = np.zeros((nr, 8), np.uint32)
         self._check(self._L.fm_debug_score_unit(self._h, first_img, second_img, row_block, _ptr(t), ld,
                                                 _ptr(bands), _ptr(ct), _ptr(cc)))
         return dict(t=t, bands=bands, cand_t=ct, cand_col=cc)

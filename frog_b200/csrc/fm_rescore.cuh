@@ -4,9 +4,10 @@
 // Soundness.  Let t~ be the FP16-operand score and t the exact value of a.b - |b|^2/2, with
 // |t~ - t| <= eps for every pair of the task.  If A2 is the second-largest t~ of a row, every
 // column that can be the exact nearest or second-nearest neighbour (or tie with them) has
-// t~ >= A2 - 2*eps.  Each candidate list keeps the row's top-4 t~ of its column segment, so it
-// holds every such column unless its 4th entry itself is >= A2 - 2*eps -- in that (rare) case
-// the row is queued for the exact brute-force row kernel below.  Surviving candidates are
+// t~ >= A2 - 2*eps: for such a column x and the better of the two approximate leaders y != x,
+// t~(x) >= t(x) - eps >= t(y) - eps >= t~(y) - 2 eps >= A2 - 2 eps.  The scoring kernel captures
+// every column above a threshold that never exceeds A2 - 2 eps, so the lists are complete unless
+// one overflowed (marker) -- then the row is queued for the exact row kernel below.  Captured are
 // re-evaluated with the reference's own arithmetic (gates, sequential FP32 norm, strict compares,
 // lowest-original-index tie rule), so accepted pairs are bit-identical to the reference.
 #pragma once
@@ -60,19 +61,20 @@ rescore_kernel(const ImageDev* __restrict__ images, const Task* __restrict__ tas
   const uint32_t row = B.perm[s];
   const float eps = task_eps(A.meta, B.meta);
 
+  // Candidate lists (one per column segment) hold every column whose score exceeded the list's
+  // final capture threshold g2 - 2 eps <= (row's 2nd best) - 2 eps, unsorted; a +inf marker in
+  // any list means that list overflowed.
   const uint32_t L = segs * kTopK;
   const Cand* c = cands + (size_t)(task.row_off + s) * L;
   float a1 = -INFINITY, a2 = -INFINITY;
+  bool overflow = false;
   for (uint32_t e = 0; e < L; e++) {
-    float v = c[e].t;
-    if (v > a1) { a2 = a1; a1 = v; } else if (v > a2) { a2 = v; }
+    const float v = c[e].t;
+    if (v == INFINITY) overflow = true;
+    else if (v > a1) { a2 = a1; a1 = v; }
+    else if (v > a2) { a2 = v; }
   }
   const float band = a2 - 2.f * eps;  // -inf when the row has fewer than two candidates
-  bool overflow = false;
-  for (uint32_t g = 0; g < segs; g++) {
-    float last = c[g * kTopK + kTopK - 1].t;
-    if (last > -INFINITY && last >= band) overflow = true;
-  }
 
   uint32_t match = kNone;
   uint32_t n_eval = 0;

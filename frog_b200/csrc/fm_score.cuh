@@ -8,9 +8,10 @@
 //                             tile, FP32 accumulators double-buffered in TMEM (4 x 128 columns)
 //   warp 2      TMEM allocator
 //   warps 4..11 epilogue    : tcgen05.ld (TMEM lane == row, so a row's scan over columns is
-//                             thread-local), gate mask on band-edge tiles only, running top-4
-//                             (value, column) per row kept in registers
-// Scores never touch HBM: per row only the 4 best (t, column) candidates leave the SM.
+//                             thread-local), gate mask on band-edge tiles only, 3-input max tree
+//                             per 16 columns, capture of the few columns above a running
+//                             threshold into a per-row shared-memory list
+// Scores never touch HBM: per row only <= 8 (t, column) candidates leave the SM.
 // t = a.b - |b|^2/2 comes straight out of the MMA (K slots 48,49, see fm_prep.cuh), so
 // larger t <=> smaller squared distance.
 #pragma once
@@ -24,7 +25,8 @@ constexpr int kTileBytes = 16384;  // 128 rows x 64 halves
 constexpr int kTileCols = 128;
 constexpr int kUnitRows = 256;
 constexpr int kStages = 6;
-constexpr int kTopK = 4;
+constexpr int kTopK = 8;        // candidate slots written per (row, column segment)
+constexpr int kCapSlots = 32;  // capture list entries per row in shared memory
 constexpr int kEpiWarps = 8;
 constexpr int kScoreThreads = (4 + kEpiWarps) * 32;
 
@@ -43,6 +45,7 @@ struct alignas(1024) ScoreSmem {
   uint64_t bar_accempty[2];
   uint32_t tmem_base;
   uint32_t cmin, cmax;
+  uint2 cap[kCapSlots][kUnitRows];  // [slot][row]: lanes of a warp hit distinct banks whatever their slot
 };
 constexpr size_t kScoreSmemBytes = sizeof(ScoreSmem) + 1024;
 
@@ -96,24 +99,6 @@ bands_kernel(const ImageDev* __restrict__ images, const Task* __restrict__ tasks
 
 // ------------------------------------------------------------------------------------------------
 
-struct TopK {
-  float v[kTopK];
-  uint32_t i[kTopK];
-};
-
-// Insert (v, idx) into the descending list; caller guarantees v > t.v[3].
-__device__ __forceinline__ void topk_insert(TopK& t, float v, uint32_t idx) {
-  if (v > t.v[1]) {
-    t.v[3] = t.v[2]; t.i[3] = t.i[2];
-    t.v[2] = t.v[1]; t.i[2] = t.i[1];
-    if (v > t.v[0]) { t.v[1] = t.v[0]; t.i[1] = t.i[0]; t.v[0] = v; t.i[0] = idx; }
-    else            { t.v[1] = v; t.i[1] = idx; }
-  } else {
-    if (v > t.v[2]) { t.v[3] = t.v[2]; t.i[3] = t.i[2]; t.v[2] = v; t.i[2] = idx; }
-    else            { t.v[3] = v; t.i[3] = idx; }
-  }
-}
-
 __device__ __forceinline__ float max3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
 
 // Certified bound on |t~ - t| (FP16-operand score vs exact a.b - |b|^2/2) for every pair of a task.
@@ -130,15 +115,53 @@ __device__ __forceinline__ float task_eps(const ImageMeta* ma, const ImageMeta* 
   return 1.01f * (na * db + da * nb + da * db) + 3e-5f * fmaxf(1.f, fmaxf(ma->max_norm2, mb->max_norm2));
 }
 
+// Per-row scan state (registers of the row's epilogue thread).
+//   g1 >= g2 : the two largest 16-column chunk maxima seen so far.  They belong to two distinct
+//              columns, so g2 <= (row's second-best score) at any time, and
+//   thr = g2 - 2 eps  is a capture threshold that never exceeds the final (2nd best - 2 eps):
+//              every column that can be -- or tie with -- the exact nearest or second-nearest
+//              neighbour scores above it (proof in fm_rescore.cuh).
+// Keeping thr needs 4 branch-free ALU ops per 16 columns; only columns above thr (about
+// 2 ln N per row) are appended to the row's shared-memory list.
+struct RowScan {
+  float g1, g2, thr;
+  uint32_t cnt;  // live entries in the capture list
+  uint32_t ovf;  // list could not hold every column above thr: row must be redone exactly
+  uint32_t cap;  // shared-space address of sm.cap[0][row]; slot k lives kCapStride bytes further per k
+};
+constexpr uint32_t kCapStride = kUnitRows * sizeof(uint2);
+
+__device__ __forceinline__ void cap_store(uint32_t addr, float v, uint32_t col) {
+  asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(__float_as_uint(v)), "r"(col) : "memory");
+}
+__device__ __forceinline__ uint2 cap_load(uint32_t addr) {
+  uint2 e;
+  asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(e.x), "=r"(e.y) : "r"(addr) : "memory");
+  return e;
+}
+
+// Drop captured entries that the (risen) threshold has made irrelevant.
+__device__ __noinline__ uint32_t cap_compress(uint32_t cap, uint32_t cnt, float thr) {
+  uint32_t k = 0;
+  for (uint32_t i = 0; i < cnt; i++) {
+    const uint2 e = cap_load(cap + i * kCapStride);
+    if (__uint_as_float(e.x) > thr) {
+      cap_store(cap + k * kCapStride, __uint_as_float(e.x), e.y);
+      k++;
+    }
+  }
+  return k;
+}
+
+__device__ __forceinline__ void cap_append(RowScan& st, float v, uint32_t col) {
+  cap_store(st.cap + st.cnt * kCapStride, v, col);
+  st.cnt++;
+}
+
 // 16 consecutive columns of one row.  kMasked: columns outside [lo, hi) are gated out.
-// Fast path: a 3-input max tree and one compare against the capture threshold
-//   thr = max(4th best so far, 2nd best so far - 2 eps).
-// Only columns above thr can be (or tie with) the exact nearest / second-nearest neighbour, or
-// must be kept so the rescoring pass can certify the list (fm_rescore.cuh); that happens for
-// about 2 ln N columns per row, so the insert stays an out-of-line branch.
-template <bool kMasked>
+template <bool kMasked, int kProbe>
 __device__ __forceinline__ void score_chunk(const uint32_t (&r)[16], uint32_t col0, uint32_t lo, uint32_t width,
-                                            TopK& tk, float& thr, float two_eps) {
+                                            RowScan& st, float two_eps) {
   float f[16];
 #pragma unroll
   for (int e = 0; e < 16; e++) {
@@ -148,26 +171,34 @@ __device__ __forceinline__ void score_chunk(const uint32_t (&r)[16], uint32_t co
   const float m0 = max3(f[0], f[1], f[2]), m1 = max3(f[3], f[4], f[5]), m2 = max3(f[6], f[7], f[8]);
   const float m3 = max3(f[9], f[10], f[11]), m4 = max3(f[12], f[13], f[14]);
   const float m = fmaxf(max3(m0, m1, m2), max3(m3, m4, f[15]));
-  if (m > thr) {
-#pragma unroll
-    for (int e = 0; e < 16; e++) {
-      if (f[e] > thr) {
-        asm volatile("" ::: "memory");  // keep a real branch (no if-conversion into 30 selects per column)
-        topk_insert(tk, f[e], col0 + e);
-        thr = fmaxf(tk.v[kTopK - 1], tk.v[1] - two_eps);
-      }
+  const float second = fminf(st.g1, m);
+  st.g1 = fmaxf(st.g1, m);
+  st.g2 = fmaxf(st.g2, second);
+  if (kProbe != 1) st.thr = st.g2 - two_eps;
+  const float th = st.thr;
+  if (m > th) {  // rare per lane, so everything below is branches the warp usually skips
+    if (st.cnt > kCapSlots - 16) {
+      st.cnt = cap_compress(st.cap, st.cnt, th);
+      if (st.cnt > kCapSlots - 16) { st.ovf = 1; st.cnt = 0; }
     }
+#define FM_TRY(e) if (f[e] > th) cap_append(st, f[e], col0 + (e))
+    if (m0 > th) { FM_TRY(0); FM_TRY(1); FM_TRY(2); }
+    if (m1 > th) { FM_TRY(3); FM_TRY(4); FM_TRY(5); }
+    if (m2 > th) { FM_TRY(6); FM_TRY(7); FM_TRY(8); }
+    if (m3 > th) { FM_TRY(9); FM_TRY(10); FM_TRY(11); }
+    if (m4 > th) { FM_TRY(12); FM_TRY(13); FM_TRY(14); }
+    FM_TRY(15);
+#undef FM_TRY
   }
 }
 
-template <bool kMasked, bool kDump>
-__device__ __forceinline__ void score_tile(uint32_t taddr, uint32_t cb, uint32_t lo, uint32_t width, TopK& tk,
-                                           float& thr, float two_eps, uint64_t* bar_release, float* dump_row) {
+template <bool kMasked, bool kDump, int kProbe>
+__device__ __forceinline__ void score_tile(uint32_t taddr, uint32_t cb, uint32_t lo, uint32_t width, RowScan& st,
+                                           float two_eps, uint64_t* bar_release, float* dump_row) {
   uint32_t ra[16], rb[16];
   ptx::tmem_ld16(ra, taddr);
   ptx::tmem_ld_wait(ra);
-  // Rolled on purpose: the insert branches make the body large, and one copy of it must stay
-  // resident in the instruction cache.
+  // Rolled on purpose: one copy of the capture branches stays resident in the instruction cache.
 #pragma unroll 1
   for (int c = 0; c < kTileCols / 16; c += 2) {
     ptx::tmem_ld16(rb, taddr + (c + 1) * 16);  // next 16 columns in flight while these are scanned
@@ -175,7 +206,7 @@ __device__ __forceinline__ void score_tile(uint32_t taddr, uint32_t cb, uint32_t
 #pragma unroll
       for (int e = 0; e < 16; e++) dump_row[cb + c * 16 + e] = __uint_as_float(ra[e]);
     }
-    score_chunk<kMasked>(ra, cb + c * 16, lo, width, tk, thr, two_eps);
+    score_chunk<kMasked, kProbe>(ra, cb + c * 16, lo, width, st, two_eps);
     ptx::tmem_ld_wait(rb);
     if (c + 2 < kTileCols / 16) {
       ptx::tmem_ld16(ra, taddr + (c + 2) * 16);
@@ -189,14 +220,16 @@ __device__ __forceinline__ void score_tile(uint32_t taddr, uint32_t cb, uint32_t
 #pragma unroll
       for (int e = 0; e < 16; e++) dump_row[cb + (c + 1) * 16 + e] = __uint_as_float(rb[e]);
     }
-    score_chunk<kMasked>(rb, cb + (c + 1) * 16, lo, width, tk, thr, two_eps);
+    score_chunk<kMasked, kProbe>(rb, cb + (c + 1) * 16, lo, width, st, two_eps);
     if (c + 2 < kTileCols / 16) ptx::tmem_ld_wait(ra);
   }
 }
 
 // unit_off: exclusive prefix of units per task (n_tasks + 1 entries).  A task with n rows has
 // ceil(n / 256) * segs units; unit = row_block * segs + seg.
-// cands: [batch rows][segs][kTopK].   dump (kDump only): [256][dump_ld] raw t of unit 0.
+// cands: [batch rows][segs][kTopK]: the columns above the row's final threshold (unsorted,
+//        -inf padded); slot 0 = (+inf, kNone) marks a row whose list overflowed.
+// dump (kDump only): [256][dump_ld] raw t of the unit.
 // kProbe (performance attribution only, results are garbage): 1 = capture threshold pinned at +inf,
 // i.e. the max-tree fast path alone; 2 = epilogue skips the TMEM loads too (TMA + MMA pipeline alone).
 template <bool kDump, int kProbe = 0>
@@ -252,9 +285,12 @@ score_kernel(const ImageDev* __restrict__ images, const Task* __restrict__ tasks
     n_tiles = tb + (uint32_t)(((uint64_t)nt * (seg + 1)) / segs) - tile0;
   }
 
-  TopK tk;
-#pragma unroll
-  for (int k = 0; k < kTopK; k++) { tk.v[k] = -INFINITY; tk.i[k] = 0; }
+  RowScan st;
+  st.g1 = st.g2 = -INFINITY;
+  st.thr = kProbe == 1 ? INFINITY : -INFINITY;
+  st.cnt = 0;
+  st.ovf = 0;
+  st.cap = ptx::smem_u32(&sm.cap[0][is_epi ? row_in_unit : 0]);
 
   if (n_tiles > 0) {  // CTA-uniform
     if (warp == 1 && lane == 0) {
@@ -278,10 +314,10 @@ score_kernel(const ImageDev* __restrict__ images, const Task* __restrict__ tasks
         ptx::bulk_g2s(sm.a[1], rowop + kTileBytes, kTileBytes, &sm.bar_a);
         const uint8_t* colop = reinterpret_cast<const uint8_t*>(A.colop);
         for (uint32_t i = 0; i < n_tiles; i++) {
-          const uint32_t st = i % kStages, use = i / kStages;
-          if (use > 0) ptx::mbar_wait(&sm.bar_bempty[st], (use - 1) & 1);
-          ptx::mbar_expect_tx(&sm.bar_bfull[st], kTileBytes);
-          ptx::bulk_g2s(sm.b[st], colop + (size_t)(tile0 + i) * kTileBytes, kTileBytes, &sm.bar_bfull[st]);
+          const uint32_t stg = i % kStages, use = i / kStages;
+          if (use > 0) ptx::mbar_wait(&sm.bar_bempty[stg], (use - 1) & 1);
+          ptx::mbar_expect_tx(&sm.bar_bfull[stg], kTileBytes);
+          ptx::bulk_g2s(sm.b[stg], colop + (size_t)(tile0 + i) * kTileBytes, kTileBytes, &sm.bar_bfull[stg]);
         }
       }
     } else if (warp == 1) {
@@ -292,18 +328,18 @@ score_kernel(const ImageDev* __restrict__ images, const Task* __restrict__ tasks
         const uint64_t adesc1 = ptx::umma_desc_sw128(ptx::smem_u32(sm.a[1]));
         ptx::mbar_wait(&sm.bar_a, 0);
         for (uint32_t i = 0; i < n_tiles; i++) {
-          const uint32_t st = i % kStages, acc = i & 1, use = i >> 1;
+          const uint32_t stg = i % kStages, acc = i & 1, use = i >> 1;
           if (use > 0) ptx::mbar_wait(&sm.bar_accempty[acc], (use - 1) & 1);
-          ptx::mbar_wait(&sm.bar_bfull[st], (i / kStages) & 1);
+          ptx::mbar_wait(&sm.bar_bfull[stg], (i / kStages) & 1);
           ptx::tc_fence_after();
-          const uint64_t bdesc = ptx::umma_desc_sw128(ptx::smem_u32(sm.b[st]));
+          const uint64_t bdesc = ptx::umma_desc_sw128(ptx::smem_u32(sm.b[stg]));
 #pragma unroll
           for (int k = 0; k < kKPad / 16; k++)  // +32 B per K step inside the 128 B swizzle row
             ptx::mma_f16_ss(tmem + acc * 256, adesc0 + 2 * k, bdesc + 2 * k, idesc, k > 0);
 #pragma unroll
           for (int k = 0; k < kKPad / 16; k++)
             ptx::mma_f16_ss(tmem + acc * 256 + 128, adesc1 + 2 * k, bdesc + 2 * k, idesc, k > 0);
-          ptx::mma_commit(&sm.bar_bempty[st]);
+          ptx::mma_commit(&sm.bar_bempty[stg]);
           ptx::mma_commit(&sm.bar_accfull[acc]);
         }
       }
@@ -311,7 +347,6 @@ score_kernel(const ImageDev* __restrict__ images, const Task* __restrict__ tasks
       // ---- epilogue ------------------------------------------------------------------------------
       const uint32_t width = hi - lo;
       const float two_eps = 2.f * task_eps(A.meta, B.meta);
-      float thr = kProbe == 1 ? INFINITY : -INFINITY;
       float* dump_row = kDump ? dump + (size_t)row_in_unit * dump_ld : nullptr;
       unsigned long long scored = 0;
       for (uint32_t i = 0; i < n_tiles; i++) {
@@ -326,10 +361,10 @@ score_kernel(const ImageDev* __restrict__ images, const Task* __restrict__ tasks
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(&sm.bar_accempty[acc]);
         } else if (!kDump && cb >= w_imin && cb + kTileCols <= w_imax) {
-          score_tile<false, kDump>(taddr, cb, lo, width, tk, thr, two_eps, &sm.bar_accempty[acc], dump_row);
+          score_tile<false, kDump, kProbe>(taddr, cb, lo, width, st, two_eps, &sm.bar_accempty[acc], dump_row);
           scored += kTileCols;
         } else {
-          score_tile<true, kDump>(taddr, cb, lo, width, tk, thr, two_eps, &sm.bar_accempty[acc], dump_row);
+          score_tile<true, kDump, kProbe>(taddr, cb, lo, width, st, two_eps, &sm.bar_accempty[acc], dump_row);
           scored += kTileCols;
         }
       }
@@ -348,9 +383,22 @@ score_kernel(const ImageDev* __restrict__ images, const Task* __restrict__ tasks
   }
 
   if (is_epi && s < B.n) {
+    // Final list: the entries above the final threshold.  More than kTopK of them (or an earlier
+    // overflow) -> marker; the rescoring kernel then queues the row for the exact row kernel.
+    uint32_t cnt = st.ovf ? 0u : cap_compress(st.cap, st.cnt, st.thr);
+    const bool ovf = st.ovf || cnt > (uint32_t)kTopK;
     Cand* out = cands + ((size_t)(task.row_off + s) * segs + seg) * kTopK;
 #pragma unroll
-    for (int k = 0; k < kTopK; k++) out[k] = Cand{tk.v[k], tk.i[k]};
+    for (int k = 0; k < kTopK; k++) {
+      Cand cd{-INFINITY, 0u};
+      if (ovf) {
+        if (k == 0) cd = Cand{INFINITY, kNone};
+      } else if ((uint32_t)k < cnt) {
+        const uint2 e = cap_load(st.cap + k * kCapStride);
+        cd = Cand{__uint_as_float(e.x), e.y};
+      }
+      out[k] = cd;
+    }
   }
 }
 

@@ -28,7 +28,8 @@ int fm_debug_image(fm_ctx* ctx, uint32_t img, uint32_t* flags, uint32_t* n_class
  *   t_out    : 256 x ld floats, t_out[r * ld + col] = raw score of (unit row r, sorted column col);
  *              columns of tiles the unit did not visit stay NaN.  ld >= n_pad(first).
  *   bands_out: min(256, rows left) x 2 uint32 (lo, hi) sorted-column interval per unit row
- *   cand_t / cand_col: rows x 4 captured candidates (score descending, sorted column)
+ *   cand_t / cand_col: rows x 8 captured candidates (unsorted, -inf padded; slot 0 = +inf marks an
+ *              overflowed list), columns are sorted positions in image `first`
  */
 int fm_debug_score_unit(fm_ctx* ctx, uint32_t first_img, uint32_t second_img, uint32_t row_block, float* t_out,
                         uint32_t ld, uint32_t* bands_out, float* cand_t, uint32_t* cand_col);
