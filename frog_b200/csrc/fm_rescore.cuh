@@ -75,6 +75,16 @@ rescore_kernel(const ImageDev* __restrict__ images, const Task* __restrict__ tas
     else if (v > a2) { a2 = v; }
   }
   const float band = a2 - 2.f * eps;  // -inf when the row has fewer than two candidates
+  // A truncated list dropped columns scoring <= its smallest kept entry: still complete iff that
+  // entry is below the band.
+  for (uint32_t g = 0; g < segs && !overflow; g++) {
+    const Cand* l = c + g * kTopK;
+    if (l[0].t > -INFINITY && (l[0].col & kCandTruncated)) {
+      float lowest = l[0].t;
+      for (int k = 1; k < kTopK; k++) lowest = fminf(lowest, l[k].t);
+      if (lowest >= band) overflow = true;
+    }
+  }
 
   uint32_t match = kNone;
   uint32_t n_eval = 0;
@@ -92,7 +102,7 @@ rescore_kernel(const ImageDev* __restrict__ images, const Task* __restrict__ tas
     for (uint32_t e = 0; e < L; e++) {
       const Cand cd = c[e];
       if (!(cd.t > -INFINITY) || !(cd.t >= band)) continue;
-      const uint32_t j = A.perm[cd.col];
+      const uint32_t j = A.perm[cd.col & ~kCandTruncated];
       if (lp != A.lap[j]) continue;                    // match.cpp:270
       if (scale_gate_fails(sc, A.scale[j])) continue;  // match.cpp:273-275
       const float dist = exact_norm48(r, A.desc + (size_t)j * kD);

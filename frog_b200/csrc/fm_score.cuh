@@ -24,16 +24,17 @@ namespace fm {
 constexpr int kTileBytes = 16384;  // 128 rows x 64 halves
 constexpr int kTileCols = 128;
 constexpr int kUnitRows = 256;
-constexpr int kStages = 6;
+constexpr int kStages = 4;
 constexpr int kTopK = 8;        // candidate slots written per (row, column segment)
-constexpr int kCapSlots = 32;  // capture list entries per row in shared memory
+constexpr int kCapSlots = 48;  // capture list entries per row in shared memory
 constexpr int kEpiWarps = 8;
 constexpr int kScoreThreads = (4 + kEpiWarps) * 32;
 
 struct Cand {
   float t;       // approximate score, -inf for an empty slot
-  uint32_t col;  // sorted column position in image `first`
+  uint32_t col;  // sorted column position in image `first` (bit 31 of slot 0: list truncated)
 };
+constexpr uint32_t kCandTruncated = 0x80000000u;
 
 struct alignas(1024) ScoreSmem {
   uint8_t a[2][kTileBytes];
@@ -153,6 +154,24 @@ __device__ __noinline__ uint32_t cap_compress(uint32_t cap, uint32_t cnt, float 
   return k;
 }
 
+// Move the kTopK largest of cnt (> kTopK) entries to the front (selection sort in shared memory;
+// only rows whose column segment is too short to establish a threshold get here).
+__device__ __noinline__ void cap_select_top(uint32_t cap, uint32_t cnt) {
+  for (uint32_t k = 0; k < (uint32_t)kTopK; k++) {
+    uint32_t best = k;
+    uint2 eb = cap_load(cap + k * kCapStride);
+    const uint2 ek = eb;
+    for (uint32_t i = k + 1; i < cnt; i++) {
+      const uint2 e = cap_load(cap + i * kCapStride);
+      if (__uint_as_float(e.x) > __uint_as_float(eb.x)) { eb = e; best = i; }
+    }
+    if (best != k) {
+      cap_store(cap + best * kCapStride, __uint_as_float(ek.x), ek.y);
+      cap_store(cap + k * kCapStride, __uint_as_float(eb.x), eb.y);
+    }
+  }
+}
+
 __device__ __forceinline__ void cap_append(RowScan& st, float v, uint32_t col) {
   cap_store(st.cap + st.cnt * kCapStride, v, col);
   st.cnt++;
@@ -175,8 +194,21 @@ __device__ __forceinline__ void score_chunk(const uint32_t (&r)[16], uint32_t co
   st.g1 = fmaxf(st.g1, m);
   st.g2 = fmaxf(st.g2, second);
   if (kProbe != 1) st.thr = st.g2 - two_eps;
-  const float th = st.thr;
+  float th = st.thr;
   if (m > th) {  // rare per lane, so everything below is branches the warp usually skips
+    if (kProbe != 1 && st.g2 == -INFINITY) {
+      // First scored chunk of the row: seed the threshold with the second largest of the six
+      // node maxima (disjoint column sets, so it cannot exceed the row's second-best score)
+      // instead of capturing all 16 columns against thr = -inf.
+      float h = m0, sec = -INFINITY;
+      sec = fmaxf(sec, fminf(h, m1)); h = fmaxf(h, m1);
+      sec = fmaxf(sec, fminf(h, m2)); h = fmaxf(h, m2);
+      sec = fmaxf(sec, fminf(h, m3)); h = fmaxf(h, m3);
+      sec = fmaxf(sec, fminf(h, m4)); h = fmaxf(h, m4);
+      sec = fmaxf(sec, fminf(h, f[15]));
+      st.g2 = sec;
+      st.thr = th = sec - two_eps;
+    }
     if (st.cnt > kCapSlots - 16) {
       st.cnt = cap_compress(st.cap, st.cnt, th);
       if (st.cnt > kCapSlots - 16) { st.ovf = 1; st.cnt = 0; }
@@ -227,8 +259,10 @@ __device__ __forceinline__ void score_tile(uint32_t taddr, uint32_t cb, uint32_t
 
 // unit_off: exclusive prefix of units per task (n_tasks + 1 entries).  A task with n rows has
 // ceil(n / 256) * segs units; unit = row_block * segs + seg.
-// cands: [batch rows][segs][kTopK]: the columns above the row's final threshold (unsorted,
-//        -inf padded); slot 0 = (+inf, kNone) marks a row whose list overflowed.
+// cands: [batch rows][segs][kTopK]: the columns above the row's final threshold (-inf padded).
+//        If more than kTopK qualify, the kTopK best are kept and bit 31 of slot 0's column is set
+//        ("truncated": every dropped column scores <= the smallest kept one).  Slot 0 =
+//        (+inf, kNone) marks a list that overflowed during the scan.
 // dump (kDump only): [256][dump_ld] raw t of the unit.
 // kProbe (performance attribution only, results are garbage): 1 = capture threshold pinned at +inf,
 // i.e. the max-tree fast path alone; 2 = epilogue skips the TMEM loads too (TMA + MMA pipeline alone).
@@ -383,19 +417,23 @@ score_kernel(const ImageDev* __restrict__ images, const Task* __restrict__ tasks
   }
 
   if (is_epi && s < B.n) {
-    // Final list: the entries above the final threshold.  More than kTopK of them (or an earlier
-    // overflow) -> marker; the rescoring kernel then queues the row for the exact row kernel.
+    // Final list: the entries above the final threshold.
     uint32_t cnt = st.ovf ? 0u : cap_compress(st.cap, st.cnt, st.thr);
-    const bool ovf = st.ovf || cnt > (uint32_t)kTopK;
+    uint32_t trunc = 0;
+    if (cnt > (uint32_t)kTopK) {
+      cap_select_top(st.cap, cnt);
+      cnt = kTopK;
+      trunc = kCandTruncated;
+    }
     Cand* out = cands + ((size_t)(task.row_off + s) * segs + seg) * kTopK;
 #pragma unroll
     for (int k = 0; k < kTopK; k++) {
       Cand cd{-INFINITY, 0u};
-      if (ovf) {
+      if (st.ovf) {
         if (k == 0) cd = Cand{INFINITY, kNone};
       } else if ((uint32_t)k < cnt) {
         const uint2 e = cap_load(st.cap + k * kCapStride);
-        cd = Cand{__uint_as_float(e.x), e.y};
+        cd = Cand{__uint_as_float(e.x), e.y | (k == 0 ? trunc : 0u)};
       }
       out[k] = cd;
     }

@@ -98,12 +98,18 @@ def test_bands_score_tile_and_candidates(matcher, kind, n_first, n_second):
             order = np.sort(tm[r])[::-1]
             a2 = order[1] if len(order) > 1 else -np.inf
             need = set(np.nonzero(np.isfinite(tm[r]) & (tm[r] >= a2 - 2 * eps))[0].tolist())
-            got = {int(c) for c, v in zip(u["cand_col"][r], u["cand_t"][r]) if np.isfinite(v)}
+            cols_r = u["cand_col"][r] & 0x7FFFFFFF
+            got = {int(c) for c, v in zip(cols_r, u["cand_t"][r]) if np.isfinite(v)}
             overflow = np.isposinf(u["cand_t"][r][0])  # marker: the row's capture list overflowed
+            truncated = np.isfinite(u["cand_t"][r][0]) and bool(u["cand_col"][r][0] >> 31)
+            if truncated:  # the 8 best were kept: complete iff the smallest kept one is below the band
+                kept = u["cand_t"][r][np.isfinite(u["cand_t"][r])]
+                assert len(kept) == 8 and kept.min() >= np.sort(tm[r])[::-1][7]
+                overflow = kept.min() >= a2 - 2 * eps
             if not overflow:
                 assert need <= got
                 assert len(got) <= 8
-            for c, v in zip(u["cand_col"][r], u["cand_t"][r]):
+            for c, v in zip(cols_r, u["cand_t"][r]):
                 if np.isfinite(v):
                     assert v == t[r, c] and gate[r0 + r, c]
     print(f"max |t_fp16 - t_exact| = {worst:.2e} (bound {eps:.2e})")
