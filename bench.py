@@ -61,17 +61,19 @@ def cpu_sample_group(tmpdir, kind, n_images, n_points):
 
 
 def run_reference(list_path, dist, ratio, threads):
+    from frog_b200 import pairsbin
     from oracle import oracle
+    out = os.path.join(os.path.dirname(list_path), "ref_pairs.bin")
     t0 = time.time()
-    res = oracle.run_ref_binary([list_path, "-o", os.path.join(os.path.dirname(list_path), "ref_pairs.bin"),
-                                 "-d", dist, "-d2", ratio], threads=threads)
+    res = oracle.run_ref_binary([list_path, "-o", out, "-d", dist, "-d2", ratio], threads=threads)
     wall = time.time() - t0
     # the reference prints " : <seconds>s" after each phase; the third one is "Pairing" (match.cpp:655)
     secs = [float(x) for x in re.findall(r"^ : ([0-9.eE+-]+)s", res.stdout, flags=re.M)]
-    counts = [int(x) for x in re.findall(r"\. \((\d+)\)", res.stdout)]
     pairing = secs[2] if len(secs) >= 3 else wall
-    n = np.array(counts, np.float64)
-    pairs = (n.sum() ** 2 - (n ** 2).sum()) / 2.0  # sum_{i<j} N_i N_j with the loaded (phantom-inclusive) sizes
+    # Loaded (phantom-inclusive, match.cpp:179-208) keypoint counts come from the pairs.bin the reference
+    # wrote: its per-image stdout lines are printed from OpenMP threads without a lock and interleave.
+    n = np.array([p.shape[0] for p in pairsbin.parse(out).points], np.float64)
+    pairs = (n.sum() ** 2 - (n ** 2).sum()) / 2.0  # sum_{i<j} N_i N_j
     return pairs, pairing, wall
 
 
