@@ -122,10 +122,16 @@ inline cudaError_t fast_match_batch(fm_ctx* c, const FastBatchArgs& a) {
   if ((e = c->d_cands.ensure((size_t)a.rows * a.segs * kTopK * sizeof(Cand))) != cudaSuccess) return e;
   if ((e = c->d_redo.ensure((size_t)a.rows * sizeof(uint2))) != cudaSuccess) return e;
   if (!c->score_attr_set) {
-    if ((e = cudaFuncSetAttribute(score_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kScoreSmemBytes)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(score_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kScoreSmemBytes)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(score_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kScoreSmemBytes)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(score_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kScoreSmemBytes)) != cudaSuccess) return e;
+    // two CTAs per SM: ask for the full shared-memory carveout
+    auto prep = [](auto kern) -> cudaError_t {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kScoreSmemBytes);
+      if (e != cudaSuccess) return e;
+      return cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    };
+    if ((e = prep(score_kernel<false, 0>)) != cudaSuccess) return e;
+    if ((e = prep(score_kernel<false, 1>)) != cudaSuccess) return e;
+    if ((e = prep(score_kernel<false, 2>)) != cudaSuccess) return e;
+    if ((e = prep(score_kernel<true, 0>)) != cudaSuccess) return e;
     c->score_attr_set = true;
   }
   {

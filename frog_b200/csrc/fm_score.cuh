@@ -2,10 +2,12 @@
 // ComputeMatches, match.cpp:243-251 and :267-317) and the band kernel that feeds it.
 //
 // One CTA scores a "unit": 256 consecutive (laplacian, scale)-sorted rows of image `second`
-// against one contiguous range of 128-column tiles of image `first`.
-//   warp 0      TMA producer: cp.async.bulk 16 KB pre-swizzled FP16 tiles -> smem ring (mbarrier tx)
-//   warp 1      MMA issuer  : tcgen05.mma kind::f16, M=128 N=128 K=16, 4 K-steps x 2 row halves per
-//                             tile, FP32 accumulators double-buffered in TMEM (4 x 128 columns)
+// against one contiguous range of 64-column tiles of image `first`.  Two CTAs share an SM
+// (256 of the 512 TMEM columns and ~110 KB of shared memory each), so 16 epilogue warps hide each
+// other's latencies and one CTA's prologue / tail overlaps the other's steady state.
+//   warp 0      TMA producer: cp.async.bulk 8 KB pre-swizzled FP16 tiles -> smem ring (mbarrier tx)
+//   warp 1      MMA issuer  : tcgen05.mma kind::f16, M=128 N=64 K=16, 4 K-steps x 2 row halves per
+//                             tile, FP32 accumulators double-buffered in TMEM (2 x 2 x 64 columns)
 //   warp 2      TMEM allocator
 //   warps 4..11 epilogue    : tcgen05.ld (TMEM lane == row, so a row's scan over columns is
 //                             thread-local), gate mask on band-edge tiles only, 3-input max tree
@@ -21,12 +23,14 @@
 
 namespace fm {
 
-constexpr int kTileBytes = 16384;  // 128 rows x 64 halves
-constexpr int kTileCols = 128;
+constexpr int kOpTileBytes = 16384;  // operand tile as stored: 128 keypoints x 64 halves, SWIZZLE_128B
+constexpr int kTileCols = 64;        // columns per MMA tile: one half of a stored operand tile
+constexpr int kTileBytes = kTileCols * 128;
 constexpr int kUnitRows = 256;
 constexpr int kStages = 4;
 constexpr int kTopK = 8;        // candidate slots written per (row, column segment)
-constexpr int kCapSlots = 48;  // capture list entries per row in shared memory
+constexpr int kCapSlots = 22;  // capture list entries per row in shared memory
+constexpr int kAccCols = 2 * 2 * kTileCols;  // TMEM columns: 2 stages x 2 row halves
 constexpr int kEpiWarps = 8;
 constexpr int kScoreThreads = (4 + kEpiWarps) * 32;
 
@@ -37,7 +41,7 @@ struct Cand {
 constexpr uint32_t kCandTruncated = 0x80000000u;
 
 struct alignas(1024) ScoreSmem {
-  uint8_t a[2][kTileBytes];
+  uint8_t a[2][kOpTileBytes];
   uint8_t b[kStages][kTileBytes];
   uint64_t bar_a;
   uint64_t bar_bfull[kStages];
@@ -126,9 +130,9 @@ __device__ __forceinline__ float task_eps(const ImageMeta* ma, const ImageMeta* 
 // 2 ln N per row) are appended to the row's shared-memory list.
 struct RowScan {
   float g1, g2, thr;
-  uint32_t cnt;  // live entries in the capture list
-  uint32_t ovf;  // list could not hold every column above thr: row must be redone exactly
-  uint32_t cap;  // shared-space address of sm.cap[0][row]; slot k lives kCapStride bytes further per k
+  uint32_t cap;   // shared-space address of sm.cap[0][row]; slot k lives kCapStride bytes further per k
+  uint32_t capw;  // address of the next free slot: cap + (live entries) * kCapStride
+  uint32_t ovf;   // list could not hold every column above thr: row must be redone exactly
 };
 constexpr uint32_t kCapStride = kUnitRows * sizeof(uint2);
 
@@ -141,7 +145,7 @@ __device__ __forceinline__ uint2 cap_load(uint32_t addr) {
   return e;
 }
 
-// Drop captured entries that the (risen) threshold has made irrelevant.
+// Drop captured entries that the (risen) threshold has made irrelevant; returns the new count.
 __device__ __noinline__ uint32_t cap_compress(uint32_t cap, uint32_t cnt, float thr) {
   uint32_t k = 0;
   for (uint32_t i = 0; i < cnt; i++) {
@@ -172,15 +176,37 @@ __device__ __noinline__ void cap_select_top(uint32_t cap, uint32_t cnt) {
   }
 }
 
-__device__ __forceinline__ void cap_append(RowScan& st, float v, uint32_t col) {
-  cap_store(st.cap + st.cnt * kCapStride, v, col);
-  st.cnt++;
+// Predicated append (no branch): if v > thr, store (v, col) at capw and advance capw.
+__device__ __forceinline__ void cap_append_if_above(uint32_t& capw, float v, float thr, uint32_t col) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "setp.gt.f32 q, %1, %2;\n\t"
+      "@q st.shared.v2.b32 [%0], {%3, %4};\n\t"
+      "@q add.u32 %0, %0, %5;\n\t}"
+      : "+r"(capw)
+      : "f"(v), "f"(thr), "r"(__float_as_uint(v)), "r"(col), "n"(kCapStride)
+      : "memory");
+}
+
+// Make room for one tree node (3 columns) in a row's capture list: drop the entries the risen
+// threshold has retired.  Returns the new write address; bit 0 set = the list is still full,
+// i.e. the row must be redone by the exact kernel (the list restarts empty).
+__device__ __noinline__ uint32_t cap_make_room(uint32_t cap, uint32_t capw, float thr) {
+  const uint32_t cnt = cap_compress(cap, (capw - cap) / kCapStride, thr);
+  if (cnt > (uint32_t)(kCapSlots - 3)) return cap | 1u;
+  return cap + cnt * kCapStride;
 }
 
 // 16 consecutive columns of one row.  kMasked: columns outside [lo, hi) are gated out.
+// Fast path (every chunk, branch-free): 3-input max tree, the two largest chunk maxima, the
+// capture threshold, one compare.  The slow path is entered by the WARP when any of its 32 rows
+// has a column above its threshold; every branch in it is warp-uniform (votes) and the per-row
+// work is predicated, so lanes never diverge.
 template <bool kMasked, int kProbe>
 __device__ __forceinline__ void score_chunk(const uint32_t (&r)[16], uint32_t col0, uint32_t lo, uint32_t width,
                                             RowScan& st, float two_eps) {
+  constexpr uint32_t kAll = 0xffffffffu;
+  constexpr uint32_t kFullAt = (uint32_t)(kCapSlots - 3) * kCapStride;  // fewer than 3 free slots beyond this
   float f[16];
 #pragma unroll
   for (int e = 0; e < 16; e++) {
@@ -195,32 +221,47 @@ __device__ __forceinline__ void score_chunk(const uint32_t (&r)[16], uint32_t co
   st.g2 = fmaxf(st.g2, second);
   if (kProbe != 1) st.thr = st.g2 - two_eps;
   float th = st.thr;
-  if (m > th) {  // rare per lane, so everything below is branches the warp usually skips
-    if (kProbe != 1 && st.g2 == -INFINITY) {
-      // First scored chunk of the row: seed the threshold with the second largest of the six
-      // node maxima (disjoint column sets, so it cannot exceed the row's second-best score)
-      // instead of capturing all 16 columns against thr = -inf.
+  if (__any_sync(kAll, m > th)) {
+    if (kProbe != 1 && __any_sync(kAll, m > th && st.g2 == -INFINITY)) {
+      // First scored chunk of a row: seed the threshold with the second largest of the six node
+      // maxima (disjoint column sets, so it cannot exceed the row's second-best score) instead
+      // of capturing all 16 columns against thr = -inf.
       float h = m0, sec = -INFINITY;
       sec = fmaxf(sec, fminf(h, m1)); h = fmaxf(h, m1);
       sec = fmaxf(sec, fminf(h, m2)); h = fmaxf(h, m2);
       sec = fmaxf(sec, fminf(h, m3)); h = fmaxf(h, m3);
       sec = fmaxf(sec, fminf(h, m4)); h = fmaxf(h, m4);
       sec = fmaxf(sec, fminf(h, f[15]));
-      st.g2 = sec;
-      st.thr = th = sec - two_eps;
+      const bool seed = st.g2 == -INFINITY;
+      st.g2 = seed ? sec : st.g2;
+      st.thr = th = seed ? sec - two_eps : th;
     }
-    if (st.cnt > kCapSlots - 16) {
-      st.cnt = cap_compress(st.cap, st.cnt, th);
-      if (st.cnt > kCapSlots - 16) { st.ovf = 1; st.cnt = 0; }
+#define FM_ROOM(mk)                                                                  \
+    if (__any_sync(kAll, (mk) > th && st.capw - st.cap > kFullAt)) {                   \
+      if ((mk) > th && st.capw - st.cap > kFullAt) {                                   \
+        const uint32_t w = cap_make_room(st.cap, st.capw, th);                         \
+        st.ovf |= w & 1u;                                                              \
+        st.capw = w & ~1u;                                                             \
+      }                                                                                \
     }
-#define FM_TRY(e) if (f[e] > th) cap_append(st, f[e], col0 + (e))
-    if (m0 > th) { FM_TRY(0); FM_TRY(1); FM_TRY(2); }
-    if (m1 > th) { FM_TRY(3); FM_TRY(4); FM_TRY(5); }
-    if (m2 > th) { FM_TRY(6); FM_TRY(7); FM_TRY(8); }
-    if (m3 > th) { FM_TRY(9); FM_TRY(10); FM_TRY(11); }
-    if (m4 > th) { FM_TRY(12); FM_TRY(13); FM_TRY(14); }
-    FM_TRY(15);
+#define FM_TRY(e) cap_append_if_above(st.capw, f[e], th, col0 + (e))
+#define FM_NODE(mk, e0, e1, e2)            \
+    if (__any_sync(kAll, (mk) > th)) {       \
+      FM_ROOM(mk)                            \
+      FM_TRY(e0); FM_TRY(e1); FM_TRY(e2);    \
+    }
+    FM_NODE(m0, 0, 1, 2)
+    FM_NODE(m1, 3, 4, 5)
+    FM_NODE(m2, 6, 7, 8)
+    FM_NODE(m3, 9, 10, 11)
+    FM_NODE(m4, 12, 13, 14)
+    if (__any_sync(kAll, f[15] > th)) {
+      FM_ROOM(f[15])
+      FM_TRY(15);
+    }
+#undef FM_NODE
 #undef FM_TRY
+#undef FM_ROOM
   }
 }
 
@@ -267,7 +308,7 @@ __device__ __forceinline__ void score_tile(uint32_t taddr, uint32_t cb, uint32_t
 // kProbe (performance attribution only, results are garbage): 1 = capture threshold pinned at +inf,
 // i.e. the max-tree fast path alone; 2 = epilogue skips the TMEM loads too (TMA + MMA pipeline alone).
 template <bool kDump, int kProbe = 0>
-__global__ void __launch_bounds__(kScoreThreads, 1)
+__global__ void __launch_bounds__(kScoreThreads, 2)
 score_kernel(const ImageDev* __restrict__ images, const Task* __restrict__ tasks,
              const uint32_t* __restrict__ unit_off, uint32_t n_tasks, uint32_t segs,
              const uint2* __restrict__ bands, Cand* __restrict__ cands, unsigned long long* __restrict__ scored_cols,
@@ -322,9 +363,8 @@ score_kernel(const ImageDev* __restrict__ images, const Task* __restrict__ tasks
   RowScan st;
   st.g1 = st.g2 = -INFINITY;
   st.thr = kProbe == 1 ? INFINITY : -INFINITY;
-  st.cnt = 0;
   st.ovf = 0;
-  st.cap = ptx::smem_u32(&sm.cap[0][is_epi ? row_in_unit : 0]);
+  st.cap = st.capw = ptx::smem_u32(&sm.cap[0][is_epi ? row_in_unit : 0]);
 
   if (n_tiles > 0) {  // CTA-uniform
     if (warp == 1 && lane == 0) {
@@ -333,7 +373,7 @@ score_kernel(const ImageDev* __restrict__ images, const Task* __restrict__ tasks
       for (int i = 0; i < 2; i++) { ptx::mbar_init(&sm.bar_accfull[i], 1); ptx::mbar_init(&sm.bar_accempty[i], kEpiWarps); }
       ptx::fence_mbar_init();
     }
-    if (warp == 2) ptx::tmem_alloc_512(&sm.tmem_base);
+    if (warp == 2) ptx::tmem_alloc<kAccCols>(&sm.tmem_base);
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
@@ -342,10 +382,10 @@ score_kernel(const ImageDev* __restrict__ images, const Task* __restrict__ tasks
     if (warp == 0) {
       if (lane == 0) {
         // ---- TMA producer ------------------------------------------------------------------
-        const uint8_t* rowop = reinterpret_cast<const uint8_t*>(B.rowop) + (size_t)rb * 2 * kTileBytes;
-        ptx::mbar_expect_tx(&sm.bar_a, 2 * kTileBytes);
-        ptx::bulk_g2s(sm.a[0], rowop, kTileBytes, &sm.bar_a);
-        ptx::bulk_g2s(sm.a[1], rowop + kTileBytes, kTileBytes, &sm.bar_a);
+        const uint8_t* rowop = reinterpret_cast<const uint8_t*>(B.rowop) + (size_t)rb * 2 * kOpTileBytes;
+        ptx::mbar_expect_tx(&sm.bar_a, 2 * kOpTileBytes);
+        ptx::bulk_g2s(sm.a[0], rowop, kOpTileBytes, &sm.bar_a);
+        ptx::bulk_g2s(sm.a[1], rowop + kOpTileBytes, kOpTileBytes, &sm.bar_a);
         const uint8_t* colop = reinterpret_cast<const uint8_t*>(A.colop);
         for (uint32_t i = 0; i < n_tiles; i++) {
           const uint32_t stg = i % kStages, use = i / kStages;
@@ -369,10 +409,10 @@ score_kernel(const ImageDev* __restrict__ images, const Task* __restrict__ tasks
           const uint64_t bdesc = ptx::umma_desc_sw128(ptx::smem_u32(sm.b[stg]));
 #pragma unroll
           for (int k = 0; k < kKPad / 16; k++)  // +32 B per K step inside the 128 B swizzle row
-            ptx::mma_f16_ss(tmem + acc * 256, adesc0 + 2 * k, bdesc + 2 * k, idesc, k > 0);
+            ptx::mma_f16_ss(tmem + acc * (2 * kTileCols), adesc0 + 2 * k, bdesc + 2 * k, idesc, k > 0);
 #pragma unroll
           for (int k = 0; k < kKPad / 16; k++)
-            ptx::mma_f16_ss(tmem + acc * 256 + 128, adesc1 + 2 * k, bdesc + 2 * k, idesc, k > 0);
+            ptx::mma_f16_ss(tmem + acc * (2 * kTileCols) + kTileCols, adesc1 + 2 * k, bdesc + 2 * k, idesc, k > 0);
           ptx::mma_commit(&sm.bar_bempty[stg]);
           ptx::mma_commit(&sm.bar_accfull[acc]);
         }
@@ -383,12 +423,16 @@ score_kernel(const ImageDev* __restrict__ images, const Task* __restrict__ tasks
       const float two_eps = 2.f * task_eps(A.meta, B.meta);
       float* dump_row = kDump ? dump + (size_t)row_in_unit * dump_ld : nullptr;
       unsigned long long scored = 0;
+      // this thread's TMEM window: lane = its row, first column of its row half.  Kept opaque so
+      // the compiler holds it in a register instead of rebuilding it from the thread id per chunk.
+      uint32_t tmem_lane = tmem + (((warp & 3) * 32) << 16) + half * kTileCols;
+      asm volatile("" : "+r"(tmem_lane));
       for (uint32_t i = 0; i < n_tiles; i++) {
         const uint32_t acc = i & 1;
         const uint32_t cb = (tile0 + i) * kTileCols;
         ptx::mbar_wait(&sm.bar_accfull[acc], (i >> 1) & 1);
         ptx::tc_fence_after();
-        const uint32_t taddr = tmem + (((warp & 3) * 32) << 16) + acc * 256 + half * 128;
+        const uint32_t taddr = tmem_lane + acc * (2 * kTileCols);
         const bool needed = kProbe != 2 && (kDump || (cb < w_cmax && cb + kTileCols > w_cmin));  // warp-uniform
         if (!needed) {
           ptx::tc_fence_before();
@@ -412,13 +456,13 @@ score_kernel(const ImageDev* __restrict__ images, const Task* __restrict__ tasks
     __syncthreads();
     if (warp == 2) {
       ptx::tc_fence_after();
-      ptx::tmem_dealloc_512(tmem);
+      ptx::tmem_dealloc<kAccCols>(tmem);
     }
   }
 
   if (is_epi && s < B.n) {
     // Final list: the entries above the final threshold.
-    uint32_t cnt = st.ovf ? 0u : cap_compress(st.cap, st.cnt, st.thr);
+    uint32_t cnt = st.ovf ? 0u : cap_compress(st.cap, (st.capw - st.cap) / kCapStride, st.thr);
     uint32_t trunc = 0;
     if (cnt > (uint32_t)kTopK) {
       cap_select_top(st.cap, cnt);
