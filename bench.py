@@ -68,7 +68,7 @@ def run_reference(list_path, dist, ratio, threads):
     res = oracle.run_ref_binary([list_path, "-o", out, "-d", dist, "-d2", ratio], threads=threads)
     wall = time.time() - t0
     # the reference prints " : <seconds>s" after each phase; the third one is "Pairing" (match.cpp:655)
-    secs = [float(x) for x in re.findall(r"^ : ([0-9.eE+-]+)s", res.stdout, flags=re.M)]
+    secs = [float(x) for x in re.findall(r" : ([0-9.eE+-]+)s$", res.stdout, flags=re.M)]
     pairing = secs[2] if len(secs) >= 3 else wall
     # Loaded (phantom-inclusive, match.cpp:179-208) keypoint counts come from the pairs.bin the reference
     # wrote: its per-image stdout lines are printed from OpenMP threads without a lock and interleave.

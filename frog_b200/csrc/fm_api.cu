@@ -115,11 +115,8 @@ void fm_destroy(fm_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
-  for (auto& im : c->images) {
-    im.desc.release(); im.scale.release(); im.lap.release();
-    im.fast.release();
-  }
-  DevBuf* bufs[] = {&c->d_images, &c->d_metas, &c->d_meta_blob, &c->d_rowres, &c->d_chunk_count, &c->d_chunk_out,
+  c->arena.release();
+  DevBuf* bufs[] = {&c->s_keys, &c->s_keys_sorted, &c->s_idx, &c->s_norm2, &c->s_sort, &c->d_images, &c->d_metas, &c->d_meta_blob, &c->d_rowres, &c->d_chunk_count, &c->d_chunk_out,
                     &c->d_totals, &c->d_bands, &c->d_cands, &c->d_redo, &c->d_taskinfo, &c->cache_out, &c->cache_counts};
   for (auto* b : bufs) b->release();
   if (c->cache_pinned) cudaFreeHost(c->cache_pinned);
@@ -149,11 +146,12 @@ int fm_synchronize(fm_ctx* c) {
 
 int fm_clear_images(fm_ctx* c) {
   if (!c) return FM_ERR_INVALID;
-  for (auto& im : c->images) im.valid = false;
+  for (auto& im : c->images) { im.valid = false; im.slab = nullptr; im.slab_bytes = 0; }
   c->images_dirty = true;
   c->dim = 0;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
+  c->arena.reset();
   c->ev_prep.reset();
   return FM_OK;
 }
@@ -176,24 +174,42 @@ int fm_upload_image(fm_ctx* c, uint32_t img, const float* desc, const float* sca
   if (img >= c->images.size()) c->images.resize(img + 1);
   if (img >= c->h_images.size()) c->h_images.resize(img + 1, ImageDev{});
   Image& im = c->images[img];
-  FM_CUDA(c, im.desc.ensure((size_t)n * d * sizeof(float)));
-  FM_CUDA(c, im.scale.ensure((size_t)n * sizeof(float)));
-  FM_CUDA(c, im.lap.ensure((size_t)n * sizeof(float)));
+  // One slab per image: desc | scale | lap | perm | scale_sorted | rowop | colop (1 KB aligned pieces).
+  auto pad = [](size_t x) { return (x + 1023) & ~(size_t)1023; };
+  const uint32_t n_pad = (n + 255u) & ~255u;  // rows are consumed 256 at a time, columns 64
+  const size_t b_desc = pad((size_t)n * d * sizeof(float)), b_vec = pad((size_t)std::max(n, 1u) * sizeof(float));
+  const size_t b_op = d == (uint32_t)kD ? pad((size_t)n_pad * kKPad * sizeof(__half)) : 0;
+  const size_t need = b_desc + 4 * b_vec + 2 * b_op + 1024;
+  if (!im.slab || im.slab_bytes < need) {  // a re-upload that fits reuses the image's slab
+    void* p = nullptr;
+    FM_CUDA(c, c->arena.alloc(need, &p));
+    im.slab = p;
+    im.slab_bytes = need;
+  }
+  char* base = static_cast<char*>(im.slab);
+  float* d_desc = reinterpret_cast<float*>(base);
+  float* d_scale = reinterpret_cast<float*>(base + b_desc);
+  float* d_lap = reinterpret_cast<float*>(base + b_desc + b_vec);
   if (n) {
-    FM_CUDA(c, cudaMemcpyAsync(im.desc.p, desc, (size_t)n * d * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-    FM_CUDA(c, cudaMemcpyAsync(im.scale.p, scale, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-    FM_CUDA(c, cudaMemcpyAsync(im.lap.p, lap, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    FM_CUDA(c, cudaMemcpyAsync(d_desc, desc, (size_t)n * d * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    FM_CUDA(c, cudaMemcpyAsync(d_scale, scale, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    FM_CUDA(c, cudaMemcpyAsync(d_lap, lap, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
   }
   im.valid = true;
   im.n = n;
   im.d = d;
   ImageDev& v = c->h_images[img];
   v = ImageDev{};
-  v.desc = im.desc.as<float>();
-  v.scale = im.scale.as<float>();
-  v.lap = im.lap.as<float>();
+  v.desc = d_desc;
+  v.scale = d_scale;
+  v.lap = d_lap;
   v.n = n;
   v.d = d;
+  v.n_pad = n_pad;
+  v.perm = reinterpret_cast<uint32_t*>(base + b_desc + 2 * b_vec);
+  v.scale_sorted = reinterpret_cast<float*>(base + b_desc + 3 * b_vec);
+  v.rowop = b_op ? reinterpret_cast<__half*>(base + b_desc + 4 * b_vec) : nullptr;
+  v.colop = b_op ? reinterpret_cast<__half*>(base + b_desc + 4 * b_vec + b_op) : nullptr;
   {
     Span sp(&c->ev_prep, c->stream, kPhPrep);
     cudaError_t e = fast_prepare_image(c, img);

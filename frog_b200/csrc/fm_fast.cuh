@@ -46,7 +46,8 @@ inline cudaError_t ensure_metas(fm_ctx* c, uint32_t n_images) {
   return cudaSuccess;
 }
 
-// Build the sorted / FP16 tensors of image `img` (already copied to im.desc/scale/lap).
+// Build the sorted / FP16 tensors of image `img`; desc/scale/lap were already copied to the image's
+// slab, perm/scale_sorted/rowop/colop point into it (fm_upload_image laid the slab out).
 inline cudaError_t fast_prepare_image(fm_ctx* c, uint32_t img) {
   Image& im = c->images[img];
   ImageDev& v = c->h_images[img];
@@ -56,47 +57,32 @@ inline cudaError_t fast_prepare_image(fm_ctx* c, uint32_t img) {
   v.meta = meta;
   if ((e = cudaMemsetAsync(meta, 0, sizeof(ImageMeta), c->stream)) != cudaSuccess) return e;
   const uint32_t n = im.n;
-  const uint32_t n_pad = (n + 255u) & ~255u;  // rows are consumed 256 at a time, columns 128
-  v.n_pad = n_pad;
-  FastImageBufs& f = im.fast;
-  if ((e = f.keys.ensure((size_t)std::max(n, 1u) * 8)) != cudaSuccess) return e;
-  if ((e = f.keys_sorted.ensure((size_t)std::max(n, 1u) * 8)) != cudaSuccess) return e;
-  if ((e = f.idx.ensure((size_t)std::max(n, 1u) * 4)) != cudaSuccess) return e;
-  if ((e = f.perm.ensure((size_t)std::max(n, 1u) * 4)) != cudaSuccess) return e;  // sorted position -> original id
-  if ((e = f.scale_sorted.ensure((size_t)std::max(n, 1u) * 4)) != cudaSuccess) return e;
-  if ((e = f.norm2.ensure((size_t)std::max(n, 1u) * 4)) != cudaSuccess) return e;
-  v.perm = f.perm.as<uint32_t>();
-  v.scale_sorted = f.scale_sorted.as<float>();
-  v.rowop = nullptr;
-  v.colop = nullptr;
   if (n == 0) {
     ImageMeta m{};
     for (int k = 0; k <= kMaxClasses; k++) m.class_begin[k] = 0;
     return cudaMemcpyAsync(meta, &m, sizeof m, cudaMemcpyHostToDevice, c->stream);
   }
-  prep_keys_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(im.desc.as<float>(), im.scale.as<float>(), im.lap.as<float>(),
-                                                          n, im.d, meta, f.keys.as<unsigned long long>(),
-                                                          f.idx.as<uint32_t>(), f.norm2.as<float>());
+  if ((e = c->s_keys.ensure((size_t)n * 8)) != cudaSuccess) return e;
+  if ((e = c->s_keys_sorted.ensure((size_t)n * 8)) != cudaSuccess) return e;
+  if ((e = c->s_idx.ensure((size_t)n * 4)) != cudaSuccess) return e;
+  if ((e = c->s_norm2.ensure((size_t)n * 4)) != cudaSuccess) return e;
+  unsigned long long* keys = c->s_keys.as<unsigned long long>();
+  unsigned long long* keys_sorted = c->s_keys_sorted.as<unsigned long long>();
+  uint32_t* perm = const_cast<uint32_t*>(v.perm);
+  prep_keys_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(v.desc, v.scale, v.lap, n, im.d, meta, keys,
+                                                          c->s_idx.as<uint32_t>(), c->s_norm2.as<float>());
   size_t tmp_bytes = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, f.keys.as<unsigned long long>(), f.keys_sorted.as<unsigned long long>(),
-                                  f.idx.as<uint32_t>(), f.perm.as<uint32_t>(), (int)n, 0, 64, c->stream);
-  if ((e = f.sort_tmp.ensure(tmp_bytes)) != cudaSuccess) return e;
-  e = cub::DeviceRadixSort::SortPairs(f.sort_tmp.p, tmp_bytes, f.keys.as<unsigned long long>(),
-                                      f.keys_sorted.as<unsigned long long>(), f.idx.as<uint32_t>(), f.perm.as<uint32_t>(),
-                                      (int)n, 0, 64, c->stream);
+  cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, keys_sorted, c->s_idx.as<uint32_t>(), perm, (int)n, 0, 64, c->stream);
+  if ((e = c->s_sort.ensure(tmp_bytes)) != cudaSuccess) return e;
+  e = cub::DeviceRadixSort::SortPairs(c->s_sort.p, tmp_bytes, keys, keys_sorted, c->s_idx.as<uint32_t>(), perm, (int)n, 0, 64,
+                                      c->stream);
   if (e != cudaSuccess) return e;
-  prep_finish_kernel<<<1, 1024, 0, c->stream>>>(f.keys_sorted.as<unsigned long long>(), n, im.d, meta,
-                                               f.scale_sorted.as<float>());
+  prep_finish_kernel<<<1, 1024, 0, c->stream>>>(keys_sorted, n, im.d, meta, const_cast<float*>(v.scale_sorted));
   if (im.d == (uint32_t)kD) {
-    const size_t op_bytes = (size_t)n_pad * kKPad * sizeof(__half);
-    if ((e = f.rowop.ensure(op_bytes)) != cudaSuccess) return e;
-    if ((e = f.colop.ensure(op_bytes)) != cudaSuccess) return e;
-    v.rowop = f.rowop.as<__half>();
-    v.colop = f.colop.as<__half>();
-    const uint32_t threads = n_pad * 8;
-    prep_pack_kernel<<<(threads + 255) / 256, 256, 0, c->stream>>>(im.desc.as<float>(), f.norm2.as<float>(),
-                                                                  f.perm.as<uint32_t>(), n, n_pad,
-                                                                  f.rowop.as<uint8_t>(), f.colop.as<uint8_t>());
+    const uint32_t threads = v.n_pad * 8;
+    prep_pack_kernel<<<(threads + 255) / 256, 256, 0, c->stream>>>(
+        v.desc, c->s_norm2.as<float>(), perm, n, v.n_pad, reinterpret_cast<uint8_t*>(const_cast<__half*>(v.rowop)),
+        reinterpret_cast<uint8_t*>(const_cast<__half*>(v.colop)));
   }
   return cudaGetLastError();
 }

@@ -74,20 +74,39 @@ struct Span {
   }
 };
 
-// Device tensors of one image on the tensor-core path (see ImageDev in fm_common.cuh).
-struct FastImageBufs {
-  DevBuf keys, keys_sorted, idx, perm, scale_sorted, norm2, rowop, colop, sort_tmp;
+// Bump allocator for the per-image device tensors: cudaMalloc costs ~0.1-1 ms a call, a 200-image
+// group needs 1400 tensors.  Chunks are kept across fm_clear_images() and reused.
+struct Arena {
+  static constexpr size_t kChunk = (size_t)256 << 20;
+  std::vector<DevBuf> chunks;
+  size_t cur = 0, off = 0;
+  cudaError_t alloc(size_t bytes, void** out) {
+    bytes = (bytes + 1023) & ~(size_t)1023;  // operand tiles want 1 KB alignment
+    while (cur < chunks.size() && off + bytes > chunks[cur].cap) { cur++; off = 0; }
+    if (cur == chunks.size()) {
+      chunks.emplace_back();
+      cudaError_t e = chunks.back().ensure(std::max(bytes, kChunk));
+      if (e != cudaSuccess) { chunks.pop_back(); return e; }
+      off = 0;
+    }
+    *out = static_cast<char*>(chunks[cur].p) + off;
+    off += bytes;
+    return cudaSuccess;
+  }
+  void reset() { cur = 0; off = 0; }
   void release() {
-    keys.release(); keys_sorted.release(); idx.release(); perm.release(); scale_sorted.release();
-    norm2.release(); rowop.release(); colop.release(); sort_tmp.release();
+    for (auto& c : chunks) c.release();
+    chunks.clear();
+    reset();
   }
 };
 
+// Device tensors of one image (see ImageDev in fm_common.cuh); all of them live in one arena slab.
 struct Image {
   bool valid = false;
   uint32_t n = 0, d = 0;
-  DevBuf desc, scale, lap;
-  FastImageBufs fast;
+  void* slab = nullptr;
+  size_t slab_bytes = 0;
 };
 
 }  // namespace fm
@@ -100,6 +119,8 @@ struct fm_ctx {
   std::vector<fm::ImageDev> h_images;
   std::vector<fm::ImageMeta> h_metas;
   fm::DevBuf d_images, d_metas;
+  fm::Arena arena;                                            // per-image tensors
+  fm::DevBuf s_keys, s_keys_sorted, s_idx, s_norm2, s_sort;  // prep scratch, reused by every upload (stream-ordered)
   uint32_t metas_cap = 0;
   bool images_dirty = true;
   uint32_t dim = 0;

@@ -197,45 +197,77 @@ __device__ __noinline__ uint32_t cap_make_room(uint32_t cap, uint32_t capw, floa
   return cap + cnt * kCapStride;
 }
 
-// 16 consecutive columns of one row.  kMasked: columns outside [lo, hi) are gated out.
-// Fast path (every chunk, branch-free): 3-input max tree, the two largest chunk maxima, the
-// capture threshold, one compare.  The slow path is entered by the WARP when any of its 32 rows
-// has a column above its threshold; every branch in it is warp-uniform (votes) and the per-row
-// work is predicated, so lanes never diverge.
-template <bool kMasked, int kProbe>
-__device__ __forceinline__ void score_chunk(const uint32_t (&r)[16], uint32_t col0, uint32_t lo, uint32_t width,
-                                            RowScan& st, float two_eps) {
-  constexpr uint32_t kAll = 0xffffffffu;
-  constexpr uint32_t kFullAt = (uint32_t)(kCapSlots - 3) * kCapStride;  // fewer than 3 free slots beyond this
-  float f[16];
+// Max tree of 16 consecutive columns of one row: five 3-column nodes, the 16th column, their maximum.
+struct ChunkMax {
+  float m0, m1, m2, m3, m4, m;
+};
+
+// kMasked: columns outside [lo, lo + width) are gated out (band-edge tiles only).
+template <bool kMasked>
+__device__ __forceinline__ ChunkMax chunk_max(const uint32_t (&r)[16], uint32_t col0, uint32_t lo, uint32_t width,
+                                              float (&f)[16]) {
 #pragma unroll
   for (int e = 0; e < 16; e++) {
     f[e] = __uint_as_float(r[e]);
     if (kMasked) f[e] = ((col0 + e) - lo < width) ? f[e] : -INFINITY;
   }
-  const float m0 = max3(f[0], f[1], f[2]), m1 = max3(f[3], f[4], f[5]), m2 = max3(f[6], f[7], f[8]);
-  const float m3 = max3(f[9], f[10], f[11]), m4 = max3(f[12], f[13], f[14]);
-  const float m = fmaxf(max3(m0, m1, m2), max3(m3, m4, f[15]));
-  const float second = fminf(st.g1, m);
-  st.g1 = fmaxf(st.g1, m);
-  st.g2 = fmaxf(st.g2, second);
+  ChunkMax c;
+  c.m0 = max3(f[0], f[1], f[2]);
+  c.m1 = max3(f[3], f[4], f[5]);
+  c.m2 = max3(f[6], f[7], f[8]);
+  c.m3 = max3(f[9], f[10], f[11]);
+  c.m4 = max3(f[12], f[13], f[14]);
+  c.m = fmaxf(max3(c.m0, c.m1, c.m2), max3(c.m3, c.m4, f[15]));
+  return c;
+}
+
+// Second largest of {h} U nodes of c, folded into (h, sec): h = running maximum.
+__device__ __forceinline__ void fold_second(const ChunkMax& c, float f15, float& h, float& sec) {
+  sec = fmaxf(sec, fminf(h, c.m0)); h = fmaxf(h, c.m0);
+  sec = fmaxf(sec, fminf(h, c.m1)); h = fmaxf(h, c.m1);
+  sec = fmaxf(sec, fminf(h, c.m2)); h = fmaxf(h, c.m2);
+  sec = fmaxf(sec, fminf(h, c.m3)); h = fmaxf(h, c.m3);
+  sec = fmaxf(sec, fminf(h, c.m4)); h = fmaxf(h, c.m4);
+  sec = fmaxf(sec, fminf(h, f15));  h = fmaxf(h, f15);
+}
+
+// 32 consecutive columns (two TMEM loads) of one row.
+// Fast path (every pair, branch-free): two 3-input max trees, the two largest chunk maxima seen so
+// far, the capture threshold, one compare, one warp vote.  The slow path is entered by the WARP
+// when any of its 32 rows has a column above its threshold: the twelve node votes are taken up
+// front (independent, so their latencies overlap), every branch is warp-uniform and the per-row
+// captures are predicated stores, so lanes never diverge.
+template <bool kMasked, int kProbe>
+__device__ __forceinline__ void score_pair(const uint32_t (&ra)[16], const uint32_t (&rb)[16], uint32_t col0, uint32_t lo,
+                                           uint32_t width, RowScan& st, float two_eps) {
+  constexpr uint32_t kAll = 0xffffffffu;
+  constexpr uint32_t kFullAt = (uint32_t)(kCapSlots - 3) * kCapStride;  // fewer than 3 free slots beyond this
+  float fa[16], fb[16];
+  const ChunkMax a = chunk_max<kMasked>(ra, col0, lo, width, fa);
+  const ChunkMax b = chunk_max<kMasked>(rb, col0 + 16, lo, width, fb);
+  const float hi = fmaxf(a.m, b.m), lw = fminf(a.m, b.m);
+  // top two of {g1, g2, hi, lw} (g1 >= g2, hi >= lw)
+  const float g2n = max3(st.g2, lw, fminf(st.g1, hi));
+  st.g1 = fmaxf(st.g1, hi);
+  st.g2 = g2n;
   if (kProbe != 1) st.thr = st.g2 - two_eps;
   float th = st.thr;
-  if (__any_sync(kAll, m > th)) {
-    if (kProbe != 1 && __any_sync(kAll, m > th && st.g2 == -INFINITY)) {
-      // First scored chunk of a row: seed the threshold with the second largest of the six node
-      // maxima (disjoint column sets, so it cannot exceed the row's second-best score) instead
-      // of capturing all 16 columns against thr = -inf.
-      float h = m0, sec = -INFINITY;
-      sec = fmaxf(sec, fminf(h, m1)); h = fmaxf(h, m1);
-      sec = fmaxf(sec, fminf(h, m2)); h = fmaxf(h, m2);
-      sec = fmaxf(sec, fminf(h, m3)); h = fmaxf(h, m3);
-      sec = fmaxf(sec, fminf(h, m4)); h = fmaxf(h, m4);
-      sec = fmaxf(sec, fminf(h, f[15]));
+  if (__any_sync(kAll, hi > th)) {
+    if (kProbe != 1 && __any_sync(kAll, hi > th && st.g2 == -INFINITY)) {
+      // First scored columns of a row: seed the threshold with the second largest of the twelve
+      // node maxima (disjoint column sets, so it cannot exceed the row's second-best score)
+      // instead of capturing every column against thr = -inf.
+      float h = -INFINITY, sec = -INFINITY;
+      fold_second(a, fa[15], h, sec);
+      fold_second(b, fb[15], h, sec);
       const bool seed = st.g2 == -INFINITY;
       st.g2 = seed ? sec : st.g2;
       st.thr = th = seed ? sec - two_eps : th;
     }
+    const bool va0 = __any_sync(kAll, a.m0 > th), va1 = __any_sync(kAll, a.m1 > th), va2 = __any_sync(kAll, a.m2 > th);
+    const bool va3 = __any_sync(kAll, a.m3 > th), va4 = __any_sync(kAll, a.m4 > th), va5 = __any_sync(kAll, fa[15] > th);
+    const bool vb0 = __any_sync(kAll, b.m0 > th), vb1 = __any_sync(kAll, b.m1 > th), vb2 = __any_sync(kAll, b.m2 > th);
+    const bool vb3 = __any_sync(kAll, b.m3 > th), vb4 = __any_sync(kAll, b.m4 > th), vb5 = __any_sync(kAll, fb[15] > th);
 #define FM_ROOM(mk)                                                                  \
     if (__any_sync(kAll, (mk) > th && st.capw - st.cap > kFullAt)) {                   \
       if ((mk) > th && st.capw - st.cap > kFullAt) {                                   \
@@ -244,46 +276,43 @@ __device__ __forceinline__ void score_chunk(const uint32_t (&r)[16], uint32_t co
         st.capw = w & ~1u;                                                             \
       }                                                                                \
     }
-#define FM_TRY(e) cap_append_if_above(st.capw, f[e], th, col0 + (e))
-#define FM_NODE(mk, e0, e1, e2)            \
-    if (__any_sync(kAll, (mk) > th)) {       \
-      FM_ROOM(mk)                            \
-      FM_TRY(e0); FM_TRY(e1); FM_TRY(e2);    \
+#define FM_TRY(f, base, e) cap_append_if_above(st.capw, f[e], th, col0 + (base) + (e))
+#define FM_NODE(v, mk, f, base, e0, e1, e2)                          \
+    if (v) {                                                           \
+      FM_ROOM(mk)                                                      \
+      FM_TRY(f, base, e0); FM_TRY(f, base, e1); FM_TRY(f, base, e2);   \
     }
-    FM_NODE(m0, 0, 1, 2)
-    FM_NODE(m1, 3, 4, 5)
-    FM_NODE(m2, 6, 7, 8)
-    FM_NODE(m3, 9, 10, 11)
-    FM_NODE(m4, 12, 13, 14)
-    if (__any_sync(kAll, f[15] > th)) {
-      FM_ROOM(f[15])
-      FM_TRY(15);
-    }
+    FM_NODE(va0, a.m0, fa, 0, 0, 1, 2)
+    FM_NODE(va1, a.m1, fa, 0, 3, 4, 5)
+    FM_NODE(va2, a.m2, fa, 0, 6, 7, 8)
+    FM_NODE(va3, a.m3, fa, 0, 9, 10, 11)
+    FM_NODE(va4, a.m4, fa, 0, 12, 13, 14)
+    if (va5) { FM_ROOM(fa[15]) FM_TRY(fa, 0, 15); }
+    FM_NODE(vb0, b.m0, fb, 16, 0, 1, 2)
+    FM_NODE(vb1, b.m1, fb, 16, 3, 4, 5)
+    FM_NODE(vb2, b.m2, fb, 16, 6, 7, 8)
+    FM_NODE(vb3, b.m3, fb, 16, 9, 10, 11)
+    FM_NODE(vb4, b.m4, fb, 16, 12, 13, 14)
+    if (vb5) { FM_ROOM(fb[15]) FM_TRY(fb, 16, 15); }
 #undef FM_NODE
 #undef FM_TRY
 #undef FM_ROOM
   }
 }
 
+// One 64-column accumulator tile of one row: two pairs of TMEM loads.
 template <bool kMasked, bool kDump, int kProbe>
 __device__ __forceinline__ void score_tile(uint32_t taddr, uint32_t cb, uint32_t lo, uint32_t width, RowScan& st,
                                            float two_eps, uint64_t* bar_release, float* dump_row) {
   uint32_t ra[16], rb[16];
-  ptx::tmem_ld16(ra, taddr);
-  ptx::tmem_ld_wait(ra);
-  // Rolled on purpose: one copy of the capture branches stays resident in the instruction cache.
+  // Rolled on purpose: one copy of the capture code stays resident in the instruction cache.
 #pragma unroll 1
   for (int c = 0; c < kTileCols / 16; c += 2) {
-    ptx::tmem_ld16(rb, taddr + (c + 1) * 16);  // next 16 columns in flight while these are scanned
-    if (kDump) {
-#pragma unroll
-      for (int e = 0; e < 16; e++) dump_row[cb + c * 16 + e] = __uint_as_float(ra[e]);
-    }
-    score_chunk<kMasked, kProbe>(ra, cb + c * 16, lo, width, st, two_eps);
+    ptx::tmem_ld16(ra, taddr + c * 16);
+    ptx::tmem_ld16(rb, taddr + (c + 1) * 16);
+    ptx::tmem_ld_wait(ra);
     ptx::tmem_ld_wait(rb);
-    if (c + 2 < kTileCols / 16) {
-      ptx::tmem_ld16(ra, taddr + (c + 2) * 16);
-    } else {
+    if (c + 2 >= kTileCols / 16) {
       // every column of this accumulator is now in registers: hand it back to the MMA warp
       ptx::tc_fence_before();
       __syncwarp();
@@ -291,10 +320,12 @@ __device__ __forceinline__ void score_tile(uint32_t taddr, uint32_t cb, uint32_t
     }
     if (kDump) {
 #pragma unroll
-      for (int e = 0; e < 16; e++) dump_row[cb + (c + 1) * 16 + e] = __uint_as_float(rb[e]);
+      for (int e = 0; e < 16; e++) {
+        dump_row[cb + c * 16 + e] = __uint_as_float(ra[e]);
+        dump_row[cb + (c + 1) * 16 + e] = __uint_as_float(rb[e]);
+      }
     }
-    score_chunk<kMasked, kProbe>(rb, cb + (c + 1) * 16, lo, width, st, two_eps);
-    if (c + 2 < kTileCols / 16) ptx::tmem_ld_wait(ra);
+    score_pair<kMasked, kProbe>(ra, rb, cb + c * 16, lo, width, st, two_eps);
   }
 }
 

@@ -43,25 +43,47 @@ struct GpuJob {
   fm_result* res = nullptr;
   fm_stats stats{};
   string error;
+  double create_s = 0, upload_s = 0, match_s = 0;  // host wall-clock of the three phases of this job
 };
+
+double now_s() {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+// CUDA start-up (driver initialisation + context + module load) takes of the order of a second per
+// process; it is started on background threads while the keypoint files are still being parsed.
+void create_context(GpuJob& job) {
+  const double t0 = now_s();
+  if (fm_create(job.device, &job.ctx) != FM_OK) job.error = fm_last_error(nullptr);
+  job.create_s = now_s() - t0;
+}
 
 void run_gpu_job(GpuJob& job, const std::vector<fmio::KeypointSet>& images, const std::vector<std::pair<int, int>>& indices,
                  float dist, float ratio, uint32_t flags) {
-  if (fm_create(job.device, &job.ctx) != FM_OK) { job.error = fm_last_error(nullptr); return; }
+  if (!job.error.empty()) return;
+  if (!job.ctx) { create_context(job); if (!job.error.empty()) return; }
+  double t0 = now_s();
   std::vector<char> needed(images.size(), 0);
   for (size_t id : job.pair_ids) { needed[indices[id].first] = 1; needed[indices[id].second] = 1; }
+  std::vector<std::vector<float>> keep;  // scale / laplacian columns stay alive until the copies have finished
+  keep.reserve(2 * images.size());
   for (size_t i = 0; i < images.size(); i++) {
     if (!needed[i]) continue;
     const fmio::KeypointSet& k = images[i];
-    std::vector<float> scale(k.n), lap(k.n);
+    keep.emplace_back(k.n);
+    keep.emplace_back(k.n);
+    std::vector<float>&scale = keep[keep.size() - 2], &lap = keep[keep.size() - 1];
     for (uint32_t r = 0; r < k.n; r++) { scale[r] = k.row_head(r)[3]; lap[r] = k.row_head(r)[4]; }
     const uint32_t d = k.d ? k.d : 48;
-    if (fm_upload_image(job.ctx, (uint32_t)i, k.desc.data(), scale.data(), lap.data(), k.n, d) != FM_OK ||
-        fm_synchronize(job.ctx) != FM_OK) {  // scale/lap are temporaries: finish the copy before they die
+    if (fm_upload_image(job.ctx, (uint32_t)i, k.desc.data(), scale.data(), lap.data(), k.n, d) != FM_OK) {
       job.error = fm_last_error(job.ctx);
       return;
     }
   }
+  if (fm_synchronize(job.ctx) != FM_OK) { job.error = fm_last_error(job.ctx); return; }
+  keep.clear();
+  job.upload_s = now_s() - t0;
+  t0 = now_s();
   std::vector<uint32_t> pf(job.pair_ids.size()), ps(job.pair_ids.size());
   for (size_t k = 0; k < job.pair_ids.size(); k++) {
     pf[k] = (uint32_t)indices[job.pair_ids[k]].first;
@@ -72,6 +94,7 @@ void run_gpu_job(GpuJob& job, const std::vector<fmio::KeypointSet>& images, cons
     return;
   }
   fm_get_stats(job.ctx, &job.stats);
+  job.match_s = now_s() - t0;
 }
 
 }  // namespace
@@ -134,6 +157,23 @@ int main(int argc, char* argv[]) {
     return 1;
   }
   if (writePoints) cerr << "match: -p (debug CSV dump) is ignored by the B200 build" << endl;
+
+  // Bring the GPUs up in the background while the keypoint files load (no CPU fallback: a machine
+  // without a CUDA device fails below, before any pairing).
+  int n_dev = 0;
+  const bool have_dev = fm_device_count(&n_dev) == FM_OK && n_dev > 0;
+  const int G_max = have_dev ? std::max(1, gpus > 0 ? std::min(gpus, n_dev) : n_dev) : 0;
+  std::vector<GpuJob> jobs(G_max);
+  std::vector<std::thread> warmers;
+  for (int g = 0; g < G_max; g++) {
+    jobs[g].device = g;
+    warmers.emplace_back(create_context, std::ref(jobs[g]));
+  }
+  auto join_warmers = [&]() { for (auto& t : warmers) if (t.joinable()) t.join(); };
+  struct Joiner {  // early `return`s below must not leave a joinable thread behind
+    std::vector<std::thread>& t;
+    ~Joiner() { for (auto& x : t) if (x.joinable()) x.join(); }
+  } joiner{warmers};
 
   std::vector<std::array<double, 3>> rigids;
   std::vector<string> filenames;
@@ -235,14 +275,16 @@ int main(int argc, char* argv[]) {
   if (target >= nb) { cerr << "match: -targ " << target << " is not a valid image index" << endl; return 1; }
 
   cout << "Pairing... " << endl;
-  int n_dev = 0;
-  if (fm_device_count(&n_dev) != FM_OK || n_dev == 0) {
+  join_warmers();
+  if (!have_dev) {
     cerr << "match: no CUDA device available (" << fm_last_error(nullptr) << "); this build has no CPU path" << endl;
     return 1;
   }
-  int G = gpus > 0 ? std::min(gpus, n_dev) : n_dev;
-  G = std::max(1, std::min<int>(G, std::max<size_t>(indices.size(), 1)));
-  std::vector<GpuJob> jobs(G);
+  const int G = std::max(1, std::min<int>(G_max, std::max<size_t>(indices.size(), 1)));
+  for (int g = G; g < G_max; g++) {  // more GPUs than image pairs: release the surplus contexts
+    if (jobs[g].ctx) fm_destroy(jobs[g].ctx);
+  }
+  jobs.resize(G);
   {
     // longest-processing-time-first sharding of image pairs (independent units, match.cpp:638-652)
     std::vector<size_t> order(indices.size());
@@ -315,7 +357,11 @@ int main(int argc, char* argv[]) {
   if (statsFile) {
     fm_stats tot{};
     float ms_max = 0;
+    double create_s = 0, upload_s = 0, match_s = 0;
     for (auto& j : jobs) {
+      create_s = std::max(create_s, j.create_s);
+      upload_s = std::max(upload_s, j.upload_s);
+      match_s = std::max(match_s, j.match_s);
       tot.descriptor_pairs += j.stats.descriptor_pairs;
       tot.scored_pairs += j.stats.scored_pairs;
       tot.rows += j.stats.rows;
@@ -328,7 +374,8 @@ int main(int argc, char* argv[]) {
     sf << "{\"gpus\": " << G << ", \"image_pairs\": " << indices.size() << ", \"descriptor_pairs\": " << tot.descriptor_pairs
        << ", \"scored_pairs\": " << tot.scored_pairs << ", \"rows\": " << tot.rows << ", \"rows_exact\": " << tot.rows_exact
        << ", \"candidates\": " << tot.candidates << ", \"kernel_launches\": " << tot.kernel_launches
-       << ", \"gpu_ms_max\": " << ms_max << ", \"pairing_s\": " << pairing_s << ", \"matches\": " << sum << "}" << endl;
+       << ", \"gpu_ms_max\": " << ms_max << ", \"pairing_s\": " << pairing_s << ", \"ctx_create_s\": " << create_s
+       << ", \"upload_s\": " << upload_s << ", \"match_call_s\": " << match_s << ", \"matches\": " << sum << "}" << endl;
   }
   for (auto& j : jobs) {
     fm_result_free(j.res);

@@ -66,7 +66,9 @@ int fm_synchronize(fm_ctx* ctx);
  * (match.cpp:39-48, 51-92, 137-208).
  *   desc  : n x d floats, row-major (Point::desc)
  *   scale : n floats (Point::scale)          lap : n floats (Point::laplacianSign)
- * Host memory, pageable or pinned.  Re-uploading an index replaces the image.  All images of one
+ * Host memory, pageable or pinned; copies are queued on the context's stream, so PINNED buffers
+ * must stay valid until the next fm_synchronize() / fm_match() on this context (pageable buffers
+ * may be reused as soon as the call returns).  Re-uploading an index replaces the image.  All images of one
  * context must share d (match.cpp:575 prints one descriptor size for the group).
  */
 int fm_upload_image(fm_ctx* ctx, uint32_t img, const float* desc, const float* scale, const float* lap,
