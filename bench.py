@@ -43,6 +43,16 @@ WORKLOADS = {
 FLOP_PER_PAIR = 96.0  # 2 * D, D = 48
 
 
+def measured_traffic(workload):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one scoring-kernel launch, from the committed ncu capture
+    of this workload (profiles/); None for workloads that were not captured."""
+    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if not os.path.exists(p):
+        return None
+    j = json.load(open(p))
+    return float(j["dram_bytes_read"] + j["dram_bytes_write"]) if j.get("workload") == workload else None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -312,7 +322,7 @@ def bench_ours(args):
     total_pairs, h2d_all, d2h_all, launches, matches_all = agg.tolist()
 
     if rank == 0:
-        peak_tf, _, which = peaks()
+        peak_tf, peak_gbs, which = peaks()
         sc_ms = float(np.mean([s["ms_score"] / max(1, s["score_launches"]) for s in stats]))
         pairs_per_launch = float(np.mean([s["descriptor_pairs"] / max(1, s["score_launches"]) for s in stats]))
         scored_per_launch = float(np.mean([s["scored_pairs"] / max(1, s["score_launches"]) for s in stats]))
@@ -332,10 +342,16 @@ def bench_ours(args):
                     "h2d_bytes_per_step": h2d_all, "d2h_bytes_per_step": d2h_all, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": achieved / peak_tf, "traffic": None, "peak_source": which + " (cuBLAS bf16 burst)",
+                         "frac": achieved / peak_tf, "traffic": measured_traffic(args.workload), "peak_source": which + " (cuBLAS bf16 burst)",
                          "kernel": "fm::score_kernel<false>", "kernel_ms": sc_ms,
                          "algorithmic_flop_per_launch": FLOP_PER_PAIR * pairs_per_launch,
                          "executed_tflops": executed, "scored_fraction": scored_per_launch / max(1.0, pairs_per_launch)},
+            # stream compaction (HBM-bound): 4 B read per row by each of the count and scatter passes,
+            # 8 B written per match, over the CUDA-event time of the three compaction kernels
+            "compaction": {"bound": "hbm", "unit": "GB/s", "peak": peak_gbs, "peak_source": which,
+                           "achieved": (8.0 * s0["rows"] + 8.0 * matches) / max(s0["ms_compact"] * 1e-3, 1e-12) / 1e9,
+                           "frac": (8.0 * s0["rows"] + 8.0 * matches) / max(s0["ms_compact"] * 1e-3, 1e-12) / 1e9 / peak_gbs,
+                           "kernel_ms": s0["ms_compact"]},
             "phases_ms": {k: s0[k] for k in ("ms_total", "ms_score", "ms_rescore", "ms_exact", "ms_compact", "ms_prep")},
             "rows_exact_frac": s0["rows_exact"] / max(1, s0["rows"]), "candidates_per_row": s0["candidates"] / max(1, s0["rows"]),
             "clocks": clocks,

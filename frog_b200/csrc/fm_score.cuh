@@ -5,11 +5,11 @@
 // against one contiguous range of 64-column tiles of image `first`.  Two CTAs share an SM
 // (256 of the 512 TMEM columns and ~110 KB of shared memory each), so 16 epilogue warps hide each
 // other's latencies and one CTA's prologue / tail overlaps the other's steady state.
-//   warp 0      TMA producer: cp.async.bulk 8 KB pre-swizzled FP16 tiles -> smem ring (mbarrier tx)
+//   warp 0      TMEM allocator, then TMA producer: cp.async.bulk 8 KB pre-swizzled FP16 tiles ->
+//                             smem ring (mbarrier tx)
 //   warp 1      MMA issuer  : tcgen05.mma kind::f16, M=128 N=64 K=16, 4 K-steps x 2 row halves per
 //                             tile, FP32 accumulators double-buffered in TMEM (2 x 2 x 64 columns)
-//   warp 2      TMEM allocator
-//   warps 4..11 epilogue    : tcgen05.ld (TMEM lane == row, so a row's scan over columns is
+//   warps 2..9  epilogue    : tcgen05.ld (TMEM lane == row, so a row's scan over columns is
 //                             thread-local), gate mask on band-edge tiles only, 3-input max tree
 //                             per 16 columns, capture of the few columns above a running
 //                             threshold into a per-row shared-memory list
@@ -32,7 +32,7 @@ constexpr int kTopK = 8;        // candidate slots written per (row, column segm
 constexpr int kCapSlots = 22;  // capture list entries per row in shared memory
 constexpr int kAccCols = 2 * 2 * kTileCols;  // TMEM columns: 2 stages x 2 row halves
 constexpr int kEpiWarps = 8;
-constexpr int kScoreThreads = (4 + kEpiWarps) * 32;
+constexpr int kScoreThreads = (2 + kEpiWarps) * 32;  // warp 0: TMA + TMEM allocator, warp 1: MMA, warps 2..9: epilogue
 
 struct Cand {
   float t;       // approximate score, -inf for an empty slot
@@ -357,9 +357,9 @@ score_kernel(const ImageDev* __restrict__ images, const Task* __restrict__ tasks
   const uint32_t rb = local / segs, seg = local - rb * segs;
 
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const bool is_epi = warp >= 4;
-  // epilogue thread -> row: TMEM sub-partition = warp % 4, accumulator half = (warp - 4) / 4
-  const uint32_t half = is_epi ? (warp - 4) >> 2 : 0;
+  const bool is_epi = warp >= 2;
+  // epilogue thread -> row: TMEM sub-partition = warp % 4 (hardware rule), accumulator half = (warp - 2) / 4
+  const uint32_t half = is_epi ? (warp - 2) >> 2 : 0;
   const uint32_t row_in_unit = half * 128 + (warp & 3) * 32 + lane;
   const uint32_t s = rb * kUnitRows + row_in_unit;
   uint32_t lo = 0, hi = 0;
@@ -404,7 +404,7 @@ score_kernel(const ImageDev* __restrict__ images, const Task* __restrict__ tasks
       for (int i = 0; i < 2; i++) { ptx::mbar_init(&sm.bar_accfull[i], 1); ptx::mbar_init(&sm.bar_accempty[i], kEpiWarps); }
       ptx::fence_mbar_init();
     }
-    if (warp == 2) ptx::tmem_alloc<kAccCols>(&sm.tmem_base);
+    if (warp == 0) ptx::tmem_alloc<kAccCols>(&sm.tmem_base);
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
@@ -485,7 +485,7 @@ score_kernel(const ImageDev* __restrict__ images, const Task* __restrict__ tasks
     }
     ptx::tc_fence_before();
     __syncthreads();
-    if (warp == 2) {
+    if (warp == 0) {
       ptx::tc_fence_after();
       ptx::tmem_dealloc<kAccCols>(tmem);
     }
