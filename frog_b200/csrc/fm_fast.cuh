@@ -138,7 +138,7 @@ inline cudaError_t fast_match_batch(fm_ctx* c, const FastBatchArgs& a) {
     rescore_kernel<<<a.blocks128, 128, 0, c->stream>>>(a.images, a.tasks, a.blk_off, a.n_tasks, a.segs,
                                                        c->d_cands.as<Cand>(), a.thr, a.ratio, a.rowres,
                                                        c->d_redo.as<uint2>(), &a.counters->rescore);
-    exact_rows_kernel<<<c->sm_count * 2, 256, 0, c->stream>>>(a.images, a.tasks, c->d_bands.as<uint2>(), c->d_redo.as<uint2>(),
+    exact_rows_kernel<<<c->sm_count, kRedoThreads, 0, c->stream>>>(a.images, a.tasks, c->d_bands.as<uint2>(), c->d_redo.as<uint2>(),
                                                              &a.counters->rescore, a.thr, a.ratio, a.rowres);
     fold_redo_kernel<<<1, 1, 0, c->stream>>>(a.counters);
   }

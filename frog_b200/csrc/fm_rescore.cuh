@@ -45,6 +45,13 @@ __device__ __forceinline__ void top2_merge_one(float dist, uint32_t j, float& d1
   else if (dist < d2) { d2 = dist; }
 }
 
+__device__ __forceinline__ void top2_merge_sets(float od1, float od2, uint32_t om, float& d1, float& d2, uint32_t& match) {
+  const bool other_wins = od1 < d1 || (od1 == d1 && om < match);
+  const float hi_d1 = fmaxf(d1, od1);  // the larger of the two minima is a second-smallest candidate
+  d2 = fminf(hi_d1, fminf(d2, od2));
+  if (other_wins) { d1 = od1; match = om; }
+}
+
 // One thread per sorted row of the task.
 __global__ void __launch_bounds__(128)
 rescore_kernel(const ImageDev* __restrict__ images, const Task* __restrict__ tasks,
@@ -122,19 +129,23 @@ rescore_kernel(const ImageDev* __restrict__ images, const Task* __restrict__ tas
   if ((threadIdx.x & 31) == 0 && n_eval) atomicAdd(&counters->candidates, (unsigned long long)n_eval);
 }
 
-// Exact redo of queued rows: one warp per row.  Lanes stride over the row's gate interval
+// Exact redo of queued rows: one CTA per row (queued rows are rare -- a handful per million -- so
+// the parallelism has to come from inside the row).  Threads stride over the row's gate interval
 // [lo, hi) of sorted columns (every column outside it fails a reference gate, fm_score.cuh
 // bands_kernel), evaluate the reference's gates and FP32 distance on each, keep an
-// order-independent (d1, lowest original index, d2) and merge across lanes as multisets.
-__global__ void __launch_bounds__(256)
+// order-independent (d1, lowest original index, d2) and merge across lanes / warps as multisets.
+constexpr int kRedoThreads = 512;
+
+__global__ void __launch_bounds__(kRedoThreads)
 exact_rows_kernel(const ImageDev* __restrict__ images, const Task* __restrict__ tasks,
                   const uint2* __restrict__ bands, const uint2* __restrict__ redo_list,
                   const RescoreCounters* __restrict__ counters, float thr, float ratio,
                   uint32_t* __restrict__ rowres) {
-  const uint32_t lane = threadIdx.x & 31;
+  __shared__ float s_d1[kRedoThreads / 32], s_d2[kRedoThreads / 32];
+  __shared__ uint32_t s_m[kRedoThreads / 32];
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned long long n = counters->redo_rows;
-  const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
-  for (unsigned long long w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n; w += warps) {
+  for (unsigned long long w = blockIdx.x; w < n; w += gridDim.x) {
     const uint2 item = redo_list[w];
     const Task task = tasks[item.x];
     const ImageDev A = images[task.col_img];
@@ -151,7 +162,7 @@ exact_rows_kernel(const ImageDev* __restrict__ images, const Task* __restrict__ 
     const float sc = B.scale[row], lp = B.lap[row];
     float d1 = FLT_MAX, d2 = FLT_MAX;
     uint32_t match = 0;
-    for (uint32_t c = band.x + lane; c < band.y; c += 32) {
+    for (uint32_t c = band.x + threadIdx.x; c < band.y; c += kRedoThreads) {
       const uint32_t j = A.perm[c];
       if (lp != A.lap[j]) continue;                    // match.cpp:270
       if (scale_gate_fails(sc, A.scale[j])) continue;  // match.cpp:273-275
@@ -163,12 +174,15 @@ exact_rows_kernel(const ImageDev* __restrict__ images, const Task* __restrict__ 
       const float od1 = __shfl_xor_sync(0xffffffffu, d1, o);
       const float od2 = __shfl_xor_sync(0xffffffffu, d2, o);
       const uint32_t om = __shfl_xor_sync(0xffffffffu, match, o);
-      const bool other_wins = od1 < d1 || (od1 == d1 && om < match);
-      const float hi_d1 = fmaxf(d1, od1);  // the larger of the two minima is a second-smallest candidate
-      d2 = fminf(hi_d1, fminf(d2, od2));
-      if (other_wins) { d1 = od1; match = om; }
+      top2_merge_sets(od1, od2, om, d1, d2, match);
     }
-    if (lane == 0) rowres[task.row_off + row] = accept_rule(d1, d2, thr, ratio) ? match : kNone;
+    if (lane == 0) { s_d1[warp] = d1; s_d2[warp] = d2; s_m[warp] = match; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int k = 1; k < kRedoThreads / 32; k++) top2_merge_sets(s_d1[k], s_d2[k], s_m[k], d1, d2, match);
+      rowres[task.row_off + row] = accept_rule(d1, d2, thr, ratio) ? match : kNone;
+    }
+    __syncthreads();
   }
 }
 

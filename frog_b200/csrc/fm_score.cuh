@@ -176,30 +176,33 @@ __device__ __noinline__ void cap_select_top(uint32_t cap, uint32_t cnt) {
   }
 }
 
-// Predicated append (no branch): if v > thr, store (v, col) at capw and advance capw.
-__device__ __forceinline__ void cap_append_if_above(uint32_t& capw, float v, float thr, uint32_t col) {
+// Predicated append (no branch): if v > thr, store (v, col) at capw (unless the list is full:
+// capw >= cap_end) and advance capw.  A pointer past cap_end afterwards means "overflowed".
+__device__ __forceinline__ void cap_append_if_above(uint32_t& capw, uint32_t cap_end, float v, float thr, uint32_t col) {
   asm volatile(
-      "{\n\t.reg .pred q;\n\t"
+      "{\n\t.reg .pred q, s;\n\t"
       "setp.gt.f32 q, %1, %2;\n\t"
-      "@q st.shared.v2.b32 [%0], {%3, %4};\n\t"
+      "setp.lt.and.u32 s, %0, %6, q;\n\t"
+      "@s st.shared.v2.b32 [%0], {%3, %4};\n\t"
       "@q add.u32 %0, %0, %5;\n\t}"
       : "+r"(capw)
-      : "f"(v), "f"(thr), "r"(__float_as_uint(v)), "r"(col), "n"(kCapStride)
+      : "f"(v), "f"(thr), "r"(__float_as_uint(v)), "r"(col), "n"(kCapStride), "r"(cap_end)
       : "memory");
 }
 
-// Make room for one tree node (3 columns) in a row's capture list: drop the entries the risen
-// threshold has retired.  Returns the new write address; bit 0 set = the list is still full,
-// i.e. the row must be redone by the exact kernel (the list restarts empty).
+// Make room in a row's capture list: drop the entries the risen threshold has retired.  Returns
+// the new write address; bit 0 set = more than half of the list is still live, i.e. the row must
+// be redone by the exact kernel (the list restarts empty).
 __device__ __noinline__ uint32_t cap_make_room(uint32_t cap, uint32_t capw, float thr) {
-  const uint32_t cnt = cap_compress(cap, (capw - cap) / kCapStride, thr);
-  if (cnt > (uint32_t)(kCapSlots - 3)) return cap | 1u;
+  const uint32_t cnt = cap_compress(cap, min((capw - cap) / kCapStride, (uint32_t)kCapSlots), thr);
+  if (cnt > (uint32_t)(kCapSlots / 2)) return cap | 1u;
   return cap + cnt * kCapStride;
 }
 
-// Max tree of 16 consecutive columns of one row: five 3-column nodes, the 16th column, their maximum.
+// Max tree of 16 consecutive columns of one row: five 3-column nodes + the 16th column, two
+// group maxima (columns 0..8 and 9..15) and the chunk maximum.
 struct ChunkMax {
-  float m0, m1, m2, m3, m4, m;
+  float m0, m1, m2, m3, m4, ga, gb, m;
 };
 
 // kMasked: columns outside [lo, lo + width) are gated out (band-edge tiles only).
@@ -217,7 +220,9 @@ __device__ __forceinline__ ChunkMax chunk_max(const uint32_t (&r)[16], uint32_t 
   c.m2 = max3(f[6], f[7], f[8]);
   c.m3 = max3(f[9], f[10], f[11]);
   c.m4 = max3(f[12], f[13], f[14]);
-  c.m = fmaxf(max3(c.m0, c.m1, c.m2), max3(c.m3, c.m4, f[15]));
+  c.ga = max3(c.m0, c.m1, c.m2);
+  c.gb = max3(c.m3, c.m4, f[15]);
+  c.m = fmaxf(c.ga, c.gb);
   return c;
 }
 
@@ -234,14 +239,18 @@ __device__ __forceinline__ void fold_second(const ChunkMax& c, float f15, float&
 // 32 consecutive columns (two TMEM loads) of one row.
 // Fast path (every pair, branch-free): two 3-input max trees, the two largest chunk maxima seen so
 // far, the capture threshold, one compare, one warp vote.  The slow path is entered by the WARP
-// when any of its 32 rows has a column above its threshold: the twelve node votes are taken up
-// front (independent, so their latencies overlap), every branch is warp-uniform and the per-row
-// captures are predicated stores, so lanes never diverge.
+// when any of its 32 rows has a column above its threshold.  It walks the max tree top-down with
+// warp votes -- four 8-column groups, then the 3-column nodes of a group some row hit -- so every
+// branch is warp-uniform, and the per-row captures are predicated stores: lanes never diverge
+// and a typical entry (one row, one column) costs ~45 instructions.
 template <bool kMasked, int kProbe>
 __device__ __forceinline__ void score_pair(const uint32_t (&ra)[16], const uint32_t (&rb)[16], uint32_t col0, uint32_t lo,
                                            uint32_t width, RowScan& st, float two_eps) {
   constexpr uint32_t kAll = 0xffffffffu;
-  constexpr uint32_t kFullAt = (uint32_t)(kCapSlots - 3) * kCapStride;  // fewer than 3 free slots beyond this
+  // An entry may append up to kEntryRoom columns per row without further checks; beyond that the
+  // predicated store is suppressed and the row is marked for the exact kernel.
+  constexpr uint32_t kEntryRoom = 8;
+  constexpr uint32_t kFullAt = (uint32_t)(kCapSlots - kEntryRoom) * kCapStride;
   float fa[16], fb[16];
   const ChunkMax a = chunk_max<kMasked>(ra, col0, lo, width, fa);
   const ChunkMax b = chunk_max<kMasked>(rb, col0 + 16, lo, width, fb);
@@ -264,39 +273,44 @@ __device__ __forceinline__ void score_pair(const uint32_t (&ra)[16], const uint3
       st.g2 = seed ? sec : st.g2;
       st.thr = th = seed ? sec - two_eps : th;
     }
-    const bool va0 = __any_sync(kAll, a.m0 > th), va1 = __any_sync(kAll, a.m1 > th), va2 = __any_sync(kAll, a.m2 > th);
-    const bool va3 = __any_sync(kAll, a.m3 > th), va4 = __any_sync(kAll, a.m4 > th), va5 = __any_sync(kAll, fa[15] > th);
-    const bool vb0 = __any_sync(kAll, b.m0 > th), vb1 = __any_sync(kAll, b.m1 > th), vb2 = __any_sync(kAll, b.m2 > th);
-    const bool vb3 = __any_sync(kAll, b.m3 > th), vb4 = __any_sync(kAll, b.m4 > th), vb5 = __any_sync(kAll, fb[15] > th);
-#define FM_ROOM(mk)                                                                  \
-    if (__any_sync(kAll, (mk) > th && st.capw - st.cap > kFullAt)) {                   \
-      if ((mk) > th && st.capw - st.cap > kFullAt) {                                   \
-        const uint32_t w = cap_make_room(st.cap, st.capw, th);                         \
-        st.ovf |= w & 1u;                                                              \
-        st.capw = w & ~1u;                                                             \
-      }                                                                                \
+    // room for kEntryRoom appends, once per entry
+    if (__any_sync(kAll, hi > th && st.capw - st.cap > kFullAt)) {
+      if (hi > th && st.capw - st.cap > kFullAt) {
+        const uint32_t w = cap_make_room(st.cap, st.capw, th);
+        st.ovf |= w & 1u;
+        st.capw = w & ~1u;
+      }
     }
-#define FM_TRY(f, base, e) cap_append_if_above(st.capw, f[e], th, col0 + (base) + (e))
-#define FM_NODE(v, mk, f, base, e0, e1, e2)                          \
-    if (v) {                                                           \
-      FM_ROOM(mk)                                                      \
-      FM_TRY(f, base, e0); FM_TRY(f, base, e1); FM_TRY(f, base, e2);   \
+    const uint32_t cap_end = st.cap + (uint32_t)kCapSlots * kCapStride;
+    const bool va = __any_sync(kAll, a.ga > th), vb = __any_sync(kAll, a.gb > th);
+    const bool vc = __any_sync(kAll, b.ga > th), vd = __any_sync(kAll, b.gb > th);
+#define FM_TRY(f, base, e) cap_append_if_above(st.capw, cap_end, f[e], th, col0 + (base) + (e))
+#define FM_NODE(mk, f, base, e0, e1, e2) \
+    if (__any_sync(kAll, (mk) > th)) { FM_TRY(f, base, e0); FM_TRY(f, base, e1); FM_TRY(f, base, e2); }
+    if (va) {
+      FM_NODE(a.m0, fa, 0, 0, 1, 2)
+      FM_NODE(a.m1, fa, 0, 3, 4, 5)
+      FM_NODE(a.m2, fa, 0, 6, 7, 8)
     }
-    FM_NODE(va0, a.m0, fa, 0, 0, 1, 2)
-    FM_NODE(va1, a.m1, fa, 0, 3, 4, 5)
-    FM_NODE(va2, a.m2, fa, 0, 6, 7, 8)
-    FM_NODE(va3, a.m3, fa, 0, 9, 10, 11)
-    FM_NODE(va4, a.m4, fa, 0, 12, 13, 14)
-    if (va5) { FM_ROOM(fa[15]) FM_TRY(fa, 0, 15); }
-    FM_NODE(vb0, b.m0, fb, 16, 0, 1, 2)
-    FM_NODE(vb1, b.m1, fb, 16, 3, 4, 5)
-    FM_NODE(vb2, b.m2, fb, 16, 6, 7, 8)
-    FM_NODE(vb3, b.m3, fb, 16, 9, 10, 11)
-    FM_NODE(vb4, b.m4, fb, 16, 12, 13, 14)
-    if (vb5) { FM_ROOM(fb[15]) FM_TRY(fb, 16, 15); }
+    if (vb) {
+      FM_NODE(a.m3, fa, 0, 9, 10, 11)
+      FM_NODE(a.m4, fa, 0, 12, 13, 14)
+      FM_TRY(fa, 0, 15);
+    }
+    if (vc) {
+      FM_NODE(b.m0, fb, 16, 0, 1, 2)
+      FM_NODE(b.m1, fb, 16, 3, 4, 5)
+      FM_NODE(b.m2, fb, 16, 6, 7, 8)
+    }
+    if (vd) {
+      FM_NODE(b.m3, fb, 16, 9, 10, 11)
+      FM_NODE(b.m4, fb, 16, 12, 13, 14)
+      FM_TRY(fb, 16, 15);
+    }
 #undef FM_NODE
 #undef FM_TRY
-#undef FM_ROOM
+    // a row that wanted more than the list holds: its write pointer ran past the end
+    st.ovf |= st.capw > cap_end ? 1u : 0u;
   }
 }
 
@@ -493,7 +507,7 @@ score_kernel(const ImageDev* __restrict__ images, const Task* __restrict__ tasks
 
   if (is_epi && s < B.n) {
     // Final list: the entries above the final threshold.
-    uint32_t cnt = st.ovf ? 0u : cap_compress(st.cap, (st.capw - st.cap) / kCapStride, st.thr);
+    uint32_t cnt = st.ovf ? 0u : cap_compress(st.cap, min((st.capw - st.cap) / kCapStride, (uint32_t)kCapSlots), st.thr);
     uint32_t trunc = 0;
     if (cnt > (uint32_t)kTopK) {
       cap_select_top(st.cap, cnt);
