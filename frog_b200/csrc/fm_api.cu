@@ -44,7 +44,8 @@ int cuda_fail(fm_ctx* c, cudaError_t e, const char* what) {
     if (e__ != cudaSuccess) return cuda_fail((ctx), e__, #expr); \
   } while (0)
 
-// Upload the ImageDev table and read the per-image metas (flags, class tables) back.
+// Upload the ImageDev table, prepare the images uploaded since the last call (one batch of
+// kernels) and read the per-image metas (flags, class tables) back.
 int sync_images(fm_ctx* c) {
   if (!c->images_dirty) return FM_OK;
   const size_t n = c->h_images.size();
@@ -52,6 +53,11 @@ int sync_images(fm_ctx* c) {
   c->h_metas.assign(n, ImageMeta{});
   if (n) {
     FM_CUDA(c, cudaMemcpyAsync(c->d_images.p, c->h_images.data(), n * sizeof(ImageDev), cudaMemcpyHostToDevice, c->stream));
+    {
+      Span sp(&c->ev_prep, c->stream, kPhPrep);
+      cudaError_t e = fast_prepare_dirty(c);
+      if (e != cudaSuccess) return cuda_fail(c, e, "image preparation");
+    }
     FM_CUDA(c, cudaMemcpyAsync(c->h_metas.data(), c->d_metas.p, n * sizeof(ImageMeta), cudaMemcpyDeviceToHost, c->stream));
     FM_CUDA(c, cudaStreamSynchronize(c->stream));
   }
@@ -116,7 +122,7 @@ void fm_destroy(fm_ctx* c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   c->arena.release();
-  DevBuf* bufs[] = {&c->s_keys, &c->s_keys_sorted, &c->s_idx, &c->s_norm2, &c->s_sort, &c->d_images, &c->d_metas, &c->d_meta_blob, &c->d_rowres, &c->d_chunk_count, &c->d_chunk_out,
+  DevBuf* bufs[] = {&c->s_keys, &c->s_keys_sorted, &c->s_idx, &c->s_idx_sorted, &c->s_norm2, &c->s_sort, &c->s_segs, &c->d_images, &c->d_metas, &c->d_meta_blob, &c->d_rowres, &c->d_chunk_count, &c->d_chunk_out,
                     &c->d_totals, &c->d_bands, &c->d_cands, &c->d_redo, &c->d_taskinfo, &c->cache_out, &c->cache_counts};
   for (auto* b : bufs) b->release();
   if (c->cache_pinned) cudaFreeHost(c->cache_pinned);
@@ -147,6 +153,7 @@ int fm_synchronize(fm_ctx* c) {
 int fm_clear_images(fm_ctx* c) {
   if (!c) return FM_ERR_INVALID;
   for (auto& im : c->images) { im.valid = false; im.slab = nullptr; im.slab_bytes = 0; }
+  c->dirty.clear();
   c->images_dirty = true;
   c->dim = 0;
   cudaSetDevice(c->device);
@@ -211,10 +218,11 @@ int fm_upload_image(fm_ctx* c, uint32_t img, const float* desc, const float* sca
   v.rowop = b_op ? reinterpret_cast<__half*>(base + b_desc + 4 * b_vec) : nullptr;
   v.colop = b_op ? reinterpret_cast<__half*>(base + b_desc + 4 * b_vec + b_op) : nullptr;
   {
-    Span sp(&c->ev_prep, c->stream, kPhPrep);
-    cudaError_t e = fast_prepare_image(c, img);
-    if (e != cudaSuccess) return cuda_fail(c, e, "fm_upload_image: prep");
+    cudaError_t e = ensure_metas(c, (uint32_t)c->h_images.size());
+    if (e != cudaSuccess) return cuda_fail(c, e, "fm_upload_image");
+    v.meta = c->d_metas.as<ImageMeta>() + img;
   }
+  c->dirty.push_back(img);  // sorted / FP16 tensors are built in one batch at the next fm_match
   c->images_dirty = true;
   return FM_OK;
 }

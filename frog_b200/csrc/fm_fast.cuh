@@ -46,44 +46,63 @@ inline cudaError_t ensure_metas(fm_ctx* c, uint32_t n_images) {
   return cudaSuccess;
 }
 
-// Build the sorted / FP16 tensors of image `img`; desc/scale/lap were already copied to the image's
-// slab, perm/scale_sorted/rowop/colop point into it (fm_upload_image laid the slab out).
-inline cudaError_t fast_prepare_image(fm_ctx* c, uint32_t img) {
-  Image& im = c->images[img];
-  ImageDev& v = c->h_images[img];
-  cudaError_t e = ensure_metas(c, (uint32_t)c->h_images.size());
-  if (e != cudaSuccess) return e;
-  ImageMeta* meta = c->d_metas.as<ImageMeta>() + img;
-  v.meta = meta;
-  if ((e = cudaMemsetAsync(meta, 0, sizeof(ImageMeta), c->stream)) != cudaSuccess) return e;
-  const uint32_t n = im.n;
-  if (n == 0) {
-    ImageMeta m{};
-    for (int k = 0; k <= kMaxClasses; k++) m.class_begin[k] = 0;
-    return cudaMemcpyAsync(meta, &m, sizeof m, cudaMemcpyHostToDevice, c->stream);
+// Build the sorted / FP16 tensors of every image uploaded since the last call (c->dirty), in one
+// batch: desc/scale/lap were already copied to the images' slabs, perm/scale_sorted/rowop/colop
+// point into them (fm_upload_image laid the slabs out) and the ImageDev table on the device is
+// current.
+inline cudaError_t fast_prepare_dirty(fm_ctx* c) {
+  if (c->dirty.empty()) return cudaSuccess;
+  std::sort(c->dirty.begin(), c->dirty.end());
+  c->dirty.erase(std::unique(c->dirty.begin(), c->dirty.end()), c->dirty.end());
+  std::vector<PrepSeg> segs;
+  uint32_t off = 0, blk_keys = 0, blk_pack = 0;
+  for (uint32_t img : c->dirty) {
+    if (img >= c->images.size() || !c->images[img].valid) continue;
+    const uint32_t n = c->images[img].n;
+    PrepSeg sg{};
+    sg.img = img; sg.n = n; sg.off = off; sg.blk_keys = blk_keys; sg.blk_pack = blk_pack;
+    segs.push_back(sg);
+    off += n;
+    blk_keys += (n + 255) / 256;
+    blk_pack += (c->h_images[img].n_pad * 8 + 255) / 256;
   }
-  if ((e = c->s_keys.ensure((size_t)n * 8)) != cudaSuccess) return e;
-  if ((e = c->s_keys_sorted.ensure((size_t)n * 8)) != cudaSuccess) return e;
-  if ((e = c->s_idx.ensure((size_t)n * 4)) != cudaSuccess) return e;
-  if ((e = c->s_norm2.ensure((size_t)n * 4)) != cudaSuccess) return e;
+  c->dirty.clear();
+  if (segs.empty()) return cudaSuccess;
+  if (segs.size() > 65535) return cudaErrorInvalidValue;  // 16 bits of the sort key name the batch segment
+  const uint32_t n_segs = (uint32_t)segs.size(), n_tot = std::max(off, 1u);
+  cudaError_t e;
+  if ((e = c->s_segs.ensure(segs.size() * sizeof(PrepSeg))) != cudaSuccess) return e;
+  if ((e = c->s_keys.ensure((size_t)n_tot * 8)) != cudaSuccess) return e;
+  if ((e = c->s_keys_sorted.ensure((size_t)n_tot * 8)) != cudaSuccess) return e;
+  if ((e = c->s_idx.ensure((size_t)n_tot * 4)) != cudaSuccess) return e;
+  if ((e = c->s_idx_sorted.ensure((size_t)n_tot * 4)) != cudaSuccess) return e;
+  if ((e = c->s_norm2.ensure((size_t)n_tot * 4)) != cudaSuccess) return e;
+  // the segment table is read by kernels after this function returns: stage it in memory that outlives the call
+  c->h_segs = segs;
+  if ((e = cudaMemcpyAsync(c->s_segs.p, c->h_segs.data(), segs.size() * sizeof(PrepSeg), cudaMemcpyHostToDevice, c->stream)) != cudaSuccess) return e;
+  if ((e = cudaStreamSynchronize(c->stream)) != cudaSuccess) return e;  // pageable source: keep it simple and safe
+  const PrepSeg* d_segs = c->s_segs.as<PrepSeg>();
+  const ImageDev* d_images = c->d_images.as<ImageDev>();
+  ImageMeta* d_metas = c->d_metas.as<ImageMeta>();
   unsigned long long* keys = c->s_keys.as<unsigned long long>();
   unsigned long long* keys_sorted = c->s_keys_sorted.as<unsigned long long>();
-  uint32_t* perm = const_cast<uint32_t*>(v.perm);
-  prep_keys_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(v.desc, v.scale, v.lap, n, im.d, meta, keys,
-                                                          c->s_idx.as<uint32_t>(), c->s_norm2.as<float>());
-  size_t tmp_bytes = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, keys_sorted, c->s_idx.as<uint32_t>(), perm, (int)n, 0, 64, c->stream);
-  if ((e = c->s_sort.ensure(tmp_bytes)) != cudaSuccess) return e;
-  e = cub::DeviceRadixSort::SortPairs(c->s_sort.p, tmp_bytes, keys, keys_sorted, c->s_idx.as<uint32_t>(), perm, (int)n, 0, 64,
-                                      c->stream);
-  if (e != cudaSuccess) return e;
-  prep_finish_kernel<<<1, 1024, 0, c->stream>>>(keys_sorted, n, im.d, meta, const_cast<float*>(v.scale_sorted));
-  if (im.d == (uint32_t)kD) {
-    const uint32_t threads = v.n_pad * 8;
-    prep_pack_kernel<<<(threads + 255) / 256, 256, 0, c->stream>>>(
-        v.desc, c->s_norm2.as<float>(), perm, n, v.n_pad, reinterpret_cast<uint8_t*>(const_cast<__half*>(v.rowop)),
-        reinterpret_cast<uint8_t*>(const_cast<__half*>(v.colop)));
+  prep_reset_kernel<<<n_segs, 64, 0, c->stream>>>(d_segs, d_metas);
+  if (blk_keys)
+    prep_keys_kernel<<<blk_keys, 256, 0, c->stream>>>(d_images, d_segs, n_segs, d_metas, keys, c->s_idx.as<uint32_t>(),
+                                                     c->s_norm2.as<float>());
+  if (off) {
+    int end_bit = 48;
+    while (end_bit < 64 && (1u << (end_bit - 48)) < n_segs) end_bit++;
+    size_t tmp_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, keys_sorted, c->s_idx.as<uint32_t>(), c->s_idx_sorted.as<uint32_t>(),
+                                    (int)off, 0, end_bit, c->stream);
+    if ((e = c->s_sort.ensure(tmp_bytes)) != cudaSuccess) return e;
+    e = cub::DeviceRadixSort::SortPairs(c->s_sort.p, tmp_bytes, keys, keys_sorted, c->s_idx.as<uint32_t>(),
+                                        c->s_idx_sorted.as<uint32_t>(), (int)off, 0, end_bit, c->stream);
+    if (e != cudaSuccess) return e;
   }
+  prep_finish_kernel<<<n_segs, 1024, 0, c->stream>>>(d_images, d_segs, d_metas, keys_sorted, c->s_idx_sorted.as<uint32_t>());
+  if (blk_pack) prep_pack_kernel<<<blk_pack, 256, 0, c->stream>>>(d_images, d_segs, n_segs, c->s_norm2.as<float>());
   return cudaGetLastError();
 }
 

@@ -6,6 +6,7 @@
 
 #include "../../include/frogmatch.h"
 #include "fm_common.cuh"
+#include "fm_prep_types.h"
 
 namespace fm {
 
@@ -120,7 +121,9 @@ struct fm_ctx {
   std::vector<fm::ImageMeta> h_metas;
   fm::DevBuf d_images, d_metas;
   fm::Arena arena;                                            // per-image tensors
-  fm::DevBuf s_keys, s_keys_sorted, s_idx, s_norm2, s_sort;  // prep scratch, reused by every upload (stream-ordered)
+  fm::DevBuf s_keys, s_keys_sorted, s_idx, s_idx_sorted, s_norm2, s_sort, s_segs;  // batched-prep scratch (stream-ordered)
+  std::vector<uint32_t> dirty;          // images uploaded since the last preparation
+  std::vector<fm::PrepSeg> h_segs;
   uint32_t metas_cap = 0;
   bool images_dirty = true;
   uint32_t dim = 0;
