@@ -17,6 +17,8 @@
 // t = a.b - |b|^2/2 comes straight out of the MMA (K slots 48,49, see fm_prep.cuh), so
 // larger t <=> smaller squared distance.
 #pragma once
+#include <cstddef>
+
 #include "fm_common.cuh"
 #include "fm_exact.cuh"
 #include "fm_ptx.cuh"
@@ -46,8 +48,8 @@ struct alignas(1024) ScoreSmem {
   uint64_t bar_a;
   uint64_t bar_bfull[kStages];
   uint64_t bar_bempty[kStages];
-  uint64_t bar_accfull[2];
-  uint64_t bar_accempty[2];
+  uint64_t bar_accfull[2][2];   // [stage][row half]: MMA -> the half's four epilogue warps
+  uint64_t bar_accempty[2][2];  // [stage][row half]: those warps -> MMA (each row half has its own accumulators)
   uint32_t tmem_base;
   uint32_t cmin, cmax;
   uint2 cap[kCapSlots][kUnitRows];  // [slot][row]: lanes of a warp hit distinct banks whatever their slot
@@ -317,7 +319,7 @@ __device__ __forceinline__ void score_pair(const uint32_t (&ra)[16], const uint3
 // One 64-column accumulator tile of one row: two pairs of TMEM loads.
 template <bool kMasked, bool kDump, int kProbe>
 __device__ __forceinline__ void score_tile(uint32_t taddr, uint32_t cb, uint32_t lo, uint32_t width, RowScan& st,
-                                           float two_eps, uint64_t* bar_release, float* dump_row) {
+                                           float two_eps, uint32_t bar_release, float* dump_row) {
   uint32_t ra[16], rb[16];
   // Rolled on purpose: one copy of the capture code stays resident in the instruction cache.
 #pragma unroll 1
@@ -330,7 +332,7 @@ __device__ __forceinline__ void score_tile(uint32_t taddr, uint32_t cb, uint32_t
       // every column of this accumulator is now in registers: hand it back to the MMA warp
       ptx::tc_fence_before();
       __syncwarp();
-      if ((threadIdx.x & 31) == 0) ptx::mbar_arrive(bar_release);
+      if ((threadIdx.x & 31) == 0) ptx::mbar_arrive_u32(bar_release);
     }
     if (kDump) {
 #pragma unroll
@@ -409,13 +411,16 @@ score_kernel(const ImageDev* __restrict__ images, const Task* __restrict__ tasks
   st.g1 = st.g2 = -INFINITY;
   st.thr = kProbe == 1 ? INFINITY : -INFINITY;
   st.ovf = 0;
-  st.cap = st.capw = ptx::smem_u32(&sm.cap[0][is_epi ? row_in_unit : 0]);
+  st.cap = ptx::smem_u32(&sm.cap[0][is_epi ? row_in_unit : 0]);
+  asm volatile("" : "+r"(st.cap));  // opaque: keep the list base in a register, do not rebuild it from the thread id
+  st.capw = st.cap;
 
   if (n_tiles > 0) {  // CTA-uniform
     if (warp == 1 && lane == 0) {
       ptx::mbar_init(&sm.bar_a, 1);
       for (int i = 0; i < kStages; i++) { ptx::mbar_init(&sm.bar_bfull[i], 1); ptx::mbar_init(&sm.bar_bempty[i], 1); }
-      for (int i = 0; i < 2; i++) { ptx::mbar_init(&sm.bar_accfull[i], 1); ptx::mbar_init(&sm.bar_accempty[i], kEpiWarps); }
+      for (int i = 0; i < 2; i++)
+        for (int h = 0; h < 2; h++) { ptx::mbar_init(&sm.bar_accfull[i][h], 1); ptx::mbar_init(&sm.bar_accempty[i][h], kEpiWarps / 2); }
       ptx::fence_mbar_init();
     }
     if (warp == 0) ptx::tmem_alloc<kAccCols>(&sm.tmem_base);
@@ -448,18 +453,23 @@ score_kernel(const ImageDev* __restrict__ images, const Task* __restrict__ tasks
         ptx::mbar_wait(&sm.bar_a, 0);
         for (uint32_t i = 0; i < n_tiles; i++) {
           const uint32_t stg = i % kStages, acc = i & 1, use = i >> 1;
-          if (use > 0) ptx::mbar_wait(&sm.bar_accempty[acc], (use - 1) & 1);
+          if (use > 0) ptx::mbar_wait(&sm.bar_accempty[acc][0], (use - 1) & 1);
           ptx::mbar_wait(&sm.bar_bfull[stg], (i / kStages) & 1);
           ptx::tc_fence_after();
           const uint64_t bdesc = ptx::umma_desc_sw128(ptx::smem_u32(sm.b[stg]));
 #pragma unroll
           for (int k = 0; k < kKPad / 16; k++)  // +32 B per K step inside the 128 B swizzle row
             ptx::mma_f16_ss(tmem + acc * (2 * kTileCols), adesc0 + 2 * k, bdesc + 2 * k, idesc, k > 0);
+          ptx::mma_commit(&sm.bar_accfull[acc][0]);
+          if (use > 0) {
+            ptx::mbar_wait(&sm.bar_accempty[acc][1], (use - 1) & 1);
+            ptx::tc_fence_after();
+          }
 #pragma unroll
           for (int k = 0; k < kKPad / 16; k++)
             ptx::mma_f16_ss(tmem + acc * (2 * kTileCols) + kTileCols, adesc1 + 2 * k, bdesc + 2 * k, idesc, k > 0);
           ptx::mma_commit(&sm.bar_bempty[stg]);
-          ptx::mma_commit(&sm.bar_accfull[acc]);
+          ptx::mma_commit(&sm.bar_accfull[acc][1]);
         }
       }
     } else if (is_epi) {
@@ -472,22 +482,27 @@ score_kernel(const ImageDev* __restrict__ images, const Task* __restrict__ tasks
       // the compiler holds it in a register instead of rebuilding it from the thread id per chunk.
       uint32_t tmem_lane = tmem + (((warp & 3) * 32) << 16) + half * kTileCols;
       asm volatile("" : "+r"(tmem_lane));
+      // shared-space address of this row half's accfull[0] barrier; accfull[1] is 16 B further,
+      // the matching accempty barriers 32 B further (layout of ScoreSmem)
+      uint32_t bar_full = ptx::smem_u32(&sm.bar_accfull[0][half]);
+      asm volatile("" : "+r"(bar_full));
+      static_assert(offsetof(ScoreSmem, bar_accempty) - offsetof(ScoreSmem, bar_accfull) == 32, "barrier layout");
       for (uint32_t i = 0; i < n_tiles; i++) {
         const uint32_t acc = i & 1;
         const uint32_t cb = (tile0 + i) * kTileCols;
-        ptx::mbar_wait(&sm.bar_accfull[acc], (i >> 1) & 1);
+        ptx::mbar_wait_u32(bar_full + acc * 16, (i >> 1) & 1);
         ptx::tc_fence_after();
         const uint32_t taddr = tmem_lane + acc * (2 * kTileCols);
         const bool needed = kProbe != 2 && (kDump || (cb < w_cmax && cb + kTileCols > w_cmin));  // warp-uniform
         if (!needed) {
           ptx::tc_fence_before();
           __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(&sm.bar_accempty[acc]);
+          if (lane == 0) ptx::mbar_arrive_u32(bar_full + 32 + acc * 16);
         } else if (!kDump && cb >= w_imin && cb + kTileCols <= w_imax) {
-          score_tile<false, kDump, kProbe>(taddr, cb, lo, width, st, two_eps, &sm.bar_accempty[acc], dump_row);
+          score_tile<false, kDump, kProbe>(taddr, cb, lo, width, st, two_eps, bar_full + 32 + acc * 16, dump_row);
           scored += kTileCols;
         } else {
-          score_tile<true, kDump, kProbe>(taddr, cb, lo, width, st, two_eps, &sm.bar_accempty[acc], dump_row);
+          score_tile<true, kDump, kProbe>(taddr, cb, lo, width, st, two_eps, bar_full + 32 + acc * 16, dump_row);
           scored += kTileCols;
         }
       }
