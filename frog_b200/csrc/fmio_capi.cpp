@@ -1,5 +1,8 @@
 // fmio_capi.cpp -- C wrappers over the host-side readers / pruning / pairs.bin writer so the
 // CPU test-suite (and Python callers) can exercise exactly the code bin/match runs.
+#include <cerrno>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "keypoint_io.h"
@@ -65,6 +68,75 @@ int fmio_write_pairs_bin(const char* path, int n_images, const char* const* file
     blocks[b].pairs = pairs + 2 * pair_offsets[b];
   }
   return fmio::write_pairs_bin(path, names, rg, images, blocks) ? 0 : 1;
+}
+
+// Fuzz the libc-free decimal parser against strtof: `n` random cells in the formats surf3d and
+// hand-edited files produce.  Returns the number of cells whose value bits or consumed length
+// differ from strtof's (must be 0); *n_fast = cells the fast path handled itself.
+int64_t fmio_fuzz_floats(uint64_t seed, int64_t n, int64_t* n_fast, char* first_bad, size_t badlen) {
+  uint64_t s = seed * 0x9E3779B97F4A7C15ull + 1;
+  auto rnd = [&]() { s ^= s << 13; s ^= s >> 7; s ^= s << 17; return s; };
+  int64_t bad = 0, fast = 0;
+  char buf[96];
+  for (int64_t i = 0; i < n; i++) {
+    const int kind = (int)(rnd() % 8);
+    int len = 0;
+    if (rnd() % 3 == 0) buf[len++] = '-';
+    if (kind <= 3) {  // "%f": integer part of 0..6 digits, 6 decimals
+      const int id = (int)(rnd() % 7);
+      if (id == 0) buf[len++] = '0';
+      for (int k = 0; k < id; k++) buf[len++] = (char)('0' + (k == 0 ? 1 + rnd() % 9 : rnd() % 10));
+      buf[len++] = '.';
+      for (int k = 0; k < 6; k++) buf[len++] = (char)('0' + rnd() % 10);
+    } else if (kind == 4) {  // many digits
+      const int nd = 1 + (int)(rnd() % 24), dot = (int)(rnd() % (nd + 1));
+      for (int k = 0; k < nd; k++) { if (k == dot) buf[len++] = '.'; buf[len++] = (char)('0' + rnd() % 10); }
+    } else if (kind == 5) {  // exponent forms, some broken ("1e", "1e+")
+      const int nd = 1 + (int)(rnd() % 9);
+      for (int k = 0; k < nd; k++) { if (k == 1) buf[len++] = '.'; buf[len++] = (char)('0' + rnd() % 10); }
+      buf[len++] = (rnd() & 1) ? 'e' : 'E';
+      const int r = (int)(rnd() % 4);
+      if (r == 0) buf[len++] = '-'; else if (r == 1) buf[len++] = '+';
+      const int ed = (int)(rnd() % 3);
+      for (int k = 0; k < ed; k++) buf[len++] = (char)('0' + rnd() % 10);
+    } else if (kind == 6) {  // floats near midpoints: a float's midpoint with its successor, printed exactly-ish
+      uint32_t fb = (uint32_t)(rnd() % 0x7F000000u);
+      float f0, f1;
+      memcpy(&f0, &fb, 4);
+      fb++;
+      memcpy(&f1, &fb, 4);
+      const double mid = ((double)f0 + (double)f1) * 0.5;
+      len += snprintf(buf + len, 60, (rnd() & 1) ? "%.17g" : "%.25g", mid);
+    } else {  // trailing junk / odd shapes
+      static const char* odd[] = {"1.5abc", ".5", "5.", "0x1p3", "inf", "nan", "-.25e1x", "00012.500", "+7", "1e400", "1e-50", "4e-39", "3.5e38", "."};
+      const char* o = odd[rnd() % (sizeof odd / sizeof odd[0])];
+      len = (int)strlen(o);
+      memcpy(buf, o, (size_t)len);
+    }
+    buf[len] = 0;
+    float got = 0, want = 0;
+    int used = -1;
+    const int how = fmio::debug_cell_to_float(buf, (size_t)len, &got, &used);
+    char* endp = nullptr;
+    errno = 0;
+    want = strtof(buf, &endp);
+    const bool want_ok = endp != buf && errno != ERANGE;
+    bool ok;
+    if (how < 0) ok = !want_ok;
+    else {
+      uint32_t a, b;
+      memcpy(&a, &got, 4);
+      memcpy(&b, &want, 4);
+      ok = want_ok && a == b && (how == 0 || used == (int)(endp - buf));
+    }
+    if (how == 1) fast++;
+    if (!ok) {
+      if (bad == 0 && first_bad && badlen) { strncpy(first_bad, buf, badlen - 1); first_bad[badlen - 1] = 0; }
+      bad++;
+    }
+  }
+  if (n_fast) *n_fast = fast;
+  return bad;
 }
 
 }  // extern "C"

@@ -27,12 +27,73 @@ bool slurp(const std::string& path, std::vector<char>& buf, std::string& err) {
   return true;
 }
 
+// Decimal text -> float without libc, bit-identical to strtof on everything it accepts and
+// "don't know" (false) on the rest.  surf3d writes "%f" cells (vtk3DSURF.cxx:451-478): a sign,
+// digits, a point, six digits -- at most 19 significant digits m and a decimal exponent e10 with
+// |e10| <= 22.  Then m and 10^|e10| are exact doubles, so one IEEE multiply/divide gives the
+// correctly rounded DOUBLE d of the exact value x (Clinger's fast path).  Rounding d once more to
+// float equals rounding x directly unless d sits exactly on the midpoint M of two adjacent floats
+// (every such M is itself a double, so no M can lie strictly between x and its nearest double):
+// those cases, and anything outside the normal float range, are left to strtof.
+// *endp = one past the longest prefix strtof would consume.
+inline bool fast_strtof(const char* c, const char* ce, float& v, const char*& endp) {
+  const char* p = c;
+  bool neg = false;
+  if (p < ce && (*p == '-' || *p == '+')) { neg = *p == '-'; p++; }
+  uint64_t m = 0;
+  int digits = 0, sig = 0, frac = 0;
+  const char* d0 = p;
+  while (p < ce && *p >= '0' && *p <= '9') {
+    if (sig || *p != '0') { if (++sig > 19) return false; }
+    m = m * 10 + (uint64_t)(*p - '0');
+    digits++; p++;
+  }
+  if (p < ce && *p == '.') {
+    p++;
+    while (p < ce && *p >= '0' && *p <= '9') {
+      if (sig || *p != '0') { if (++sig > 19) return false; }
+      m = m * 10 + (uint64_t)(*p - '0');
+      digits++; frac++; p++;
+    }
+  }
+  if (digits == 0) return false;  // "inf", "nan", ".", junk: strtof decides
+  (void)d0;
+  int e10 = -frac;
+  if (p < ce && (*p == 'e' || *p == 'E')) {
+    const char* q = p + 1;
+    bool eneg = false;
+    if (q < ce && (*q == '-' || *q == '+')) { eneg = *q == '-'; q++; }
+    if (q < ce && *q >= '0' && *q <= '9') {
+      int ex = 0;
+      while (q < ce && *q >= '0' && *q <= '9') { if (ex < 10000) ex = ex * 10 + (*q - '0'); q++; }
+      e10 += eneg ? -ex : ex;
+      p = q;
+    }  // else: "1e" / "1e+" -- the exponent marker is not part of the number
+  } else if (p < ce && (*p == 'x' || *p == 'X' || *p == 'p' || *p == 'P')) {
+    return false;  // hex float: strtof decides
+  }
+  endp = p;
+  if (m == 0) { v = neg ? -0.0f : 0.0f; return true; }
+  if (m >= (1ull << 53) || e10 < -22 || e10 > 22) return false;
+  static const double kPow10[23] = {1e0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7, 1e8, 1e9, 1e10, 1e11,
+                                    1e12, 1e13, 1e14, 1e15, 1e16, 1e17, 1e18, 1e19, 1e20, 1e21, 1e22};
+  const double d = e10 < 0 ? (double)m / kPow10[-e10] : (double)m * kPow10[e10];
+  if (!(d >= 1.1754943508222875e-38 && d <= 3.4028234663852886e38)) return false;  // subnormal / overflow: ERANGE rules
+  uint64_t bits;
+  memcpy(&bits, &d, 8);
+  if ((bits & 0x1FFFFFFFull) == 0x10000000ull) return false;  // exactly on a float midpoint
+  v = neg ? -(float)d : (float)d;
+  return true;
+}
+
 // std::stof semantics (match.cpp:69,152) on the cell [c, ce): strtof after leading blanks, longest
 // valid prefix, trailing junk ignored; no conversion or ERANGE make std::stof throw, which
 // terminates the reference -- reported here as an error.
 inline bool cell_to_float(const char* c, const char* ce, float& v) {
   while (c < ce && (*c == ' ' || (*c >= '\t' && *c <= '\r'))) c++;
   if (c == ce) return false;
+  const char* fe = nullptr;
+  if (fast_strtof(c, ce, v, fe)) return true;
   char* endp = nullptr;
   errno = 0;
   v = strtof(c, &endp);  // stops at ',' '\n' or NUL at the latest: none can continue a number
@@ -41,6 +102,16 @@ inline bool cell_to_float(const char* c, const char* ce, float& v) {
 }
 
 }  // namespace
+
+// Test hook: 1 = the libc-free path handled the cell, 0 = it deferred to strtof, -1 = not a number.
+// *endp_off = characters consumed (fast path only).
+int debug_cell_to_float(const char* c, size_t len, float* v, int* endp_off) {
+  const char* fe = c;
+  float x = 0;
+  if (fast_strtof(c, c + len, x, fe)) { *v = x; *endp_off = (int)(fe - c); return 1; }
+  *endp_off = -1;
+  return cell_to_float(c, c + len, *v) ? 0 : -1;
+}
 
 bool parse_csv_text(const char* text, size_t len, KeypointSet& out, std::string& err) {
   out = KeypointSet{};

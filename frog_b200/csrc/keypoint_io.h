@@ -47,4 +47,7 @@ bool write_pairs_bin(const std::string& path, const std::vector<std::string>& fi
                      const std::vector<std::array<double, 3>>& rigids, const std::vector<KeypointSet>& images,
                      const std::vector<PairBlock>& blocks);
 
+// Test hook for the libc-free decimal parser (keypoint_io.cpp fast_strtof).
+int debug_cell_to_float(const char* c, size_t len, float* v, int* endp_off);
+
 }  // namespace fmio

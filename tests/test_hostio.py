@@ -75,3 +75,20 @@ def test_writer_layout(built, tmp_path):
     assert pf.names == ["a.bin", "c.csv"] and pf.rigids[0] == (1.0, 2.0, 3.0)
     assert [b[:2] for b in pf.blocks] == [(0, 1), (3, 1)]  # ids truncated to u16 (match.cpp:735-736)
     assert pf.blocks[1][2].shape == (0, 2)  # empty blocks are still written (match.cpp:732-738)
+
+
+def test_fast_decimal_parser_is_strtof(built):
+    """keypoint_io.cpp fast_strtof: the libc-free text->float path must agree with strtof (= std::stof,
+    match.cpp:69,152) bit for bit, value and consumed prefix, on surf3d-style "%f" cells, long digit
+    strings, exponent forms (also broken ones), exact float midpoints and odd shapes."""
+    import ctypes as C
+
+    from frog_b200 import build
+    L = C.CDLL(build.FMIO)
+    L.fmio_fuzz_floats.argtypes = [C.c_uint64, C.c_int64, C.POINTER(C.c_int64), C.c_char_p, C.c_size_t]
+    L.fmio_fuzz_floats.restype = C.c_int64
+    n_fast, bad = C.c_int64(), C.create_string_buffer(128)
+    for seed in (1, 2, 3):
+        n_bad = L.fmio_fuzz_floats(seed, 400_000, C.byref(n_fast), bad, 128)
+        assert n_bad == 0, f"first mismatching cell: {bad.value!r}"
+        assert n_fast.value > 200_000  # the fast path really carries the common formats
