@@ -17,13 +17,14 @@ LIB_PATH = os.path.join(_HERE, "libfrogmatch.so")
 FLAG_SYM = 1
 FLAG_FORCE_EXACT = 2
 FLAG_DEVICE_ONLY = 4
+FLAG_ASYNC = 8
 
 # every symbol include/frogmatch.h declares (checked by tests/test_abi.py)
 PUBLIC_SYMBOLS = [
     "fm_device_count", "fm_create", "fm_destroy", "fm_last_error", "fm_set_stream", "fm_synchronize", "fm_upload_image",
-    "fm_clear_images", "fm_image_points", "fm_match", "fm_result_num_pairs", "fm_result_total",
+    "fm_clear_images", "fm_image_points", "fm_match", "fm_result_wait", "fm_result_num_pairs", "fm_result_total",
     "fm_result_count", "fm_result_pairs", "fm_result_fetch", "fm_result_device_counts",
-    "fm_result_device_pairs", "fm_result_free", "fm_get_stats", "fm_version",
+    "fm_result_device_pairs", "fm_result_free", "fm_get_stats", "fm_result_stats", "fm_version",
 ]
 DEBUG_SYMBOLS = ["fm_debug_image", "fm_debug_score_unit"]
 
@@ -77,6 +78,8 @@ def load():
     L.fm_result_pairs.argtypes = [vp, C.c_size_t]
     L.fm_result_pairs.restype = u32p
     L.fm_result_fetch.argtypes = [vp]
+    L.fm_result_wait.argtypes = [vp]
+    L.fm_result_stats.argtypes = [vp, C.POINTER(Stats)]
     L.fm_result_device_counts.argtypes = [vp]
     L.fm_result_device_counts.restype = vp
     L.fm_result_device_pairs.argtypes = [vp]
@@ -98,18 +101,42 @@ def _ptr(a: np.ndarray):
 class Result:
     """Owns one fm_result: per-pair match lists, on the host and/or on the device."""
 
-    def __init__(self, matcher: "Matcher", handle):
+    def __init__(self, matcher: "Matcher", handle, pending: bool = False):
         self._m, self._h = matcher, handle
-        L = matcher._L
-        self.n_pairs = L.fm_result_num_pairs(handle)
-        self.total = L.fm_result_total(handle)
-        self.counts = np.array([L.fm_result_count(handle, p) for p in range(self.n_pairs)], np.uint32)
+        self.n_pairs = matcher._L.fm_result_num_pairs(handle)
+        self.total, self.counts = None, None
+        if not pending:
+            self._read_counts()
+
+    def _read_counts(self) -> None:
+        L = self._m._L
+        self.total = L.fm_result_total(self._h)
+        self.counts = np.array([L.fm_result_count(self._h, p) for p in range(self.n_pairs)], np.uint32)
+
+    def wait(self) -> "Result":
+        """Complete an asynchronous (FM_FLAG_ASYNC) result: counts, totals and -- unless device-only -- host lists."""
+        self._m._check(self._m._L.fm_result_wait(self._h))
+        if self.counts is None:
+            self._read_counts()
+        return self
 
     def fetch(self) -> None:
         self._m._check(self._m._L.fm_result_fetch(self._h))
+        if self.counts is None:
+            self._read_counts()
+
+    def stats(self) -> dict:
+        """fm_stats of the call that produced this result (waits for it)."""
+        s = Stats()
+        self._m._check(self._m._L.fm_result_stats(self._h, C.byref(s)))
+        if self.counts is None:
+            self._read_counts()
+        return s.as_dict()
 
     def pairs(self, p: int) -> np.ndarray:
         """[count,2] uint32 (first_idx, second_idx) of pair p -- the bytes match.cpp:738 writes."""
+        if self.counts is None:
+            self.wait()
         n = int(self.counts[p])
         if n == 0:
             return np.zeros((0, 2), np.uint32)
@@ -189,14 +216,14 @@ class Matcher:
                                             C.c_void_p(lap_ptr), n, d))
 
     def match(self, pair_first, pair_second, dist: float = 0.22, ratio: float = 1.0, sym: bool = False,
-              force_exact: bool = False, device_only: bool = False) -> Result:
+              force_exact: bool = False, device_only: bool = False, asynchronous: bool = False) -> Result:
         pf = np.ascontiguousarray(pair_first, np.uint32)
         ps = np.ascontiguousarray(pair_second, np.uint32)
         flags = (FLAG_SYM if sym else 0) | (FLAG_FORCE_EXACT if force_exact else 0) | \
-                (FLAG_DEVICE_ONLY if device_only else 0)
+                (FLAG_DEVICE_ONLY if device_only else 0) | (FLAG_ASYNC if asynchronous else 0)
         h = C.c_void_p()
         self._check(self._L.fm_match(self._h, _ptr(pf), _ptr(ps), pf.shape[0], dist, ratio, flags, C.byref(h)))
-        return Result(self, h)
+        return Result(self, h, pending=asynchronous)
 
     def stats(self) -> dict:
         s = Stats()

@@ -17,12 +17,20 @@ struct fm_result {
   fm_ctx* ctx = nullptr;
   size_t n_pairs = 0;
   uint64_t total = 0;
+  uint32_t flags = 0;
   std::vector<uint32_t> counts;
   std::vector<uint64_t> offsets;
   DevBuf d_out, d_counts;
   uint32_t* h_pairs = nullptr;  // pinned
   size_t h_cap = 0;
   bool fetched = false;
+  // completion: the call's DeviceCounters and per-pair counts land in a pinned block, `done` fires behind them
+  void* h_block = nullptr;
+  size_t h_block_cap = 0;
+  cudaEvent_t done = nullptr;
+  bool waited = false;
+  EventPool ev;     // this call's phase brackets (and `done`)
+  fm_stats stats{};  // launch-side counters; device counters and event times are filled in by finalize()
 };
 
 namespace {
@@ -62,6 +70,87 @@ int sync_images(fm_ctx* c) {
     FM_CUDA(c, cudaStreamSynchronize(c->stream));
   }
   c->images_dirty = false;
+  return FM_OK;
+}
+
+// Small free lists so that several results can be in flight (FM_FLAG_ASYNC) without a cudaMalloc /
+// cudaFree (a device-wide synchronisation) per call.
+DevBuf take_buf(std::vector<DevBuf>& list, size_t bytes) {
+  int best = -1;
+  for (size_t i = 0; i < list.size(); i++)
+    if (list[i].cap >= bytes && (best < 0 || list[i].cap < list[best].cap)) best = (int)i;
+  if (best < 0 && !list.empty()) {  // none fits: grow the largest
+    best = 0;
+    for (size_t i = 1; i < list.size(); i++)
+      if (list[i].cap > list[best].cap) best = (int)i;
+  }
+  DevBuf b;
+  if (best >= 0) {
+    b = list[best];
+    list.erase(list.begin() + best);
+  }
+  return b;
+}
+
+void give_buf(std::vector<DevBuf>& list, DevBuf& b) {
+  if (!b.p) return;
+  if (list.size() < 4) list.push_back(b);
+  else cudaFree(b.p);
+  b = DevBuf{};
+}
+
+cudaError_t take_pinned(fm_ctx* c, size_t bytes, void** out, size_t* cap) {
+  for (size_t i = 0; i < c->pin_free.size(); i++)
+    if (c->pin_free[i].second >= bytes) {
+      *out = c->pin_free[i].first;
+      *cap = c->pin_free[i].second;
+      c->pin_free.erase(c->pin_free.begin() + i);
+      return cudaSuccess;
+    }
+  const size_t want = std::max<size_t>(bytes + bytes / 4, 4096);
+  cudaError_t e = cudaMallocHost(out, want);
+  if (e == cudaSuccess) *cap = want;
+  return e;
+}
+
+void give_pinned(fm_ctx* c, void* p, size_t cap) {
+  if (!p) return;
+  if (c->pin_free.size() < 8) c->pin_free.emplace_back(p, cap);
+  else cudaFreeHost(p);
+}
+
+// Complete a result: wait for its `done` event, then read the totals, per-pair counts and phase
+// times the device left in the pinned block / the call's events.
+int finalize(fm_result* r) {
+  if (r->waited) return FM_OK;
+  fm_ctx* c = r->ctx;
+  FM_CUDA(c, cudaSetDevice(c->device));
+  FM_CUDA(c, cudaEventSynchronize(r->done));
+  const DeviceCounters* hc = static_cast<const DeviceCounters*>(r->h_block);
+  const uint32_t* hcounts = reinterpret_cast<const uint32_t*>(static_cast<const char*>(r->h_block) + sizeof(DeviceCounters));
+  r->total = hc->running_total;
+  r->counts.assign(hcounts, hcounts + r->n_pairs);
+  r->offsets.assign(r->n_pairs + 1, 0);
+  for (size_t p = 0; p < r->n_pairs; p++) r->offsets[p + 1] = r->offsets[p] + r->counts[p];
+  r->stats.scored_pairs = hc->scored_cols;
+  r->stats.candidates = hc->rescore.candidates;
+  r->stats.rows_exact += hc->redo_total;
+  float acc[kNumPhases] = {0};
+  for (auto& s : r->ev.spans) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, s.a, s.b) == cudaSuccess) acc[s.phase] += ms;
+  }
+  r->stats.ms_total = acc[kPhTotal];
+  r->stats.ms_score = acc[kPhScore];
+  r->stats.ms_rescore = acc[kPhRescore] + acc[kPhBands];
+  r->stats.ms_exact = acc[kPhExact];
+  r->stats.ms_compact = acc[kPhCompact];
+  r->waited = true;
+  const float ms_prep = c->stats.ms_prep;
+  c->stats = r->stats;
+  c->stats.ms_prep = ms_prep;
+  if (r->offsets[r->n_pairs] != r->total)
+    return fail(c, FM_ERR_CUDA, "fm_match: internal error, per-pair counts do not sum to the compacted total");
   return FM_OK;
 }
 
@@ -123,11 +212,15 @@ void fm_destroy(fm_ctx* c) {
   cudaStreamSynchronize(c->stream);
   c->arena.release();
   DevBuf* bufs[] = {&c->s_keys, &c->s_keys_sorted, &c->s_idx, &c->s_idx_sorted, &c->s_norm2, &c->s_sort, &c->s_segs, &c->d_images, &c->d_metas, &c->d_meta_blob, &c->d_rowres, &c->d_chunk_count, &c->d_chunk_out,
-                    &c->d_totals, &c->d_bands, &c->d_cands, &c->d_redo, &c->d_taskinfo, &c->cache_out, &c->cache_counts};
+                    &c->d_totals, &c->d_bands, &c->d_cands, &c->d_redo, &c->d_taskinfo};
   for (auto* b : bufs) b->release();
+  for (auto& b : c->out_free) b.release();
+  for (auto& b : c->counts_free) b.release();
+  for (auto& pb : c->pin_free) cudaFreeHost(pb.first);
   if (c->cache_pinned) cudaFreeHost(c->cache_pinned);
   if (c->h_pinned) cudaFreeHost(c->h_pinned);
   c->ev_match.destroy();
+  for (auto& e : c->ev_free) e.destroy();
   c->ev_prep.destroy();
   cudaStreamDestroy(c->own_stream);
   delete c;
@@ -302,8 +395,9 @@ int fm_match(fm_ctx* c, const uint32_t* pair_first, const uint32_t* pair_second,
   if (!r) return fail(c, FM_ERR_NOMEM, "fm_match: out of host memory");
   r->ctx = c;
   r->n_pairs = n_pairs;
-  std::swap(r->d_out, c->cache_out);
-  std::swap(r->d_counts, c->cache_counts);
+  r->flags = flags;
+  r->d_out = take_buf(c->out_free, std::max<uint64_t>(total_rows, 1) * sizeof(uint2));
+  r->d_counts = take_buf(c->counts_free, std::max<size_t>(n_pairs, 1) * sizeof(uint32_t));
 #define FM_CUDA_R(expr)                       \
   do {                                        \
     cudaError_t e__ = (expr);                 \
@@ -314,6 +408,10 @@ int fm_match(fm_ctx* c, const uint32_t* pair_first, const uint32_t* pair_second,
     }                                         \
   } while (0)
 
+  if (c->ev_match.pool.empty() && !c->ev_free.empty()) {
+    c->ev_match = std::move(c->ev_free.back());
+    c->ev_free.pop_back();
+  }
   c->ev_match.reset();
   fm_stats prev = c->stats;
   c->stats = fm_stats{};
@@ -328,18 +426,23 @@ int fm_match(fm_ctx* c, const uint32_t* pair_first, const uint32_t* pair_second,
   const size_t off_chunk = off_blk + sizeof(uint32_t) * np;
   const size_t off_unit = off_chunk + sizeof(uint32_t) * np;
   const size_t blob_bytes = off_unit + sizeof(uint32_t) * np;
-  std::vector<unsigned char> blob(std::max<size_t>(blob_bytes, 16));
+  // The blob is staged in the result's pinned block (behind the counters and per-pair counts the device
+  // writes back) so that the copy is asynchronous whatever its size: a pageable source would make
+  // cudaMemcpyAsync wait for the stream, i.e. for the previous FM_FLAG_ASYNC call.
+  const size_t off_blob = (sizeof(DeviceCounters) + std::max<size_t>(n_pairs, 1) * sizeof(uint32_t) + 15) & ~(size_t)15;
+  FM_CUDA_R(take_pinned(c, off_blob + std::max<size_t>(blob_bytes, 16), &r->h_block, &r->h_block_cap));
+  unsigned char* blob = static_cast<unsigned char*>(r->h_block) + off_blob;
   if (n_tasks) {
-    memcpy(blob.data(), tasks.data(), sizeof(Task) * n_tasks);
-    memcpy(blob.data() + off_pot, pair_of_task.data(), sizeof(uint32_t) * n_tasks);
+    memcpy(blob, tasks.data(), sizeof(Task) * n_tasks);
+    memcpy(blob + off_pot, pair_of_task.data(), sizeof(uint32_t) * n_tasks);
   }
   if (np) {
-    memcpy(blob.data() + off_blk, blk_off.data(), sizeof(uint32_t) * np);
-    memcpy(blob.data() + off_chunk, chunk_off.data(), sizeof(uint32_t) * np);
-    memcpy(blob.data() + off_unit, unit_off.data(), sizeof(uint32_t) * np);
+    memcpy(blob + off_blk, blk_off.data(), sizeof(uint32_t) * np);
+    memcpy(blob + off_chunk, chunk_off.data(), sizeof(uint32_t) * np);
+    memcpy(blob + off_unit, unit_off.data(), sizeof(uint32_t) * np);
   }
-  FM_CUDA_R(c->d_meta_blob.ensure(blob.size()));
-  FM_CUDA_R(cudaMemcpyAsync(c->d_meta_blob.p, blob.data(), blob.size(), cudaMemcpyHostToDevice, c->stream));
+  FM_CUDA_R(c->d_meta_blob.ensure(std::max<size_t>(blob_bytes, 16)));
+  FM_CUDA_R(cudaMemcpyAsync(c->d_meta_blob.p, blob, std::max<size_t>(blob_bytes, 16), cudaMemcpyHostToDevice, c->stream));
   const unsigned char* blob_d = c->d_meta_blob.as<unsigned char>();
   const Task* d_tasks = reinterpret_cast<const Task*>(blob_d);
   const uint32_t* d_pot = reinterpret_cast<const uint32_t*>(blob_d + off_pot);
@@ -423,25 +526,19 @@ int fm_match(fm_ctx* c, const uint32_t* pair_first, const uint32_t* pair_second,
   }
   FM_CUDA_R(cudaGetLastError());
 
-  // ---- totals and (optionally) the lists to the host -------------------------------------------
-  r->counts.assign(n_pairs, 0);
-  FM_CUDA_R(cudaMemcpyAsync(c->h_pinned, c->d_totals.p, sizeof(DeviceCounters), cudaMemcpyDeviceToHost, c->stream));
+  // ---- totals and per-pair counts to a pinned block; (optionally) the lists to the host ----------
+  FM_CUDA_R(cudaMemcpyAsync(r->h_block, c->d_totals.p, sizeof(DeviceCounters), cudaMemcpyDeviceToHost, c->stream));
   if (n_pairs)
-    FM_CUDA_R(cudaMemcpyAsync(r->counts.data(), r->d_counts.p, n_pairs * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
-  FM_CUDA_R(cudaStreamSynchronize(c->stream));
-  const DeviceCounters* hc = reinterpret_cast<const DeviceCounters*>(c->h_pinned);
-  r->total = hc->running_total;
-  c->stats.scored_pairs = hc->scored_cols;
-  c->stats.candidates = hc->rescore.candidates;
-  c->stats.rows_exact += hc->redo_total;
-  r->offsets.assign(n_pairs + 1, 0);
-  for (size_t p = 0; p < n_pairs; p++) r->offsets[p + 1] = r->offsets[p] + r->counts[p];
-  if (r->offsets[n_pairs] != r->total) {
-    fm_result_free(r);
-    return fail(c, FM_ERR_CUDA, "fm_match: internal error, per-pair counts do not sum to the compacted total");
-  }
-  if (!(flags & FM_FLAG_DEVICE_ONLY)) {
-    rc = fm_result_fetch(r);
+    FM_CUDA_R(cudaMemcpyAsync(static_cast<char*>(r->h_block) + sizeof(DeviceCounters), r->d_counts.p, n_pairs * sizeof(uint32_t),
+                              cudaMemcpyDeviceToHost, c->stream));
+  r->done = c->ev_match.get();
+  FM_CUDA_R(cudaEventRecord(r->done, c->stream));
+  r->stats = c->stats;
+  r->ev = std::move(c->ev_match);
+  c->ev_match = EventPool{};
+  c->last = r;
+  if (!(flags & FM_FLAG_ASYNC)) {
+    rc = fm_result_wait(r);
     if (rc != FM_OK) { fm_result_free(r); return rc; }
   }
   *out = r;
@@ -449,10 +546,20 @@ int fm_match(fm_ctx* c, const uint32_t* pair_first, const uint32_t* pair_second,
 #undef FM_CUDA_R
 }
 
+int fm_result_wait(fm_result* r) {
+  if (!r) return FM_ERR_INVALID;
+  int rc = finalize(r);
+  if (rc != FM_OK) return rc;
+  if (!(r->flags & FM_FLAG_DEVICE_ONLY)) return fm_result_fetch(r);
+  return FM_OK;
+}
+
 int fm_result_fetch(fm_result* r) {
   if (!r) return FM_ERR_INVALID;
   if (r->fetched) return FM_OK;
   fm_ctx* c = r->ctx;
+  int rc = finalize(r);
+  if (rc != FM_OK) return rc;
   FM_CUDA(c, cudaSetDevice(c->device));
   const size_t bytes = std::max<uint64_t>(r->total, 1) * sizeof(uint2);
   if (c->cache_pinned && c->cache_pinned_cap >= bytes) {
@@ -474,8 +581,8 @@ int fm_result_fetch(fm_result* r) {
 }
 
 size_t fm_result_num_pairs(const fm_result* r) { return r ? r->n_pairs : 0; }
-uint64_t fm_result_total(const fm_result* r) { return r ? r->total : 0; }
-uint32_t fm_result_count(const fm_result* r, size_t p) { return (r && p < r->n_pairs) ? r->counts[p] : 0; }
+uint64_t fm_result_total(const fm_result* r) { return (r && r->waited) ? r->total : 0; }
+uint32_t fm_result_count(const fm_result* r, size_t p) { return (r && r->waited && p < r->n_pairs) ? r->counts[p] : 0; }
 const uint32_t* fm_result_pairs(const fm_result* r, size_t p) {
   if (!r || p >= r->n_pairs || !r->fetched) return nullptr;
   return r->h_pairs + 2 * r->offsets[p];
@@ -487,11 +594,16 @@ void fm_result_free(fm_result* r) {
   if (!r) return;
   fm_ctx* c = r->ctx;
   cudaSetDevice(c->device);
-  // hand the big buffers back to the context so the next call does not reallocate
-  if (r->d_out.cap > c->cache_out.cap) std::swap(r->d_out, c->cache_out);
-  if (r->d_counts.cap > c->cache_counts.cap) std::swap(r->d_counts, c->cache_counts);
-  r->d_out.release();
-  r->d_counts.release();
+  if (r->done && !r->waited) cudaEventSynchronize(r->done);  // the pinned block is still a copy target
+  if (c->last == r) c->last = nullptr;
+  // hand the buffers and events back to the context so the next call does not reallocate
+  give_buf(c->out_free, r->d_out);
+  give_buf(c->counts_free, r->d_counts);
+  give_pinned(c, r->h_block, r->h_block_cap);
+  if (!r->ev.pool.empty()) {
+    if (c->ev_free.size() < 8) c->ev_free.push_back(std::move(r->ev));
+    else r->ev.destroy();
+  }
   if (r->h_pairs) {
     if (r->h_cap > c->cache_pinned_cap) {
       if (c->cache_pinned) cudaFreeHost(c->cache_pinned);
@@ -508,22 +620,25 @@ int fm_get_stats(fm_ctx* c, fm_stats* out) {
   if (!c || !out) return FM_ERR_INVALID;
   FM_CUDA(c, cudaSetDevice(c->device));
   FM_CUDA(c, cudaStreamSynchronize(c->stream));
-  float acc[kNumPhases] = {0};
-  for (auto& s : c->ev_match.spans) {
-    float ms = 0;
-    if (cudaEventElapsedTime(&ms, s.a, s.b) == cudaSuccess) acc[s.phase] += ms;
+  if (c->last && !c->last->waited) {
+    int rc = finalize(c->last);
+    if (rc != FM_OK) return rc;
   }
+  float ms_prep = 0;
   for (auto& s : c->ev_prep.spans) {
     float ms = 0;
-    if (cudaEventElapsedTime(&ms, s.a, s.b) == cudaSuccess) acc[kPhPrep] += ms;
+    if (cudaEventElapsedTime(&ms, s.a, s.b) == cudaSuccess) ms_prep += ms;
   }
-  c->stats.ms_total = acc[kPhTotal];
-  c->stats.ms_score = acc[kPhScore];
-  c->stats.ms_rescore = acc[kPhRescore] + acc[kPhBands];
-  c->stats.ms_exact = acc[kPhExact];
-  c->stats.ms_compact = acc[kPhCompact];
-  c->stats.ms_prep = acc[kPhPrep];
+  c->stats.ms_prep = ms_prep;
   *out = c->stats;
+  return FM_OK;
+}
+
+int fm_result_stats(fm_result* r, fm_stats* out) {
+  if (!r || !out) return FM_ERR_INVALID;
+  int rc = finalize(r);
+  if (rc != FM_OK) return rc;
+  *out = r->stats;
   return FM_OK;
 }
 

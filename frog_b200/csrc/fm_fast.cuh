@@ -80,7 +80,7 @@ inline cudaError_t fast_prepare_dirty(fm_ctx* c) {
   // the segment table is read by kernels after this function returns: stage it in memory that outlives the call
   c->h_segs = segs;
   if ((e = cudaMemcpyAsync(c->s_segs.p, c->h_segs.data(), segs.size() * sizeof(PrepSeg), cudaMemcpyHostToDevice, c->stream)) != cudaSuccess) return e;
-  if ((e = cudaStreamSynchronize(c->stream)) != cudaSuccess) return e;  // pageable source: keep it simple and safe
+  // (pageable source: cudaMemcpyAsync returns once c->h_segs has been staged, so no synchronisation is needed)
   const PrepSeg* d_segs = c->s_segs.as<PrepSeg>();
   const ImageDev* d_images = c->d_images.as<ImageDev>();
   ImageMeta* d_metas = c->d_metas.as<ImageMeta>();

@@ -130,8 +130,11 @@ struct fm_ctx {
   // per-call scratch
   fm::DevBuf d_meta_blob, d_rowres, d_chunk_count, d_chunk_out, d_totals;
   fm::DevBuf d_bands, d_cands, d_redo, d_taskinfo;
-  // caches handed to results
-  fm::DevBuf cache_out, cache_counts;
+  // free lists handed to results (several results may be in flight: FM_FLAG_ASYNC)
+  std::vector<fm::DevBuf> out_free, counts_free;
+  std::vector<std::pair<void*, size_t>> pin_free;  // pinned blocks: DeviceCounters + per-pair counts
+  std::vector<fm::EventPool> ev_free;
+  fm_result* last = nullptr;  // most recent result of fm_match (cleared when it is freed)
   void* cache_pinned = nullptr;
   size_t cache_pinned_cap = 0;
   unsigned long long* h_pinned = nullptr;  // 8 x u64 scratch for small D2H reads

@@ -83,6 +83,43 @@ def gather_match_lists(counts: torch.Tensor, pairs: torch.Tensor, dst: int = 0):
     return None
 
 
+class FixedGather:
+    """Gather of compacted match lists to rank `dst` WITHOUT a size exchange, so that no host
+    synchronisation sits between the matcher's kernels and the transfer: every rank sends its
+    per-pair counts (n_pairs int32) and its list buffer at full capacity (`cap_elems` int32 =
+    2 x outer-loop rows: a row yields at most one match, match.cpp:320-327); the receiver reads the
+    first 2 * sum(counts) entries.  `slots` receive buffers per peer let a transfer overlap the
+    next step.  start() returns the in-flight works; Work.wait() orders the current stream (NCCL)
+    or blocks the host (gloo) behind the transfer."""
+
+    def __init__(self, n_pairs: int, cap_elems: int, device, slots: int = 2, dst: int = 0):
+        self.world, self.rank, self.dst = dist.get_world_size(), dist.get_rank(), dst
+        self.n_pairs, self.cap = n_pairs, cap_elems
+        self.counts, self.pairs = [], []
+        if self.rank == dst:
+            for _ in range(slots):
+                self.counts.append([torch.zeros(n_pairs, dtype=torch.int32, device=device) for _ in range(self.world)])
+                self.pairs.append([torch.zeros(cap_elems, dtype=torch.int32, device=device) for _ in range(self.world)])
+
+    def start(self, counts: torch.Tensor, pairs_cap: torch.Tensor, slot: int = 0):
+        assert counts.numel() == self.n_pairs and pairs_cap.numel() == self.cap
+        ops = []
+        if self.rank == self.dst:
+            for r in range(self.world):
+                if r != self.dst:
+                    ops.append(dist.P2POp(dist.irecv, self.counts[slot][r], r))
+                    ops.append(dist.P2POp(dist.irecv, self.pairs[slot][r], r))
+        else:
+            ops.append(dist.P2POp(dist.isend, counts, self.dst))
+            ops.append(dist.P2POp(dist.isend, pairs_cap, self.dst))
+        return dist.batch_isend_irecv(ops) if ops else []
+
+    def received(self, slot: int, r: int):
+        """On dst, after the works completed: (counts, pairs[: 2 * sum(counts)]) of rank r != dst."""
+        c = self.counts[slot][r]
+        return c, self.pairs[slot][r][: 2 * int(c.sum().item())]
+
+
 def assemble(shards, counts_per_rank, pairs_per_rank, n_pairs: int):
     """Rank 0: undo the sharding.  Returns a list of [m,2] uint32 arrays in global pair order."""
     out = [None] * n_pairs

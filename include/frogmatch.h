@@ -41,6 +41,8 @@ typedef enum fm_status {
 #define FM_FLAG_SYM 1u          /* also run the reverse direction and append it: -sym, match.cpp:643-646 */
 #define FM_FLAG_FORCE_EXACT 2u  /* score every pair with the exact FP32 brute-force kernel only */
 #define FM_FLAG_DEVICE_ONLY 4u  /* leave the compacted lists in device memory (fm_result_fetch() copies later) */
+#define FM_FLAG_ASYNC 8u        /* return as soon as the work is queued on the context's stream; fm_result_wait()
+                                 * completes the result.  Several results may be in flight on one context. */
 
 /* ---- context --------------------------------------------------------------------------------- */
 
@@ -92,8 +94,14 @@ int fm_image_points(const fm_ctx* ctx, uint32_t img, uint32_t* n);
 int fm_match(fm_ctx* ctx, const uint32_t* pair_first, const uint32_t* pair_second, size_t n_pairs,
              float dist, float dist2second, uint32_t flags, fm_result** out);
 
+/* Complete a result of an FM_FLAG_ASYNC call: block until its kernels have finished, read the
+ * per-pair counts and (unless FM_FLAG_DEVICE_ONLY) copy the lists to pinned host memory.  A no-op
+ * for results of synchronous calls.  The device views below are valid (in stream order) without it. */
+int fm_result_wait(fm_result* r);
+
 size_t fm_result_num_pairs(const fm_result* r);
-/* Total matches over all pairs (valid once the call returned; device-only results included). */
+/* Total matches over all pairs (device-only results included).  Counts and totals are valid once
+ * fm_match returned, or, for FM_FLAG_ASYNC calls, once fm_result_wait() returned (0 before). */
 uint64_t fm_result_total(const fm_result* r);
 /* Number of matches of pair p (MatchVect::size(), match.cpp:734). */
 uint32_t fm_result_count(const fm_result* r, size_t p);
@@ -129,6 +137,8 @@ typedef struct fm_stats {
 
 /* Statistics of the most recent fm_match on this context (synchronises the stream). */
 int fm_get_stats(fm_ctx* ctx, fm_stats* out);
+/* Statistics of the call that produced `r` (waits for it; ms_prep is not attributed to a call: 0). */
+int fm_result_stats(fm_result* r, fm_stats* out);
 
 /* Library/build description, e.g. "frogmatch 0.1 sm_100a". */
 const char* fm_version(void);

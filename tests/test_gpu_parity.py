@@ -177,3 +177,35 @@ def test_full_size_engines_agree(env):
     want = port.compute_matches(img[0], sub, 1.0, 0.8)
     got = lf[0][lf[0][:, 1] < 1500]
     assert np.array_equal(got, want)
+
+
+def test_async_results_in_flight(env):
+    """FM_FLAG_ASYNC: several fm_match calls queued back to back on one context, completed out of
+    order with fm_result_wait(); every list equals the oracle's (and the synchronous call's)."""
+    m, port = env
+    images = helpers.random_group("bank", 4, 1500)
+    sched = helpers.pair_schedule(4, -1)
+    pf, ps = [s[0] for s in sched], [s[1] for s in sched]
+    m.clear()
+    for i, (d, s, l) in enumerate(images):
+        m.upload(i, d, s, l)
+    params = [(1.0, 1.0, False), (0.22, 1.0, False), (1.0, 0.8, True), (1.0, 1.0, False)]
+    want = [port.match_pairs(images, pf, ps, t, r, False) for t, r, _ in params]
+    inflight = [m.match(pf, ps, t, r, device_only=dev_only, asynchronous=True) for t, r, dev_only in params]
+    assert all(r.counts is None for r in inflight)
+    for k in (2, 0, 3, 1):  # completion order differs from submission order
+        res = inflight[k].wait()
+        if params[k][2]:
+            res.fetch()
+        assert res.total == sum(len(w) for w in want[k])
+        st = res.stats()
+        assert st["score_launches"] >= 1 and st["ms_score"] > 0
+        for g, w in zip(res.all_pairs(), want[k]):
+            assert np.array_equal(g, w)
+    for r in inflight:
+        r.free()
+    # the context is still good for a synchronous call afterwards
+    res = m.match(pf, ps, 1.0, 1.0)
+    for g, w in zip(res.all_pairs(), want[0]):
+        assert np.array_equal(g, w)
+    res.free()
