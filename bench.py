@@ -213,8 +213,16 @@ def bench_ours(args):
         raise SystemExit("bench.py: no CUDA device -- the matcher has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # stdout carries exactly ONE JSON line: native libraries that write to fd 1 (NCCL prints its version banner
+    # there) are pointed at stderr, the line itself goes to a private duplicate of the original stdout
+    sys.stdout.flush()
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL on a high-priority stream: the list transfer of one group runs while the next group's scoring kernel
+        # still has thread blocks waiting to be dispatched, and must not queue behind them
+        opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+        dist.init_process_group("nccl", device_id=dev, pg_options=opts)
     n_img, n_pts, kind, thr, ratio = WORKLOADS[args.workload]
 
     # ---- synthetic group of this rank, in pinned host memory -----------------------------------
@@ -312,15 +320,18 @@ def bench_ours(args):
     m.close()
 
     # ---- end to end: host buffers in, host lists out, through the C ABI ---------------------------
-    # Two contexts on two streams, used alternately: while one matches group k (prep + kernels + lists to pinned
-    # host memory), the other's H2D upload of group k+1 is already running on the copy engine.  Every step's
-    # H2D and D2H is inside the timed region, which is ONE CUDA-event bracket around all K steps (L2 flush
-    # writes included).
+    # Two contexts on two streams, used alternately as a three-stage pipeline: while one runs group k's prep +
+    # kernels, the other first hands group k-1's lists to pinned host memory (D2H; for N > 1 after the NCCL gather
+    # to rank 0) and then uploads group k+1 (H2D).  Every step's H2D and D2H is inside the timed region, which is
+    # ONE CUDA-event bracket around all K steps (L2 flush writes included).
     streams = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]
     ctxs = [capi.Matcher(local), capi.Matcher(local)]
     for mm, st in zip(ctxs, streams):
         mm.set_stream(st.cuda_stream)
-    pinned_out = {"buf": None}
+    e2e_gather = fdist.FixedGather(len(pf), 2 * rows_rank, dev, slots=2) if world > 1 else None
+    e2e_no = [0]
+    pinned_out = [(torch.empty(len(pf), dtype=torch.int32).pin_memory(), torch.empty(2 * rows_rank, dtype=torch.int32).pin_memory())
+                  for _ in range(world if (world > 1 and rank == 0) else 0)]
 
     def e2e_start(mm, st):
         with torch.cuda.stream(st):
@@ -336,38 +347,49 @@ def bench_ours(args):
                 res.free()
                 return d2h
             cptr, pptr = res.device_pointers()
-            got = fdist.gather_match_lists(fdist.as_torch_u32(cptr, res.n_pairs, dev), fdist.as_torch_u32(pptr, 2 * res.total, dev), 0)
+            pairs_cap = fdist.as_torch_u32(pptr, 2 * rows_rank, dev)
+            slot = e2e_no[0] % 2
+            e2e_no[0] += 1
+            for w in e2e_gather.start(fdist.as_torch_u32(cptr, res.n_pairs, dev), pairs_cap, slot):
+                w.wait()
             d2h = 0
-            if got is not None:
-                for c, p in zip(*got):
-                    n = p.numel()
-                    if pinned_out["buf"] is None or pinned_out["buf"].numel() < n:
-                        pinned_out["buf"] = torch.empty(max(n, 1) * 2, dtype=torch.int32).pin_memory()
-                    pinned_out["buf"][:n].copy_(p, non_blocking=True)
-                    d2h += n * 4 + c.numel() * 4
-                    c.cpu()
+            if rank == 0:
+                # rank 0: its own lists plus every peer's counts and (capacity-sized) list buffer to pinned host memory
+                n = 2 * res.total
+                pinned_out[0][1][:n].copy_(pairs_cap[:n], non_blocking=True)
+                d2h += n * 4 + res.n_pairs * 4
+                for r in range(1, world):
+                    pinned_out[r][0].copy_(e2e_gather.counts[slot][r], non_blocking=True)
+                    pinned_out[r][1].copy_(e2e_gather.pairs[slot][r], non_blocking=True)
+                    d2h += (len(pf) + 2 * rows_rank) * 4
                 st.synchronize()
             res.free()
             return d2h
 
     def timed_e2e(steps, warmup):
-        d2h, total = [], warmup + steps
+        d2h, total, prev = [], warmup + steps, None
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ctxs[0].clear()
         upload_all(ctxs[0])
         for k in range(total):
             cur, st = ctxs[k % 2], streams[k % 2]
             if k == warmup:
+                if prev is not None:
+                    d2h.append(e2e_finish(*prev))
+                    prev = None
                 barrier()  # every stream of every rank is idle: start the clock
                 e0.record(st)
                 cur.clear()
                 upload_all(cur)  # pipeline fill: the first timed group's own upload is inside the region
-            res = e2e_start(cur, st)
+            res = e2e_start(cur, st)  # group k: prep + kernels queued
+            if prev is not None:
+                d2h.append(e2e_finish(*prev))  # group k-1: lists to (rank 0's) pinned host memory, under group k's kernels
             if k + 1 < total and k + 1 != warmup:
                 nxt = ctxs[(k + 1) % 2]
                 nxt.clear()
-                upload_all(nxt)  # group k+1: H2D from pinned host memory, overlapping group k's kernels
-            d2h.append(e2e_finish(res, st))
+                upload_all(nxt)  # group k+1: H2D from pinned host memory, under group k's kernels
+            prev = (res, st)
+        d2h.append(e2e_finish(*prev))
         e1.record(streams[(total - 1) % 2])
         barrier()
         ms = e0.elapsed_time(e1)
@@ -431,7 +453,7 @@ def bench_ours(args):
             except Exception as e:  # the baseline must never take the GPU numbers down with it
                 line["cpu_baseline"] = {"value": None, "unit": "descriptor pairs/s", "cores": os.cpu_count(), "kind": "reference",
                                         "sample": f"failed: {e}"}
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=json_out, flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
