@@ -339,32 +339,61 @@ def bench_ours(args):
             # prep + kernels queued, call returns; lists go to pinned host memory in e2e_finish (world == 1)
             return mm.match(pf, ps, thr, ratio, device_only=world > 1, asynchronous=True)
 
+    host_ms = collections.defaultdict(float)  # host wall-clock per e2e phase (this rank), timed steps only
+
+    class phase:
+        def __init__(self, name):
+            self.name = name
+
+        def __enter__(self):
+            self.t = time.perf_counter()
+
+        def __exit__(self, *a):
+            host_ms[self.name] += (time.perf_counter() - self.t) * 1e3
+
+    # N > 1: list transfers of a finished group run beside the next group's upload, on streams of their own
+    drain = [torch.cuda.Stream(device=dev) for _ in range(world if rank == 0 else 1)]
+
     def e2e_finish(res, st):
-        with torch.cuda.stream(st):
-            res.wait()
-            if world == 1:
-                d2h = res.total * 8 + res.n_pairs * 4
-                res.free()
-                return d2h
+        if world == 1:
+            with phase("wait_fetch"):
+                res.wait()  # counts, then the lists to pinned host memory (D2H on the context's stream)
+            d2h = res.total * 8 + res.n_pairs * 4
+            res.free()
+            return d2h
+        with phase("wait_kernels"):
+            res.wait()  # the group's kernels are done; its lists sit in the result's own device buffers
+        with phase("gather_d2h"):
             cptr, pptr = res.device_pointers()
             pairs_cap = fdist.as_torch_u32(pptr, 2 * rows_rank, dev)
             slot = e2e_no[0] % 2
             e2e_no[0] += 1
-            for w in e2e_gather.start(fdist.as_torch_u32(cptr, res.n_pairs, dev), pairs_cap, slot):
-                w.wait()
+            with torch.cuda.stream(drain[0]):
+                works = e2e_gather.start(fdist.as_torch_u32(cptr, res.n_pairs, dev), pairs_cap, slot, per_peer=True)
             d2h = 0
             if rank == 0:
-                # rank 0: its own lists plus every peer's counts and (capacity-sized) list buffer to pinned host memory
-                n = 2 * res.total
-                pinned_out[0][1][:n].copy_(pairs_cap[:n], non_blocking=True)
-                d2h += n * 4 + res.n_pairs * 4
+                # rank 0: its own lists, then every peer's counts and (capacity-sized) list buffer to pinned host memory,
+                # each peer on a stream of its own so that its D2H copy starts as soon as ITS lists have arrived
+                with torch.cuda.stream(drain[0]):
+                    n = 2 * res.total
+                    pinned_out[0][1][:n].copy_(pairs_cap[:n], non_blocking=True)
+                    d2h += n * 4 + res.n_pairs * 4
                 for r in range(1, world):
-                    pinned_out[r][0].copy_(e2e_gather.counts[slot][r], non_blocking=True)
-                    pinned_out[r][1].copy_(e2e_gather.pairs[slot][r], non_blocking=True)
+                    with torch.cuda.stream(drain[r]):
+                        for w in works[r]:
+                            w.wait()
+                        pinned_out[r][0].copy_(e2e_gather.counts[slot][r], non_blocking=True)
+                        pinned_out[r][1].copy_(e2e_gather.pairs[slot][r], non_blocking=True)
                     d2h += (len(pf) + 2 * rows_rank) * 4
-                st.synchronize()
-            res.free()
-            return d2h
+                for st_r in drain:
+                    st_r.synchronize()  # lists are on the host
+            else:
+                with torch.cuda.stream(drain[0]):
+                    for w in works[0]:
+                        w.wait()
+                drain[0].synchronize()  # lists have left this GPU
+        res.free()
+        return d2h
 
     def timed_e2e(steps, warmup):
         d2h, total, prev = [], warmup + steps, None
@@ -378,16 +407,22 @@ def bench_ours(args):
                     d2h.append(e2e_finish(*prev))
                     prev = None
                 barrier()  # every stream of every rank is idle: start the clock
+                host_ms.clear()
                 e0.record(st)
                 cur.clear()
                 upload_all(cur)  # pipeline fill: the first timed group's own upload is inside the region
-            res = e2e_start(cur, st)  # group k: prep + kernels queued
+            with phase("start_prep"):
+                res = e2e_start(cur, st)  # group k: prep + kernels queued
+            if k + 1 < total and k + 1 != warmup:
+                # group k+1: H2D from pinned host memory, under group k's kernels.  Its context is the one that ran
+                # group k-1; that group's lists live in the result's own buffers, not in the image arena.
+                nxt = ctxs[(k + 1) % 2]
+                with phase("clear"):
+                    nxt.clear()
+                with phase("upload_enqueue"):
+                    upload_all(nxt)
             if prev is not None:
                 d2h.append(e2e_finish(*prev))  # group k-1: lists to (rank 0's) pinned host memory, under group k's kernels
-            if k + 1 < total and k + 1 != warmup:
-                nxt = ctxs[(k + 1) % 2]
-                nxt.clear()
-                upload_all(nxt)  # group k+1: H2D from pinned host memory, under group k's kernels
             prev = (res, st)
         d2h.append(e2e_finish(*prev))
         e1.record(streams[(total - 1) % 2])
@@ -430,7 +465,8 @@ def bench_ours(args):
                                  "used alternately so a group's H2D upload overlaps the previous group's kernels",
                        "matches_per_step": matches_all},
             "e2e": {"value": total_pairs * args.steps / (ms_e2e * 1e-3), "unit": "descriptor pairs/s",
-                    "h2d_bytes_per_step": h2d_all, "d2h_bytes_per_step": d2h_all, "ms_per_step": ms_e2e / args.steps},
+                    "h2d_bytes_per_step": h2d_all, "d2h_bytes_per_step": d2h_all, "ms_per_step": ms_e2e / args.steps,
+                    "rank0_host_ms_per_step": {k: round(v / args.steps, 4) for k, v in host_ms.items()}},
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": achieved / peak_tf, "traffic": measured_traffic(args.workload), "peak_source": which + " (cuBLAS bf16 burst)",

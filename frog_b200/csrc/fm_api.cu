@@ -703,7 +703,7 @@ int fm_debug_score_unit(fm_ctx* c, uint32_t first_img, uint32_t second_img, uint
                                               c->d_bands.as<uint2>());
   score_kernel<true><<<1, kScoreThreads, kScoreSmemBytes, c->stream>>>(
       c->d_images.as<ImageDev>(), d_task.as<Task>(), d_meta.as<uint32_t>() + 2, 1, 1, c->d_bands.as<uint2>(),
-      c->d_cands.as<Cand>(), nullptr, d_dump.as<float>(), ld, row_block);
+      c->d_cands.as<Cand>(), nullptr, d_dump.as<float>(), ld, row_block, 0);
   FM_CUDA(c, cudaGetLastError());
   FM_CUDA(c, cudaStreamSynchronize(c->stream));
   const uint32_t r0 = row_block * kUnitRows, nr = std::min<uint32_t>(kUnitRows, nB - r0);

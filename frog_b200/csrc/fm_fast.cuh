@@ -147,10 +147,11 @@ inline cudaError_t fast_match_batch(fm_ctx* c, const FastBatchArgs& a) {
     Span sp(&c->ev_match, c->stream, kPhScore);
     // FM_PROBE=1|2 selects a timing-attribution variant of the kernel (wrong results, see fm_score.cuh)
     static const int probe = getenv("FM_PROBE") ? atoi(getenv("FM_PROBE")) : 0;
+    static const uint32_t pre_tiles = getenv("FM_PRE") ? (uint32_t)atoi(getenv("FM_PRE")) : kPreTiles;
     auto kern = probe == 1 ? score_kernel<false, 1> : probe == 2 ? score_kernel<false, 2> : score_kernel<false, 0>;
     kern<<<a.units, kScoreThreads, kScoreSmemBytes, c->stream>>>(
         a.images, a.tasks, a.unit_off, a.n_tasks, a.segs, c->d_bands.as<uint2>(), c->d_cands.as<Cand>(),
-        &a.counters->scored_cols, nullptr, 0, 0);
+        &a.counters->scored_cols, nullptr, 0, 0, pre_tiles);
   }
   {
     Span sp(&c->ev_match, c->stream, kPhRescore);

@@ -34,6 +34,7 @@ constexpr int kTopK = 8;        // candidate slots written per (row, column segm
 constexpr int kCapSlots = 22;  // capture list entries per row in shared memory
 constexpr int kAccCols = 2 * 2 * kTileCols;  // TMEM columns: 2 stages x 2 row halves
 constexpr int kEpiWarps = 8;
+constexpr uint32_t kPreTiles = 8;  // look-ahead tiles per unit (score_kernel); FM_PRE overrides it for experiments
 constexpr int kScoreThreads = (2 + kEpiWarps) * 32;  // warp 0: TMA + TMEM allocator, warp 1: MMA, warps 2..9: epilogue
 
 struct Cand {
@@ -245,9 +246,14 @@ __device__ __forceinline__ void fold_second(const ChunkMax& c, float f15, float&
 // warp votes -- four 8-column groups, then the 3-column nodes of a group some row hit -- so every
 // branch is warp-uniform, and the per-row captures are predicated stores: lanes never diverge
 // and a typical entry (one row, one column) costs ~45 instructions.
+//
+// upd / cap (warp-uniform): the first tiles of a unit are visited twice (see score_kernel) -- a look-ahead visit
+// that only tracks the two largest chunk maxima (upd, !cap) and a capture visit against the threshold the
+// look-ahead established (!upd, cap: the chunk maxima must not be folded in a second time, g2 has to stay the
+// score of a column distinct from g1's).  Every other tile is visited once with both set.
 template <bool kMasked, int kProbe>
 __device__ __forceinline__ void score_pair(const uint32_t (&ra)[16], const uint32_t (&rb)[16], uint32_t col0, uint32_t lo,
-                                           uint32_t width, RowScan& st, float two_eps) {
+                                           uint32_t width, RowScan& st, float two_eps, bool upd, bool cap) {
   constexpr uint32_t kAll = 0xffffffffu;
   // An entry may append up to kEntryRoom columns per row without further checks; beyond that the
   // predicated store is suppressed and the row is marked for the exact kernel.
@@ -258,25 +264,28 @@ __device__ __forceinline__ void score_pair(const uint32_t (&ra)[16], const uint3
   const ChunkMax b = chunk_max<kMasked>(rb, col0 + 16, lo, width, fb);
   const float hi = fmaxf(a.m, b.m), lw = fminf(a.m, b.m);
   // top two of {g1, g2, hi, lw} (g1 >= g2, hi >= lw)
-  const float g2n = max3(st.g2, lw, fminf(st.g1, hi));
-  st.g1 = fmaxf(st.g1, hi);
+  const float hi_u = upd ? hi : -INFINITY, lw_u = upd ? lw : -INFINITY;
+  const float g2n = max3(st.g2, lw_u, fminf(st.g1, hi_u));
+  st.g1 = fmaxf(st.g1, hi_u);
   st.g2 = g2n;
   if (kProbe != 1) st.thr = st.g2 - two_eps;
   float th = st.thr;
-  if (__any_sync(kAll, hi > th)) {
-    if (kProbe != 1 && __any_sync(kAll, hi > th && st.g2 == -INFINITY)) {
-      // First scored columns of a row: seed the threshold with the second largest of the twelve
-      // node maxima (disjoint column sets, so it cannot exceed the row's second-best score)
-      // instead of capturing every column against thr = -inf.
-      float h = -INFINITY, sec = -INFINITY;
-      fold_second(a, fa[15], h, sec);
-      fold_second(b, fb[15], h, sec);
-      const bool seed = st.g2 == -INFINITY;
-      st.g2 = seed ? sec : st.g2;
-      st.thr = th = seed ? sec - two_eps : th;
-    }
-    // room for kEntryRoom appends, once per entry
-    if (__any_sync(kAll, hi > th && st.capw - st.cap > kFullAt)) {
+  const bool hit = cap && hi > th;
+  if (__any_sync(kAll, hit)) {
+    // Two rare situations share one vote: a row without a threshold yet, a row whose list is nearly full.
+    if (__any_sync(kAll, hit && (st.g2 == -INFINITY || st.capw - st.cap > kFullAt))) {
+      if (kProbe != 1 && __any_sync(kAll, hit && st.g2 == -INFINITY)) {
+        // First scored columns of a row: seed the threshold with the second largest of the twelve
+        // node maxima (disjoint column sets, so it cannot exceed the row's second-best score)
+        // instead of capturing every column against thr = -inf.
+        float h = -INFINITY, sec = -INFINITY;
+        fold_second(a, fa[15], h, sec);
+        fold_second(b, fb[15], h, sec);
+        const bool seed = st.g2 == -INFINITY;
+        st.g2 = seed ? sec : st.g2;
+        st.thr = th = seed ? sec - two_eps : th;
+      }
+      // room for kEntryRoom appends, once per entry
       if (hi > th && st.capw - st.cap > kFullAt) {
         const uint32_t w = cap_make_room(st.cap, st.capw, th);
         st.ovf |= w & 1u;
@@ -287,26 +296,31 @@ __device__ __forceinline__ void score_pair(const uint32_t (&ra)[16], const uint3
     const bool va = __any_sync(kAll, a.ga > th), vb = __any_sync(kAll, a.gb > th);
     const bool vc = __any_sync(kAll, b.ga > th), vd = __any_sync(kAll, b.gb > th);
 #define FM_TRY(f, base, e) cap_append_if_above(st.capw, cap_end, f[e], th, col0 + (base) + (e))
-#define FM_NODE(mk, f, base, e0, e1, e2) \
-    if (__any_sync(kAll, (mk) > th)) { FM_TRY(f, base, e0); FM_TRY(f, base, e1); FM_TRY(f, base, e2); }
+#define FM_NODE(v, f, base, e0, e1, e2) \
+    if (v) { FM_TRY(f, base, e0); FM_TRY(f, base, e1); FM_TRY(f, base, e2); }
+    // the node votes of a group are taken together, before any of its branches: one vote latency per group
     if (va) {
-      FM_NODE(a.m0, fa, 0, 0, 1, 2)
-      FM_NODE(a.m1, fa, 0, 3, 4, 5)
-      FM_NODE(a.m2, fa, 0, 6, 7, 8)
+      const bool n0 = __any_sync(kAll, a.m0 > th), n1 = __any_sync(kAll, a.m1 > th), n2 = __any_sync(kAll, a.m2 > th);
+      FM_NODE(n0, fa, 0, 0, 1, 2)
+      FM_NODE(n1, fa, 0, 3, 4, 5)
+      FM_NODE(n2, fa, 0, 6, 7, 8)
     }
     if (vb) {
-      FM_NODE(a.m3, fa, 0, 9, 10, 11)
-      FM_NODE(a.m4, fa, 0, 12, 13, 14)
+      const bool n0 = __any_sync(kAll, a.m3 > th), n1 = __any_sync(kAll, a.m4 > th);
+      FM_NODE(n0, fa, 0, 9, 10, 11)
+      FM_NODE(n1, fa, 0, 12, 13, 14)
       FM_TRY(fa, 0, 15);
     }
     if (vc) {
-      FM_NODE(b.m0, fb, 16, 0, 1, 2)
-      FM_NODE(b.m1, fb, 16, 3, 4, 5)
-      FM_NODE(b.m2, fb, 16, 6, 7, 8)
+      const bool n0 = __any_sync(kAll, b.m0 > th), n1 = __any_sync(kAll, b.m1 > th), n2 = __any_sync(kAll, b.m2 > th);
+      FM_NODE(n0, fb, 16, 0, 1, 2)
+      FM_NODE(n1, fb, 16, 3, 4, 5)
+      FM_NODE(n2, fb, 16, 6, 7, 8)
     }
     if (vd) {
-      FM_NODE(b.m3, fb, 16, 9, 10, 11)
-      FM_NODE(b.m4, fb, 16, 12, 13, 14)
+      const bool n0 = __any_sync(kAll, b.m3 > th), n1 = __any_sync(kAll, b.m4 > th);
+      FM_NODE(n0, fb, 16, 9, 10, 11)
+      FM_NODE(n1, fb, 16, 12, 13, 14)
       FM_TRY(fb, 16, 15);
     }
 #undef FM_NODE
@@ -319,7 +333,7 @@ __device__ __forceinline__ void score_pair(const uint32_t (&ra)[16], const uint3
 // One 64-column accumulator tile of one row: two pairs of TMEM loads.
 template <bool kMasked, bool kDump, int kProbe>
 __device__ __forceinline__ void score_tile(uint32_t taddr, uint32_t cb, uint32_t lo, uint32_t width, RowScan& st,
-                                           float two_eps, uint32_t bar_release, float* dump_row) {
+                                           float two_eps, uint32_t bar_release, float* dump_row, bool upd, bool cap) {
   uint32_t ra[16], rb[16];
   // Rolled on purpose: one copy of the capture code stays resident in the instruction cache.
 #pragma unroll 1
@@ -341,7 +355,7 @@ __device__ __forceinline__ void score_tile(uint32_t taddr, uint32_t cb, uint32_t
         dump_row[cb + (c + 1) * 16 + e] = __uint_as_float(rb[e]);
       }
     }
-    score_pair<kMasked, kProbe>(ra, rb, cb + c * 16, lo, width, st, two_eps);
+    score_pair<kMasked, kProbe>(ra, rb, cb + c * 16, lo, width, st, two_eps, upd, cap);
   }
 }
 
@@ -359,7 +373,7 @@ __global__ void __launch_bounds__(kScoreThreads, 2)
 score_kernel(const ImageDev* __restrict__ images, const Task* __restrict__ tasks,
              const uint32_t* __restrict__ unit_off, uint32_t n_tasks, uint32_t segs,
              const uint2* __restrict__ bands, Cand* __restrict__ cands, unsigned long long* __restrict__ scored_cols,
-             float* __restrict__ dump, uint32_t dump_ld, uint32_t unit_base) {
+             float* __restrict__ dump, uint32_t dump_ld, uint32_t unit_base, uint32_t pre_tiles) {
   extern __shared__ uint8_t smem_raw[];
   ScoreSmem& sm = *reinterpret_cast<ScoreSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
 
@@ -406,6 +420,13 @@ score_kernel(const ImageDev* __restrict__ images, const Task* __restrict__ tasks
     tile0 = tb + (uint32_t)(((uint64_t)nt * seg) / segs);
     n_tiles = tb + (uint32_t)(((uint64_t)nt * (seg + 1)) / segs) - tile0;
   }
+  // Look-ahead: the first n_pre tiles are scored twice.  A streaming top-2 scan captures ~2 ln(columns) columns per
+  // row, most of them early, while the running threshold is still far below its final value -- and a capture by
+  // ONE row costs its whole warp the slow path.  Visiting the first tiles once without capturing establishes
+  // the threshold of a 64 * n_pre column prefix before the first column is captured: a few tiles of extra
+  // MMA work (the tensor pipe has slack) for about a third fewer slow-path entries and no list overflow handling.
+  const uint32_t n_pre = kDump ? 0u : min(pre_tiles, n_tiles / 4);
+  const uint32_t n_sched = n_tiles + n_pre;
 
   RowScan st;
   st.g1 = st.g2 = -INFINITY;
@@ -437,11 +458,12 @@ score_kernel(const ImageDev* __restrict__ images, const Task* __restrict__ tasks
         ptx::bulk_g2s(sm.a[0], rowop, kOpTileBytes, &sm.bar_a);
         ptx::bulk_g2s(sm.a[1], rowop + kOpTileBytes, kOpTileBytes, &sm.bar_a);
         const uint8_t* colop = reinterpret_cast<const uint8_t*>(A.colop);
-        for (uint32_t i = 0; i < n_tiles; i++) {
+        for (uint32_t i = 0; i < n_sched; i++) {
           const uint32_t stg = i % kStages, use = i / kStages;
+          const uint32_t tile = tile0 + (i < n_pre ? i : i - n_pre);
           if (use > 0) ptx::mbar_wait(&sm.bar_bempty[stg], (use - 1) & 1);
           ptx::mbar_expect_tx(&sm.bar_bfull[stg], kTileBytes);
-          ptx::bulk_g2s(sm.b[stg], colop + (size_t)(tile0 + i) * kTileBytes, kTileBytes, &sm.bar_bfull[stg]);
+          ptx::bulk_g2s(sm.b[stg], colop + (size_t)tile * kTileBytes, kTileBytes, &sm.bar_bfull[stg]);
         }
       }
     } else if (warp == 1) {
@@ -451,7 +473,7 @@ score_kernel(const ImageDev* __restrict__ images, const Task* __restrict__ tasks
         const uint64_t adesc0 = ptx::umma_desc_sw128(ptx::smem_u32(sm.a[0]));
         const uint64_t adesc1 = ptx::umma_desc_sw128(ptx::smem_u32(sm.a[1]));
         ptx::mbar_wait(&sm.bar_a, 0);
-        for (uint32_t i = 0; i < n_tiles; i++) {
+        for (uint32_t i = 0; i < n_sched; i++) {
           const uint32_t stg = i % kStages, acc = i & 1, use = i >> 1;
           if (use > 0) ptx::mbar_wait(&sm.bar_accempty[acc][0], (use - 1) & 1);
           ptx::mbar_wait(&sm.bar_bfull[stg], (i / kStages) & 1);
@@ -487,9 +509,10 @@ score_kernel(const ImageDev* __restrict__ images, const Task* __restrict__ tasks
       uint32_t bar_full = ptx::smem_u32(&sm.bar_accfull[0][half]);
       asm volatile("" : "+r"(bar_full));
       static_assert(offsetof(ScoreSmem, bar_accempty) - offsetof(ScoreSmem, bar_accfull) == 32, "barrier layout");
-      for (uint32_t i = 0; i < n_tiles; i++) {
+      for (uint32_t i = 0; i < n_sched; i++) {
         const uint32_t acc = i & 1;
-        const uint32_t cb = (tile0 + i) * kTileCols;
+        const uint32_t cb = (tile0 + (i < n_pre ? i : i - n_pre)) * kTileCols;
+        const bool cap = i >= n_pre, upd = i < n_pre || i >= 2 * n_pre;  // look-ahead visit, capture visit, both
         ptx::mbar_wait_u32(bar_full + acc * 16, (i >> 1) & 1);
         ptx::tc_fence_after();
         const uint32_t taddr = tmem_lane + acc * (2 * kTileCols);
@@ -499,10 +522,10 @@ score_kernel(const ImageDev* __restrict__ images, const Task* __restrict__ tasks
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive_u32(bar_full + 32 + acc * 16);
         } else if (!kDump && cb >= w_imin && cb + kTileCols <= w_imax) {
-          score_tile<false, kDump, kProbe>(taddr, cb, lo, width, st, two_eps, bar_full + 32 + acc * 16, dump_row);
+          score_tile<false, kDump, kProbe>(taddr, cb, lo, width, st, two_eps, bar_full + 32 + acc * 16, dump_row, upd, cap);
           scored += kTileCols;
         } else {
-          score_tile<true, kDump, kProbe>(taddr, cb, lo, width, st, two_eps, bar_full + 32 + acc * 16, dump_row);
+          score_tile<true, kDump, kProbe>(taddr, cb, lo, width, st, two_eps, bar_full + 32 + acc * 16, dump_row, upd, cap);
           scored += kTileCols;
         }
       }

@@ -101,17 +101,22 @@ class FixedGather:
                 self.counts.append([torch.zeros(n_pairs, dtype=torch.int32, device=device) for _ in range(self.world)])
                 self.pairs.append([torch.zeros(cap_elems, dtype=torch.int32, device=device) for _ in range(self.world)])
 
-    def start(self, counts: torch.Tensor, pairs_cap: torch.Tensor, slot: int = 0):
+    def start(self, counts: torch.Tensor, pairs_cap: torch.Tensor, slot: int = 0, per_peer: bool = False):
+        """Queue the transfer.  Returns the in-flight works: one flat list, or with per_peer=True a dict
+        {peer: works} on dst (one batch per peer, so a peer's lists can be consumed -- e.g. copied to the
+        host -- while the next peer's are still arriving) and {dst: works} on the senders."""
         assert counts.numel() == self.n_pairs and pairs_cap.numel() == self.cap
+        if self.rank != self.dst:
+            works = dist.batch_isend_irecv([dist.P2POp(dist.isend, counts, self.dst), dist.P2POp(dist.isend, pairs_cap, self.dst)])
+            return {self.dst: works} if per_peer else works
+        peers = [r for r in range(self.world) if r != self.dst]
+        if per_peer:
+            return {r: dist.batch_isend_irecv([dist.P2POp(dist.irecv, self.counts[slot][r], r),
+                                               dist.P2POp(dist.irecv, self.pairs[slot][r], r)]) for r in peers}
         ops = []
-        if self.rank == self.dst:
-            for r in range(self.world):
-                if r != self.dst:
-                    ops.append(dist.P2POp(dist.irecv, self.counts[slot][r], r))
-                    ops.append(dist.P2POp(dist.irecv, self.pairs[slot][r], r))
-        else:
-            ops.append(dist.P2POp(dist.isend, counts, self.dst))
-            ops.append(dist.P2POp(dist.isend, pairs_cap, self.dst))
+        for r in peers:
+            ops.append(dist.P2POp(dist.irecv, self.counts[slot][r], r))
+            ops.append(dist.P2POp(dist.irecv, self.pairs[slot][r], r))
         return dist.batch_isend_irecv(ops) if ops else []
 
     def received(self, slot: int, r: int):
