@@ -55,6 +55,11 @@ def build_cli(force: bool = False) -> str:
            os.path.join(CSRC, "match_main.cpp"), os.path.join(CSRC, "keypoint_io.cpp"),
            "-o", BIN, "-L", os.path.dirname(LIB), "-lfrogmatch", "-lz",
            "-Wl,-rpath,$ORIGIN/../frog_b200"]
+    # multi-GPU list gather over NCCL (system libnccl; only the executable links it, never libfrogmatch.so, so a
+    # Python process that already carries torch's NCCL is not given a second copy)
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    if os.path.exists("/usr/include/nccl.h") and os.path.exists(os.path.join(cuda, "include", "cuda_runtime.h")):
+        cmd += ["-DFM_WITH_NCCL", "-I", os.path.join(cuda, "include"), "-L", os.path.join(cuda, "lib64"), "-lnccl", "-lcudart"]
     subprocess.run(cmd, check=True, cwd=ROOT)
     return BIN
 

@@ -2,7 +2,7 @@
 //
 //   match <listfile-or-directory> [-o out] [-d dist] [-d2 ratio] [-n N] [-sp thr] [-np n] [-nt threads]
 //         [-zmin z] [-zmax z] [-sym] [-targ k]            (reference keys, same meaning)
-//         [-gpus G] [-exact 1] [-stats file.json]         (new keys; unknown to the reference)
+//         [-gpus G] [-exact 1] [-stats file.json] [-gather nccl|host]   (new keys; unknown to the reference)
 //
 // Same argv quirks (every key consumes two tokens except -sym, match.cpp:365-431), same keypoint
 // readers, same stdout protocol, byte-identical pairs.bin.  The pairing phase (match.cpp:638-652)
@@ -27,6 +27,11 @@
 
 #include "frogmatch.h"
 #include "keypoint_io.h"
+
+#ifdef FM_WITH_NCCL
+#include <cuda_runtime.h>
+#include <nccl.h>
+#endif
 
 namespace fs = std::filesystem;
 using std::cerr;
@@ -97,6 +102,88 @@ void run_gpu_job(GpuJob& job, const std::vector<fmio::KeypointSet>& images, cons
   job.match_s = now_s() - t0;
 }
 
+#ifdef FM_WITH_NCCL
+// Multi-GPU result hand-off: every GPU leaves its compacted match lists in device
+// memory (FM_FLAG_DEVICE_ONLY); they travel GPU-to-GPU over NVLink to GPU 0 (one grouped
+// ncclSend/ncclRecv per peer) and reach the host in ONE device-to-host copy, mirroring the single
+// writer of match.cpp:660-745.  One process, one communicator per GPU (ncclCommInitAll), brought
+// up on a background thread while the keypoint files load.
+struct NcclGather {
+  std::vector<ncclComm_t> comms;
+  std::vector<cudaStream_t> streams;
+  std::vector<int> devices;
+  string error;
+  uint32_t* d_stage = nullptr;  // on devices[0]: the peers' lists, concatenated
+  uint32_t* h_stage = nullptr;  // pinned
+  double init_s = 0, gather_s = 0;
+
+  void init(int n) {
+    const double t0 = now_s();
+    devices.resize(n);
+    std::iota(devices.begin(), devices.end(), 0);
+    comms.assign(n, nullptr);
+    ncclResult_t r = ncclCommInitAll(comms.data(), n, devices.data());
+    if (r != ncclSuccess) { error = string("ncclCommInitAll: ") + ncclGetErrorString(r); comms.clear(); return; }
+    streams.assign(n, nullptr);
+    for (int g = 0; g < n; g++) {
+      cudaError_t e = cudaSetDevice(g);
+      if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&streams[g], cudaStreamNonBlocking);
+      if (e != cudaSuccess) { error = string("NCCL gather stream: ") + cudaGetErrorString(e); return; }
+    }
+    init_s = now_s() - t0;
+  }
+
+  // lists[g] / totals[g]: device pointer and match count of GPU g's result (g < n_used).  Returns, per
+  // peer g >= 1, the host pointer of its concatenated lists in `host_of` (host_of[0] stays null: GPU 0's
+  // own lists are fetched through the library).
+  bool gather(const std::vector<const uint32_t*>& lists, const std::vector<uint64_t>& totals, std::vector<const uint32_t*>& host_of) {
+    const double t0 = now_s();
+    const int n_used = (int)lists.size();
+    host_of.assign(n_used, nullptr);
+    uint64_t elems = 0;
+    std::vector<uint64_t> off(n_used, 0);
+    for (int g = 1; g < n_used; g++) { off[g] = elems; elems += 2 * totals[g]; }
+    if (elems == 0) return true;
+    auto cu = [&](cudaError_t e, const char* what) {
+      if (e != cudaSuccess) { error = string(what) + ": " + cudaGetErrorString(e); return false; }
+      return true;
+    };
+    auto nc = [&](ncclResult_t r, const char* what) {
+      if (r != ncclSuccess) { error = string(what) + ": " + ncclGetErrorString(r); return false; }
+      return true;
+    };
+    if (!cu(cudaSetDevice(devices[0]), "cudaSetDevice")) return false;
+    if (!cu(cudaMalloc(reinterpret_cast<void**>(&d_stage), elems * sizeof(uint32_t)), "cudaMalloc(gather stage)")) return false;
+    if (!cu(cudaMallocHost(reinterpret_cast<void**>(&h_stage), elems * sizeof(uint32_t)), "cudaMallocHost(gather stage)")) return false;
+    if (!nc(ncclGroupStart(), "ncclGroupStart")) return false;
+    for (int g = 1; g < n_used; g++) {
+      if (totals[g] == 0) continue;
+      if (!nc(ncclSend(lists[g], 2 * totals[g], ncclUint32, 0, comms[g], streams[g]), "ncclSend")) return false;
+      if (!nc(ncclRecv(d_stage + off[g], 2 * totals[g], ncclUint32, g, comms[0], streams[0]), "ncclRecv")) return false;
+    }
+    if (!nc(ncclGroupEnd(), "ncclGroupEnd")) return false;
+    if (!cu(cudaSetDevice(devices[0]), "cudaSetDevice")) return false;
+    if (!cu(cudaMemcpyAsync(h_stage, d_stage, elems * sizeof(uint32_t), cudaMemcpyDeviceToHost, streams[0]), "gather D2H")) return false;
+    for (int g = 0; g < n_used; g++) {
+      if (!cu(cudaSetDevice(devices[g]), "cudaSetDevice")) return false;
+      if (!cu(cudaStreamSynchronize(streams[g]), "gather synchronize")) return false;
+    }
+    for (int g = 1; g < n_used; g++) host_of[g] = h_stage + off[g];
+    gather_s = now_s() - t0;
+    return true;
+  }
+
+  ~NcclGather() {
+    if (d_stage) { cudaSetDevice(devices[0]); cudaFree(d_stage); }
+    if (h_stage) cudaFreeHost(h_stage);
+    for (size_t g = 0; g < streams.size(); g++)
+      if (streams[g]) { cudaSetDevice(devices[g]); cudaStreamDestroy(streams[g]); }
+    for (auto c : comms)
+      if (c) ncclCommDestroy(c);
+  }
+};
+#endif
+
 }  // namespace
 
 int main(int argc, char* argv[]) {
@@ -119,6 +206,11 @@ int main(int argc, char* argv[]) {
   int target = -1;
   int gpus = -1;
   const char* statsFile = nullptr;
+  // How the lists of GPUs 1.. reach the writer: "host" = every GPU copies its own lists over its own PCIe link,
+  // "nccl" = GPU-to-GPU over NVLink to GPU 0, then one device-to-host copy.  Bringing the communicators up
+  // (ncclCommInitAll, 1.5-2 s measured) costs a one-shot process more than matching a 50 x 50k group, so "host"
+  // is the default here; long-lived callers (bench.py under torchrun) gather over NCCL.
+  const char* gatherMode = "host";
 
   // match.cpp:365-431: key = argv[k], value = argv[k+1]; advance by 2, by 1 for -sym.
   for (int k = 2; k < argc;) {
@@ -140,6 +232,7 @@ int main(int argc, char* argv[]) {
       if (has("-gpus")) gpus = atoi(value);
       if (has("-exact")) forceExact = atoi(value) != 0;
       if (has("-stats")) statsFile = value;
+      if (has("-gather")) gatherMode = value;
     }
     if (has("-all")) matchAll = true;
     if (has("-p")) writePoints = true;
@@ -211,6 +304,24 @@ int main(int argc, char* argv[]) {
     return 1;
   }
 
+  // The NCCL communicators (one per GPU that will get image pairs) come up on their own thread, under the file
+  // loading and the matching; it is joined just before the gather.
+#ifdef FM_WITH_NCCL
+  NcclGather gatherer;  // declared before the thread's joiner: destroyed after the thread has been joined
+#endif
+  std::thread nccl_thread;
+  struct NcclJoiner {
+    std::thread& t;
+    ~NcclJoiner() { if (t.joinable()) t.join(); }
+  } nccl_joiner{nccl_thread};
+#ifdef FM_WITH_NCCL
+  {
+    const size_t n_load = std::min<size_t>(filenames.size(), (size_t)std::max(N, 0));
+    const size_t planned_pairs = n_load < 2 ? 0 : (target >= 0 ? n_load - 1 : n_load * (n_load - 1) / 2);
+    const int G_plan = (int)std::min<size_t>((size_t)G_max, std::max<size_t>(planned_pairs, 1));
+    if (G_plan > 1 && strcmp(gatherMode, "nccl") == 0) nccl_thread = std::thread([&gatherer, G_plan]() { gatherer.init(G_plan); });
+  }
+#endif
   cout << "Found " << filenames.size() << " files, loading : " << fmin(N, filenames.size()) << endl;
   start = std::chrono::system_clock::now();
   if (filenames.size() > (size_t)N) filenames.resize(N);
@@ -302,11 +413,14 @@ int main(int argc, char* argv[]) {
       std::sort(jobs[g].pair_ids.begin(), jobs[g].pair_ids.end());  // consecutive pairs share the first image
     }
   }
+  // (a failed NCCL start-up is reported when the thread is joined; the lists of GPUs 1.. are then fetched per GPU)
+  const bool use_nccl = nccl_thread.joinable() && G > 1;
   const uint32_t flags = (symFlag ? FM_FLAG_SYM : 0u) | (forceExact ? FM_FLAG_FORCE_EXACT : 0u);
   {
     std::vector<std::thread> threads;
     for (int g = 1; g < G; g++)
-      threads.emplace_back(run_gpu_job, std::ref(jobs[g]), std::cref(images), std::cref(indices), dist, dist2second, flags);
+      threads.emplace_back(run_gpu_job, std::ref(jobs[g]), std::cref(images), std::cref(indices), dist, dist2second,
+                           flags | (use_nccl ? FM_FLAG_DEVICE_ONLY : 0u));
     run_gpu_job(jobs[0], images, indices, dist, dist2second, flags);
     for (auto& t : threads) t.join();
   }
@@ -314,20 +428,41 @@ int main(int argc, char* argv[]) {
     if (!j.error.empty()) { cerr << "match: GPU " << j.device << ": " << j.error << endl; return 1; }
 
   // gather: per pair, where its list lives
+  bool nccl_ok = true;
+  std::vector<const uint32_t*> host_of(G, nullptr);  // NCCL gather: host copy of GPU g's concatenated lists (g >= 1)
+#ifdef FM_WITH_NCCL
+  if (nccl_thread.joinable()) nccl_thread.join();
+  if (use_nccl && (!gatherer.error.empty() || (int)gatherer.comms.size() < G)) {
+    cerr << "match: NCCL gather unavailable (" << gatherer.error << "); fetching the match lists per GPU" << endl;
+    for (int g = 1; g < G; g++)
+      if (fm_result_fetch(jobs[g].res) != FM_OK) { cerr << "match: GPU " << g << ": " << fm_last_error(jobs[g].ctx) << endl; return 1; }
+    nccl_ok = false;
+  }
+  if (use_nccl && nccl_ok) {
+    std::vector<const uint32_t*> lists(G);
+    std::vector<uint64_t> totals(G);
+    for (int g = 0; g < G; g++) { lists[g] = fm_result_device_pairs(jobs[g].res); totals[g] = fm_result_total(jobs[g].res); }
+    if (!gatherer.gather(lists, totals, host_of)) { cerr << "match: " << gatherer.error << endl; return 1; }
+  }
+#endif
   std::vector<fmio::PairBlock> by_pair(indices.size());
   long long sum = 0;
-  for (auto& j : jobs)
+  for (int g = 0; g < G; g++) {
+    GpuJob& j = jobs[g];
+    uint64_t off = 0;
     for (size_t k = 0; k < j.pair_ids.size(); k++) {
       const size_t id = j.pair_ids[k];
       fmio::PairBlock b;
       b.first = indices[id].first;
       b.second = indices[id].second;
       b.count = fm_result_count(j.res, k);
-      b.pairs = fm_result_pairs(j.res, k);
+      b.pairs = (use_nccl && nccl_ok && g > 0) ? host_of[g] + 2 * off : fm_result_pairs(j.res, k);
+      off += b.count;
       by_pair[id] = b;
       sum += b.count;
       cout << "." << std::flush;  // match.cpp:650
     }
+  }
   end = std::chrono::system_clock::now();
   const float pairing_s = std::chrono::duration<float>(end - start).count();
   cout << " : " << pairing_s << "s" << endl;
@@ -375,7 +510,12 @@ int main(int argc, char* argv[]) {
        << ", \"scored_pairs\": " << tot.scored_pairs << ", \"rows\": " << tot.rows << ", \"rows_exact\": " << tot.rows_exact
        << ", \"candidates\": " << tot.candidates << ", \"kernel_launches\": " << tot.kernel_launches
        << ", \"gpu_ms_max\": " << ms_max << ", \"pairing_s\": " << pairing_s << ", \"ctx_create_s\": " << create_s
-       << ", \"upload_s\": " << upload_s << ", \"match_call_s\": " << match_s << ", \"matches\": " << sum << "}" << endl;
+       << ", \"upload_s\": " << upload_s << ", \"match_call_s\": " << match_s << ", \"matches\": " << sum
+       << ", \"gather\": \"" << (use_nccl && nccl_ok ? "nccl" : (G > 1 ? "host" : "none")) << "\""
+#ifdef FM_WITH_NCCL
+       << ", \"nccl_init_s\": " << gatherer.init_s << ", \"nccl_gather_s\": " << gatherer.gather_s
+#endif
+       << "}" << endl;
   }
   for (auto& j : jobs) {
     fm_result_free(j.res);

@@ -31,6 +31,7 @@ ap.add_argument("--gpus", type=int, default=1)
 ap.add_argument("--sub", type=int, default=0, help="images the reference is run on (0 = all)")
 ap.add_argument("--fmt", default=None)
 ap.add_argument("--keep", action="store_true")
+ap.add_argument("--gather", default=None, choices=["nccl", "host"], help="bin/match -gather (multi-GPU list hand-off)")
 a = ap.parse_args()
 n_img, n_pts, kind, fmt, flags = CONFIGS[a.config]
 fmt = a.fmt or fmt
@@ -43,7 +44,7 @@ try:
     res["generate_s"] = round(time.time() - t0, 2)
     out, stats = os.path.join(tmp, "pairs.bin"), os.path.join(tmp, "stats.json")
     t0 = time.time()
-    r = subprocess.run([build.BIN, lst, "-o", out, "-gpus", str(a.gpus), "-stats", stats] + flags, capture_output=True, text=True)
+    r = subprocess.run([build.BIN, lst, "-o", out, "-gpus", str(a.gpus), "-stats", stats] + flags + (["-gather", a.gather] if a.gather else []), capture_output=True, text=True)
     res["match_wall_s"] = round(time.time() - t0, 3)
     if r.returncode != 0:
         print(r.stdout[-2000:], r.stderr[-2000:]); sys.exit(2)

@@ -55,3 +55,19 @@ def test_cli_vs_reference_binary_fresh_group(built, tmp_path):
     assert open(out, "rb").read() == open(ref_out, "rb").read()
     nb = [l for l in ref.stdout.splitlines() if l.startswith("Nb Match")][0]
     assert nb in new.stdout
+
+
+@pytest.mark.parametrize("gather", ["host", "nccl"])
+def test_cli_two_gpus_gather(built, golden_dir, tmp_path, gather):
+    """-gpus 2: image pairs sharded over two GPUs, lists merged on the host or gathered to GPU 0 over NCCL;
+    either way the file is the reference's, byte for byte."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    out, stats = str(tmp_path / "p.bin"), str(tmp_path / "s.json")
+    r = subprocess.run([build.BIN, os.path.join(golden_dir, "list_bin.txt"), "-o", out, "-d", "1", "-gpus", "2",
+                        "-gather", gather, "-stats", stats], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert open(out, "rb").read() == open(os.path.join(golden_dir, "bin_runsh.pairs.bin"), "rb").read()
+    s = json.load(open(stats))
+    assert s["gpus"] == 2 and s["gather"] == gather
