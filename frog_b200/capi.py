@@ -18,6 +18,7 @@ FLAG_SYM = 1
 FLAG_FORCE_EXACT = 2
 FLAG_DEVICE_ONLY = 4
 FLAG_ASYNC = 8
+FLAG_MATCH_ALL = 16
 
 # every symbol include/frogmatch.h declares (checked by tests/test_abi.py)
 PUBLIC_SYMBOLS = [
@@ -216,11 +217,13 @@ class Matcher:
                                             C.c_void_p(lap_ptr), n, d))
 
     def match(self, pair_first, pair_second, dist: float = 0.22, ratio: float = 1.0, sym: bool = False,
-              force_exact: bool = False, device_only: bool = False, asynchronous: bool = False) -> Result:
+              force_exact: bool = False, device_only: bool = False, asynchronous: bool = False,
+              match_all: bool = False) -> Result:
         pf = np.ascontiguousarray(pair_first, np.uint32)
         ps = np.ascontiguousarray(pair_second, np.uint32)
         flags = (FLAG_SYM if sym else 0) | (FLAG_FORCE_EXACT if force_exact else 0) | \
-                (FLAG_DEVICE_ONLY if device_only else 0) | (FLAG_ASYNC if asynchronous else 0)
+                (FLAG_DEVICE_ONLY if device_only else 0) | (FLAG_ASYNC if asynchronous else 0) | \
+                (FLAG_MATCH_ALL if match_all else 0)
         h = C.c_void_p()
         self._check(self._L.fm_match(self._h, _ptr(pf), _ptr(ps), pf.shape[0], dist, ratio, flags, C.byref(h)))
         return Result(self, h, pending=asynchronous)

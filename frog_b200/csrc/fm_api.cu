@@ -6,6 +6,7 @@
 
 #include "../../include/frogmatch.h"
 #include "../../include/frogmatch_debug.h"
+#include "fm_all.cuh"
 #include "fm_compact.cuh"
 #include "fm_exact.cuh"
 #include "fm_fast.cuh"
@@ -212,7 +213,7 @@ void fm_destroy(fm_ctx* c) {
   cudaStreamSynchronize(c->stream);
   c->arena.release();
   DevBuf* bufs[] = {&c->s_keys, &c->s_keys_sorted, &c->s_idx, &c->s_idx_sorted, &c->s_norm2, &c->s_sort, &c->s_segs, &c->d_images, &c->d_metas, &c->d_meta_blob, &c->d_rowres, &c->d_chunk_count, &c->d_chunk_out,
-                    &c->d_totals, &c->d_bands, &c->d_cands, &c->d_redo, &c->d_taskinfo};
+                    &c->d_totals, &c->d_bands, &c->d_cands, &c->d_redo, &c->d_taskinfo, &c->d_all, &c->d_all_tasks};
   for (auto* b : bufs) b->release();
   for (auto& b : c->out_free) b.release();
   for (auto& b : c->counts_free) b.release();
@@ -338,6 +339,7 @@ int fm_match(fm_ctx* c, const uint32_t* pair_first, const uint32_t* pair_second,
   int rc = sync_images(c);
   if (rc != FM_OK) return rc;
   const bool sym = flags & FM_FLAG_SYM;
+  const bool match_all = flags & FM_FLAG_MATCH_ALL;
   const bool force_exact = (flags & FM_FLAG_FORCE_EXACT) || c->dim != (uint32_t)kD;
 
   // ---- tasks --------------------------------------------------------------------------------
@@ -365,7 +367,8 @@ int fm_match(fm_ctx* c, const uint32_t* pair_first, const uint32_t* pair_second,
   uint32_t segs = 1;
   if (base_units > 0 && base_units < (uint64_t)2 * c->sm_count)
     segs = (uint32_t)std::min<uint64_t>(8, ((uint64_t)2 * c->sm_count + base_units - 1) / base_units);
-  constexpr uint32_t kMaxBatchRows = 24u << 20;
+  if (match_all && total_rows > 0xFFFFFFF0ull) return fail(c, FM_ERR_UNSUPPORTED, "fm_match: -all supports at most 2^32 outer-loop rows per call");
+  const uint32_t kMaxBatchRows = match_all ? 0xFFFFFFF0u : (24u << 20);  // -all: one batch (its scan spans all rows)
   std::vector<Batch> batches;
   std::vector<uint32_t> blk_off, chunk_off, unit_off;
   for (uint32_t t = 0; t < n_tasks;) {
@@ -468,7 +471,73 @@ int fm_match(fm_ctx* c, const uint32_t* pair_first, const uint32_t* pair_second,
   const ImageDev* d_images = c->d_images.as<ImageDev>();
   uint32_t* d_rowres = c->d_rowres.as<uint32_t>();
   DeviceCounters* d_counters = c->d_totals.as<DeviceCounters>();
-  {
+  if (match_all) {
+    // ---- -all: count pass, per-task scan, emit pass (fm_all.cuh); list sizes are data-dependent ----
+    Span total_span(&c->ev_match, c->stream, kPhTotal);
+    std::vector<unsigned long long> task_total(std::max<uint32_t>(n_tasks, 1), 0), task_base(std::max<uint32_t>(n_tasks, 1), 0);
+    std::vector<uint32_t> pair_counts(std::max<size_t>(n_pairs, 1), 0);
+    unsigned long long grand = 0;
+    if (!batches.empty() && batches[0].rows > 0) {
+      const Batch& b = batches[0];
+      const size_t rows = b.rows;
+      FM_CUDA_R(c->d_all.ensure(rows * (3 * sizeof(uint32_t) + sizeof(unsigned long long)) + 16));
+      FM_CUDA_R(c->d_all_tasks.ensure((size_t)n_tasks * 2 * sizeof(unsigned long long)));
+      unsigned long long* row_off = c->d_all.as<unsigned long long>();
+      uint32_t* row_count = reinterpret_cast<uint32_t*>(row_off + rows);
+      uint32_t* row_final = row_count + rows;
+      uint32_t* row_carry = row_final + rows;
+      unsigned long long* d_task_total = c->d_all_tasks.as<unsigned long long>();
+      unsigned long long* d_task_base = d_task_total + n_tasks;
+      const bool d48 = c->dim == (uint32_t)kD;
+      const size_t smem = exact_smem_bytes((int)c->dim, !d48);
+      if (!d48 && !c->all_attr_set) {
+        FM_CUDA_R(cudaFuncSetAttribute(match_all_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        FM_CUDA_R(cudaFuncSetAttribute(match_all_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        c->all_attr_set = true;
+      }
+      {
+        Span sp(&c->ev_match, c->stream, kPhExact);
+        if (d48)
+          match_all_kernel<kD, false><<<b.blocks, kExactRows, smem, c->stream>>>(d_images, d_tasks, d_blk, n_tasks, dist, row_count,
+                                                                                 row_final, nullptr, nullptr, nullptr, nullptr);
+        else
+          match_all_kernel<0, false><<<b.blocks, kExactRows, smem, c->stream>>>(d_images, d_tasks, d_blk, n_tasks, dist, row_count,
+                                                                                row_final, nullptr, nullptr, nullptr, nullptr);
+        all_scan_kernel<<<(n_tasks + 63) / 64, 64, 0, c->stream>>>(d_images, d_tasks, n_tasks, row_count, row_final, row_carry, row_off,
+                                                                    d_task_total);
+      }
+      FM_CUDA_R(cudaMemcpyAsync(task_total.data(), d_task_total, (size_t)n_tasks * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+      FM_CUDA_R(cudaStreamSynchronize(c->stream));
+      for (uint32_t t = 0; t < n_tasks; t++) {
+        task_base[t] = grand;
+        grand += task_total[t];
+        const unsigned long long pc = (unsigned long long)pair_counts[pair_of_task[t]] + task_total[t];
+        if (pc > 0xFFFFFFFFull) { fm_result_free(r); return fail(c, FM_ERR_UNSUPPORTED, "fm_match: an -all list exceeds 2^32 pairs (pairs.bin block sizes are u32, match.cpp:734)"); }
+        pair_counts[pair_of_task[t]] = (uint32_t)pc;
+      }
+      FM_CUDA_R(r->d_out.ensure(std::max<unsigned long long>(grand, 1) * sizeof(uint2)));
+      FM_CUDA_R(cudaMemcpyAsync(d_task_base, task_base.data(), (size_t)n_tasks * sizeof(unsigned long long), cudaMemcpyHostToDevice, c->stream));
+      {
+        Span sp(&c->ev_match, c->stream, kPhExact);
+        if (d48)
+          match_all_kernel<kD, true><<<b.blocks, kExactRows, smem, c->stream>>>(d_images, d_tasks, d_blk, n_tasks, dist, nullptr, nullptr,
+                                                                                row_carry, row_off, d_task_base, r->d_out.as<uint2>());
+        else
+          match_all_kernel<0, true><<<b.blocks, kExactRows, smem, c->stream>>>(d_images, d_tasks, d_blk, n_tasks, dist, nullptr, nullptr,
+                                                                               row_carry, row_off, d_task_base, r->d_out.as<uint2>());
+      }
+      FM_CUDA_R(cudaStreamSynchronize(c->stream));  // task_base (pageable) must outlive the copy
+      c->stats.kernel_launches += 3;
+      c->stats.rows_exact += total_rows;
+    }
+    // hand the totals to the common tail: DeviceCounters.running_total and the per-pair counts
+    DeviceCounters hc{};
+    hc.running_total = grand;
+    FM_CUDA_R(cudaMemcpyAsync(c->d_totals.p, &hc, sizeof hc, cudaMemcpyHostToDevice, c->stream));
+    if (n_pairs)
+      FM_CUDA_R(cudaMemcpyAsync(r->d_counts.p, pair_counts.data(), n_pairs * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+    FM_CUDA_R(cudaStreamSynchronize(c->stream));
+  } else {
     Span total_span(&c->ev_match, c->stream, kPhTotal);
     for (auto& b : batches) {
       const uint32_t nt = b.t1 - b.t0;

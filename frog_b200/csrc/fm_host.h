@@ -130,6 +130,7 @@ struct fm_ctx {
   // per-call scratch
   fm::DevBuf d_meta_blob, d_rowres, d_chunk_count, d_chunk_out, d_totals;
   fm::DevBuf d_bands, d_cands, d_redo, d_taskinfo;
+  fm::DevBuf d_all, d_all_tasks;  // -all mode: per-row count / final / carry / offset, per-task totals and bases
   // free lists handed to results (several results may be in flight: FM_FLAG_ASYNC)
   std::vector<fm::DevBuf> out_free, counts_free;
   std::vector<std::pair<void*, size_t>> pin_free;  // pinned blocks: DeviceCounters + per-pair counts
@@ -140,6 +141,6 @@ struct fm_ctx {
   unsigned long long* h_pinned = nullptr;  // 8 x u64 scratch for small D2H reads
   fm::EventPool ev_match, ev_prep;
   fm_stats stats{};
-  bool exact_attr_set = false, score_attr_set = false;
+  bool exact_attr_set = false, score_attr_set = false, all_attr_set = false;
   std::string err;
 };

@@ -1,7 +1,7 @@
 // match_main.cpp -- drop-in replacement for valette/FROG's `bin/match` (match/match.cpp:340-747).
 //
 //   match <listfile-or-directory> [-o out] [-d dist] [-d2 ratio] [-n N] [-sp thr] [-np n] [-nt threads]
-//         [-zmin z] [-zmax z] [-sym] [-targ k]            (reference keys, same meaning)
+//         [-zmin z] [-zmax z] [-sym] [-targ k] [-all x]   (reference keys, same meaning)
 //         [-gpus G] [-exact 1] [-stats file.json] [-gather nccl|host]   (new keys; unknown to the reference)
 //
 // Same argv quirks (every key consumes two tokens except -sym, match.cpp:365-431), same keypoint
@@ -239,11 +239,6 @@ int main(int argc, char* argv[]) {
     if (has("-sym")) { symFlag = true; k -= 1; }
     k += 2;
   }
-  if (matchAll) {
-    cerr << "match: -all is not supported by the B200 build (the reference emits stale column ids in this "
-            "mode, match.cpp:295-300)" << endl;
-    return 1;
-  }
   if (anatVal != 0.0f) {
     cerr << "match: -anat is not supported (the reference reads uninitialised transformedCoordinates, "
             "match.cpp:548-559)" << endl;
@@ -415,7 +410,8 @@ int main(int argc, char* argv[]) {
   }
   // (a failed NCCL start-up is reported when the thread is joined; the lists of GPUs 1.. are then fetched per GPU)
   const bool use_nccl = nccl_thread.joinable() && G > 1;
-  const uint32_t flags = (symFlag ? FM_FLAG_SYM : 0u) | (forceExact ? FM_FLAG_FORCE_EXACT : 0u);
+  const uint32_t flags = (symFlag ? FM_FLAG_SYM : 0u) | (forceExact ? FM_FLAG_FORCE_EXACT : 0u) |
+                         (matchAll ? FM_FLAG_MATCH_ALL : 0u);  // -all: match.cpp:295-300, bug-compatible (fm_all.cuh)
   {
     std::vector<std::thread> threads;
     for (int g = 1; g < G; g++)

@@ -41,6 +41,9 @@ typedef enum fm_status {
 #define FM_FLAG_SYM 1u          /* also run the reverse direction and append it: -sym, match.cpp:643-646 */
 #define FM_FLAG_FORCE_EXACT 2u  /* score every pair with the exact FP32 brute-force kernel only */
 #define FM_FLAG_DEVICE_ONLY 4u  /* leave the compacted lists in device memory (fm_result_fetch() copies later) */
+#define FM_FLAG_MATCH_ALL 16u    /* the reference's -all mode, bug-compatible (match.cpp:295-300): every gated-in column under
+                                 * `dist` emits a pair naming the running nearest column that was NOT under it; dist2second is
+                                 * ignored; lists can hold up to N_first * N_second pairs.  Exact FP32 kernels only. */
 #define FM_FLAG_ASYNC 8u        /* return as soon as the work is queued on the context's stream; fm_result_wait()
                                  * completes the result.  Several results may be in flight on one context. */
 

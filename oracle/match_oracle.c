@@ -37,7 +37,8 @@ float mo_norm(const float* a, const float* b, int size) {
  * Outer loop over rows of `second` (:262), inner over rows of `first` (:267); Laplacian gate
  * (:270), scale-ratio gate against the double constant 1.3 (:273-275), top-2 with strict '<'
  * (:303-313), acceptance (:320-321), emit orientation (:323-327).  `match` is deliberately NOT
- * reset per row (:259).  -all and -anat are out of scope.
+ * reset per row (:259).  -all is restated separately below (mo_compute_matches_all); -anat is out of
+ * scope.
  * out_pairs: 2 * n_second uint32.  Returns the number of matches.
  */
 int64_t mo_compute_matches(const float* desc_first, const float* scale_first, const float* lap_first,
@@ -79,6 +80,70 @@ int64_t mo_compute_matches(const float* desc_first, const float* scale_first, co
     }
   }
   return n_out;
+}
+
+/*
+ * match/match.cpp:255-336 with matchAll == true (the `-all` key, :417-418).  Every gated-in column
+ * whose distance is under the threshold emits a pair (:295-300) -- but the pair names `match`, the
+ * running nearest among the columns that were NOT under the threshold (:303-313 is the `else` of
+ * :295), carried over from earlier rows when the current row has not seen such a column yet
+ * (`match` is declared outside the row loop, :259).  Nothing is emitted at the end of a row (:319).
+ * out_pairs may be NULL (count only); otherwise at most `cap` pairs are written.  Returns the count.
+ */
+int64_t mo_compute_matches_all(const float* desc_first, const float* scale_first, const float* lap_first,
+                               uint32_t n_first, const float* desc_second, const float* scale_second,
+                               const float* lap_second, uint32_t n_second, uint32_t d, float threshold,
+                               int sym, uint32_t* out_pairs, int64_t cap) {
+  int64_t n_out = 0;
+  int match = 0;
+  for (int i = 0; i < (int)n_second; i++) {
+    float d1 = FLT_MAX, d2 = FLT_MAX;
+    const float* di = desc_second + (size_t)i * d;
+    for (int j = 0; j < (int)n_first; j++) {
+      if (lap_second[i] != lap_first[j]) continue;
+      if (((double)(scale_second[i] / scale_first[j]) > 1.3) ||
+          ((double)(scale_first[j] / scale_second[i]) > 1.3))
+        continue;
+      float dist = mo_norm(di, desc_first + (size_t)j * d, (int)d);
+      if (sqrtf(dist) < threshold) {
+        if (out_pairs && n_out < cap) {
+          out_pairs[2 * n_out] = sym ? (uint32_t)i : (uint32_t)match;
+          out_pairs[2 * n_out + 1] = sym ? (uint32_t)match : (uint32_t)i;
+        }
+        n_out++;
+      } else if (dist < d1) {
+        d2 = d1;
+        d1 = dist;
+        match = j;
+      } else if (dist < d2) {
+        d2 = dist;
+      }
+    }
+  }
+  return n_out;
+}
+
+/* -all over a list of image pairs (:638-652): counts[p] = size of pair p's list (forward pass, then the
+ * -sym reverse pass appended); with out_pairs != NULL the lists are written at out_pairs + 2*out_offsets[p]. */
+void mo_match_pairs_all(const float* desc, const float* scale, const float* lap, const int64_t* offsets,
+                        uint32_t d, const uint32_t* pair_first, const uint32_t* pair_second, int64_t n_pairs,
+                        float threshold, int sym, const int64_t* out_offsets, uint32_t* out_pairs,
+                        int64_t* counts) {
+#pragma omp parallel for schedule(dynamic)
+  for (int64_t p = 0; p < n_pairs; p++) {
+    uint32_t a = pair_first[p], b = pair_second[p];
+    uint32_t na = (uint32_t)(offsets[a + 1] - offsets[a]), nb = (uint32_t)(offsets[b + 1] - offsets[b]);
+    uint32_t* out = out_pairs ? out_pairs + 2 * out_offsets[p] : NULL;
+    int64_t cap = out_pairs ? out_offsets[p + 1] - out_offsets[p] : 0;
+    int64_t n = mo_compute_matches_all(desc + offsets[a] * d, scale + offsets[a], lap + offsets[a], na,
+                                       desc + offsets[b] * d, scale + offsets[b], lap + offsets[b], nb, d,
+                                       threshold, 0, out, cap);
+    if (sym)
+      n += mo_compute_matches_all(desc + offsets[b] * d, scale + offsets[b], lap + offsets[b], nb,
+                                  desc + offsets[a] * d, scale + offsets[a], lap + offsets[a], na, d,
+                                  threshold, 1, out ? out + 2 * n : NULL, out ? cap - n : 0);
+    counts[p] = n;
+  }
 }
 
 /*

@@ -48,6 +48,10 @@ class _CMLib:
         self._cm = getattr(self.lib, prefix + "compute_matches")
         self._cm.argtypes = _CM_ARGS
         self._cm.restype = C.c_int64
+        self._cma = getattr(self.lib, prefix + "compute_matches_all")
+        self._cma.argtypes = [_f32p, _f32p, _f32p, C.c_uint32, _f32p, _f32p, _f32p, C.c_uint32, C.c_uint32,
+                              C.c_float, C.c_int, C.c_void_p, C.c_int64]
+        self._cma.restype = C.c_int64
         self._norm = getattr(self.lib, prefix + "norm")
         self._norm.argtypes = [_f32p, _f32p, C.c_int]
         self._norm.restype = C.c_float
@@ -64,6 +68,17 @@ class _CMLib:
         out = np.zeros((max(d2.shape[0], 1), 2), np.uint32)
         n = self._cm(d1, s1, l1, d1.shape[0], d2, s2, l2, d2.shape[0], d1.shape[1],
                      threshold, ratio, int(sym), out.reshape(-1))
+        return out[:n].copy()
+
+
+    def compute_matches_all(self, first, second, threshold: float, sym: bool = False) -> np.ndarray:
+        """ComputeMatches with matchAll = true (`-all`, match.cpp:295-300): [M,2] uint32 as pushed."""
+        d1, s1, l1 = map(_f32, first)
+        d2, s2, l2 = map(_f32, second)
+        args = (d1, s1, l1, d1.shape[0], d2, s2, l2, d2.shape[0], d1.shape[1], threshold, int(sym))
+        n = self._cma(*args, None, 0)
+        out = np.zeros((max(n, 1), 2), np.uint32)
+        self._cma(*args, out.ctypes.data_as(C.c_void_p), n)
         return out[:n].copy()
 
 
@@ -111,6 +126,29 @@ class PortLib(_CMLib):
                                 threshold, ratio, int(sym), out_off, out, counts)
         return [out[2 * out_off[p]: 2 * (out_off[p] + counts[p])].reshape(-1, 2).copy()
                 for p in range(pf.shape[0])]
+
+    def match_pairs_all(self, images, pair_first, pair_second, threshold, sym=False):
+        """`-all` over image pairs: list of [M,2] uint32 per pair (count pass, then fill pass)."""
+        desc = _f32(np.concatenate([im[0] for im in images]))
+        scale = _f32(np.concatenate([im[1] for im in images]))
+        lap = _f32(np.concatenate([im[2] for im in images]))
+        ns = np.array([im[1].shape[0] for im in images], np.int64)
+        offsets = np.concatenate([[0], np.cumsum(ns)]).astype(np.int64)
+        pf = np.ascontiguousarray(pair_first, np.uint32)
+        ps = np.ascontiguousarray(pair_second, np.uint32)
+        counts = np.zeros(pf.shape[0], np.int64)
+        fn = self.lib.mo_match_pairs_all
+        fn.argtypes = [_f32p, _f32p, _f32p, _i64p, C.c_uint32, _u32p, _u32p, C.c_int64, C.c_float, C.c_int,
+                       C.c_void_p, C.c_void_p, _i64p]
+        fn.restype = None
+        fn(desc, scale, lap, offsets, desc.shape[1], pf, ps, pf.shape[0], threshold, int(sym), None, None, counts)
+        out_off = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+        out = np.zeros(2 * max(int(out_off[-1]), 1), np.uint32)
+        counts2 = np.zeros_like(counts)
+        fn(desc, scale, lap, offsets, desc.shape[1], pf, ps, pf.shape[0], threshold, int(sym),
+           out_off.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p), counts2)
+        assert np.array_equal(counts, counts2)
+        return [out[2 * out_off[p]: 2 * out_off[p + 1]].reshape(-1, 2).copy() for p in range(pf.shape[0])]
 
     def read_bin(self, path: str) -> np.ndarray:
         cap = os.path.getsize(path) // 216 + 2

@@ -50,6 +50,25 @@ int64_t ref_compute_matches(const float* desc_first, const float* scale_first, c
   return n;
 }
 
+// The same with matchAll = true (the `-all` key, match.cpp:417-418).  Writes at most `cap` pairs, returns the
+// size of the reference's list.
+int64_t ref_compute_matches_all(const float* desc_first, const float* scale_first, const float* lap_first,
+                                uint32_t n_first, const float* desc_second, const float* scale_second,
+                                const float* lap_second, uint32_t n_second, uint32_t d, float threshold,
+                                int sym, uint32_t* out_pairs, int64_t cap) {
+  Points p2, p1;
+  fill_points(p2, desc_first, scale_first, lap_first, n_first, d);
+  fill_points(p1, desc_second, scale_second, lap_second, n_second, d);
+  MatchVect* m = ComputeMatches(p2, p1, threshold, 1.0f, true, 0.0f, sym != 0);
+  int64_t n = (int64_t)m->size();
+  for (int64_t k = 0; k < n && k < cap; k++) {
+    out_pairs[2 * k] = (*m)[k].first;
+    out_pairs[2 * k + 1] = (*m)[k].second;
+  }
+  delete m;
+  return n;
+}
+
 // Reference distances for chosen (row of second image, column of first image) pairs.
 void ref_distances(const float* desc_first, const float* desc_second, uint32_t d,
                    const uint32_t* first_idx, const uint32_t* second_idx, int64_t n, float* out) {

@@ -80,6 +80,10 @@ CASES = {
     "gz_default": ("list_gz.txt", []),
     "csv_relative": ("list_csv.txt", ["-d", "1", "-d2", "0.9"]),
     "csv_quirks": ("list_quirks.txt", ["-d", "1"]),
+    # -all (desk UI): every gated-in column under -d emits a pair naming the stale running nearest (match.cpp:295-300);
+    # the key is a flag but the parser skips the token after it
+    "bin_all": ("list_bin.txt", ["-d", "0.3", "-all", "1"]),
+    "bin_all_sym": ("list_bin.txt", ["-all", "1", "-d", "0.45", "-sym"]),
 }
 
 

@@ -14,7 +14,7 @@ from frog_b200 import hostio
 def parse_args(argv):
     """match.cpp:365-431: key/value pairs, every key advances by 2 except -sym (1)."""
     o = dict(N=1000000, sp=0.0, np=1000000, dist=np.float32(0.22), ratio=np.float32(1.0), zmin=np.float32(-1e20),
-             zmax=np.float32(1e20), sym=False, target=-1, out=None)
+             zmax=np.float32(1e20), sym=False, target=-1, out=None, all=False)
     k = 0
     while k < len(argv):
         key = argv[k]
@@ -29,6 +29,8 @@ def parse_args(argv):
             if key == "-zmax": o["zmax"] = np.float32(float(val))
             if key == "-o": o["out"] = val
             if key == "-targ": o["target"] = int(val)
+        if key == "-all":  # a flag, but the parser still skips the token after it (match.cpp:417-418, 430)
+            o["all"] = True
         if key == "-sym":
             o["sym"] = True
             k -= 1

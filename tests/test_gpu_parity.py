@@ -209,3 +209,45 @@ def test_async_results_in_flight(env):
     for g, w in zip(res.all_pairs(), want[0]):
         assert np.array_equal(g, w)
     res.free()
+
+
+@pytest.mark.parametrize("thr,sym", [(0.22, False), (0.45, True), (1.0, False)])
+def test_match_all_mode(env, thr, sym):
+    """FM_FLAG_MATCH_ALL = the reference's -all (match.cpp:295-300), stale `match` and all: lists equal the
+    oracle's, pair for pair, in emission order."""
+    m, port = env
+    images = helpers.random_group("bank", 4, 700)
+    images[1] = tuple(x[:333] for x in images[1])
+    images.append(tuple(x[:0] for x in images[0]))  # an empty image on either side
+    sched = helpers.pair_schedule(5, -1)
+    pf, ps = [s[0] for s in sched], [s[1] for s in sched]
+    want = port.match_pairs_all(images, pf, ps, thr, sym)
+    m.clear()
+    for i, (d, s, l) in enumerate(images):
+        m.upload(i, d, s, l)
+    res = m.match(pf, ps, thr, 1.0, sym=sym, match_all=True)
+    assert res.total == sum(len(w) for w in want) and res.total > 0
+    for p, (g, w) in enumerate(zip(res.all_pairs(), want)):
+        assert np.array_equal(g, w), f"pair {p}: {len(g)} vs {len(w)}"
+    res.free()
+
+
+def test_match_all_generic_descriptor_length(env):
+    m, port = env
+    rng = np.random.default_rng(5)
+    images = []
+    for i in range(3):
+        n = 150 + 10 * i
+        d = rng.normal(size=(n, 24)).astype(np.float32)
+        d /= np.linalg.norm(d, axis=1, keepdims=True)
+        images.append((d, rng.uniform(1.0, 1.5, n).astype(np.float32), rng.integers(0, 2, n).astype(np.float32)))
+    pf, ps = [0, 0, 1], [1, 2, 2]
+    want = port.match_pairs_all(images, pf, ps, 1.25, True)
+    m.clear()
+    for i, (d, s, l) in enumerate(images):
+        m.upload(i, d, s, l)
+    res = m.match(pf, ps, 1.25, 1.0, sym=True, match_all=True)
+    assert res.total == sum(len(w) for w in want) and res.total > 0
+    for g, w in zip(res.all_pairs(), want):
+        assert np.array_equal(g, w)
+    res.free()

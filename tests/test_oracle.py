@@ -84,6 +84,30 @@ def test_known_answers(libs):
     assert cm((e[:1] * 0.5, one, one * 0), row, thr=float(np.nextafter(np.float32(d), np.float32(9)))) == [[0, 0]]
 
 
+def test_match_all_port_equals_reference(libs):
+    """`-all` (matchAll, match.cpp:295-300): the C port against the verbatim reference in-process, including the
+    stale `match` carried across rows and the -sym orientation."""
+    port, ref = libs
+    if ref is None:
+        pytest.skip("oracle/_ref/libmatch_ref.so not built here")
+    from frog_b200 import synth
+    for seed in range(3):
+        a, b = synth.make("bank", 300, seed), synth.make("bank", 260, seed + 5)
+        A, B = (a.desc, a.scale, a.lap), (b.desc, b.scale, b.lap)
+        for thr in (0.22, 0.6, 5.0):
+            for sym in (False, True):
+                assert np.array_equal(ref.compute_matches_all(A, B, thr, sym), port.compute_matches_all(A, B, thr, sym))
+    # known answer: rows 0 and 1 both lie within the threshold of column 1 only; column 0 is far.  Row 0 meets the far
+    # column first (match = 0), row 1 has its own far column 0 as well -> both emit (0, row); a third row that sees NO
+    # far column before its near one inherits the previous row's value.
+    e = np.eye(48, dtype=np.float32)
+    first = (np.stack([e[0], e[1] * 0.5]), np.ones(2, np.float32), np.zeros(2, np.float32))
+    second = (np.stack([e[1] * 0.6, e[1] * 0.55, e[1] * 0.5]), np.ones(3, np.float32), np.zeros(3, np.float32))
+    assert port.compute_matches_all(first, second, 0.2).tolist() == [[0, 0], [0, 1], [0, 2]]
+    first_r = (first[0][::-1].copy(), first[1], first[2])  # near column first: row 0 emits the initial match = 0
+    assert port.compute_matches_all(first_r, second, 0.2).tolist() == [[0, 0], [1, 1], [1, 2]]
+
+
 @pytest.mark.parametrize("name,case", CASES)
 def test_golden_pairs_bin(libs, golden_dir, tmp_path, name, case):
     """host readers/pruning/writer (the C++ bin/match runs) + oracle port == reference bytes."""
@@ -91,8 +115,12 @@ def test_golden_pairs_bin(libs, golden_dir, tmp_path, name, case):
     opts = helpers.parse_args(case["args"])
     filenames, rigids, heads, descs = helpers.load_group(os.path.join(golden_dir, case["list"]), opts)
     sched = helpers.pair_schedule(len(filenames), opts["target"])
-    lists = port.match_pairs(helpers.images_of(heads, descs), [s[0] for s in sched], [s[1] for s in sched],
-                             opts["dist"], opts["ratio"], opts["sym"])
+    if opts["all"]:
+        lists = port.match_pairs_all(helpers.images_of(heads, descs), [s[0] for s in sched], [s[1] for s in sched],
+                                     opts["dist"], opts["sym"])
+    else:
+        lists = port.match_pairs(helpers.images_of(heads, descs), [s[0] for s in sched], [s[1] for s in sched],
+                                 opts["dist"], opts["ratio"], opts["sym"])
     assert sum(len(l) for l in lists) == case["nb_match"]
     out = str(tmp_path / "pairs.bin")
     helpers.write_pairs(out, filenames, rigids, heads, sched, lists)
