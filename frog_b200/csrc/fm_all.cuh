@@ -31,30 +31,25 @@ match_all_kernel(const ImageDev* __restrict__ images, const Task* __restrict__ t
   const Task task = tasks[t];
   const ImageDev A = images[task.col_img];
   const ImageDev B = images[task.row_img];
-  const int d = D_T > 0 ? D_T : (int)A.d;
+  constexpr int d = D_T;  // other descriptor lengths: exact_generic_kernel<1|2> (fm_generic.cuh)
   float* s_desc = smem;                      // [kExactCols][d]
   float* s_scale = s_desc + kExactCols * d;  // [kExactCols]
   float* s_lap = s_scale + kExactCols;       // [kExactCols]
-  float* s_row = s_lap + kExactCols;         // D_T == 0 only: [kExactRows][d + 1]
 
   const uint32_t row = (blockIdx.x - task_blk_off[t]) * kExactRows + threadIdx.x;
   const bool active = row < B.n;
   const bool swap = task.flags & kTaskSwap;
 
-  float r[D_T > 0 ? D_T : 1];
+  float r[D_T];
   float sc = 1.f, lp = 0.f;
   if (active) {
     sc = B.scale[row];
     lp = B.lap[row];
-    if (D_T > 0) {
-      const float4* src = reinterpret_cast<const float4*>(B.desc + (size_t)row * D_T);
+    const float4* src = reinterpret_cast<const float4*>(B.desc + (size_t)row * D_T);
 #pragma unroll
-      for (int q = 0; q < D_T / 4; q++) {
-        float4 v = __ldg(src + q);
-        r[4 * q] = v.x; r[4 * q + 1] = v.y; r[4 * q + 2] = v.z; r[4 * q + 3] = v.w;
-      }
-    } else {
-      for (int k = 0; k < d; k++) s_row[threadIdx.x * (d + 1) + k] = B.desc[(size_t)row * d + k];
+    for (int q = 0; q < D_T / 4; q++) {
+      float4 v = __ldg(src + q);
+      r[4 * q] = v.x; r[4 * q + 1] = v.y; r[4 * q + 2] = v.z; r[4 * q + 3] = v.w;
     }
   }
 
@@ -77,24 +72,15 @@ match_all_kernel(const ImageDev* __restrict__ images, const Task* __restrict__ t
       if (lp != s_lap[c]) continue;                    // match.cpp:270
       if (scale_gate_fails(sc, s_scale[c])) continue;  // match.cpp:273-275
       float acc = 0.f;
-      if (D_T > 0) {
-        const float4* col = reinterpret_cast<const float4*>(s_desc + c * D_T);
+      const float4* col = reinterpret_cast<const float4*>(s_desc + c * D_T);
 #pragma unroll
-        for (int q = 0; q < D_T / 4; q++) {
-          float4 v = col[q];
-          float e;
-          e = __fsub_rn(r[4 * q], v.x);     acc = __fadd_rn(acc, __fmul_rn(e, e));
-          e = __fsub_rn(r[4 * q + 1], v.y); acc = __fadd_rn(acc, __fmul_rn(e, e));
-          e = __fsub_rn(r[4 * q + 2], v.z); acc = __fadd_rn(acc, __fmul_rn(e, e));
-          e = __fsub_rn(r[4 * q + 3], v.w); acc = __fadd_rn(acc, __fmul_rn(e, e));
-        }
-      } else {
-        const float* col = s_desc + c * d;
-        const float* rr = s_row + threadIdx.x * (d + 1);
-        for (int k = 0; k < d; k++) {
-          float e = __fsub_rn(rr[k], col[k]);
-          acc = __fadd_rn(acc, __fmul_rn(e, e));
-        }
+      for (int q = 0; q < D_T / 4; q++) {
+        float4 v = col[q];
+        float e;
+        e = __fsub_rn(r[4 * q], v.x);     acc = __fadd_rn(acc, __fmul_rn(e, e));
+        e = __fsub_rn(r[4 * q + 1], v.y); acc = __fadd_rn(acc, __fmul_rn(e, e));
+        e = __fsub_rn(r[4 * q + 2], v.z); acc = __fadd_rn(acc, __fmul_rn(e, e));
+        e = __fsub_rn(r[4 * q + 3], v.w); acc = __fadd_rn(acc, __fmul_rn(e, e));
       }
       if (__fsqrt_rn(acc) < thr) {  // match.cpp:295: emit, and do NOT take part in the top-2 update
         if (kEmit) o[count] = swap ? make_uint2(row, match) : make_uint2(match, row);

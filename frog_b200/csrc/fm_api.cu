@@ -10,6 +10,7 @@
 #include "fm_compact.cuh"
 #include "fm_exact.cuh"
 #include "fm_fast.cuh"
+#include "fm_generic.cuh"
 #include "fm_host.h"
 
 using namespace fm;
@@ -267,7 +268,7 @@ int fm_upload_image(fm_ctx* c, uint32_t img, const float* desc, const float* sca
                     uint32_t d) {
   if (!c) return FM_ERR_INVALID;
   if ((n && (!desc || !scale || !lap)) || d == 0) return fail(c, FM_ERR_INVALID, "fm_upload_image: null input or d == 0");
-  if (d > 320) return fail(c, FM_ERR_UNSUPPORTED, "fm_upload_image: descriptor length above 320 is not supported");
+  if (d > (1u << 20)) return fail(c, FM_ERR_UNSUPPORTED, "fm_upload_image: descriptor length above 2^20 is not supported");
   if (img >= 65536u) return fail(c, FM_ERR_INVALID, "fm_upload_image: image index above 65535 (pairs.bin ids are u16, match.cpp:735)");
   if (c->dim != 0 && c->dim != d) return fail(c, FM_ERR_INVALID, "fm_upload_image: all images of a context must share d");
   FM_CUDA(c, cudaSetDevice(c->device));
@@ -463,10 +464,6 @@ int fm_match(fm_ctx* c, const uint32_t* pair_first, const uint32_t* pair_second,
   FM_CUDA_R(r->d_counts.ensure(std::max<size_t>(n_pairs, 1) * sizeof(uint32_t)));
   FM_CUDA_R(cudaMemsetAsync(r->d_counts.p, 0, std::max<size_t>(n_pairs, 1) * sizeof(uint32_t), c->stream));
   FM_CUDA_R(cudaMemsetAsync(c->d_totals.p, 0, sizeof(DeviceCounters), c->stream));
-  if (c->dim != (uint32_t)kD && !c->exact_attr_set) {
-    FM_CUDA_R(cudaFuncSetAttribute(exact_match_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    c->exact_attr_set = true;
-  }
 
   const ImageDev* d_images = c->d_images.as<ImageDev>();
   uint32_t* d_rowres = c->d_rowres.as<uint32_t>();
@@ -489,20 +486,15 @@ int fm_match(fm_ctx* c, const uint32_t* pair_first, const uint32_t* pair_second,
       unsigned long long* d_task_total = c->d_all_tasks.as<unsigned long long>();
       unsigned long long* d_task_base = d_task_total + n_tasks;
       const bool d48 = c->dim == (uint32_t)kD;
-      const size_t smem = exact_smem_bytes((int)c->dim, !d48);
-      if (!d48 && !c->all_attr_set) {
-        FM_CUDA_R(cudaFuncSetAttribute(match_all_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        FM_CUDA_R(cudaFuncSetAttribute(match_all_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        c->all_attr_set = true;
-      }
+      const size_t smem = exact_smem_bytes(kD);
       {
         Span sp(&c->ev_match, c->stream, kPhExact);
         if (d48)
           match_all_kernel<kD, false><<<b.blocks, kExactRows, smem, c->stream>>>(d_images, d_tasks, d_blk, n_tasks, dist, row_count,
                                                                                  row_final, nullptr, nullptr, nullptr, nullptr);
         else
-          match_all_kernel<0, false><<<b.blocks, kExactRows, smem, c->stream>>>(d_images, d_tasks, d_blk, n_tasks, dist, row_count,
-                                                                                row_final, nullptr, nullptr, nullptr, nullptr);
+          exact_generic_kernel<1><<<b.blocks, kExactRows, 0, c->stream>>>(d_images, d_tasks, d_blk, n_tasks, dist, 1.f, 0u, nullptr, row_count,
+                                                                          row_final, nullptr, nullptr, nullptr, nullptr);
         all_scan_kernel<<<(n_tasks + 63) / 64, 64, 0, c->stream>>>(d_images, d_tasks, n_tasks, row_count, row_final, row_carry, row_off,
                                                                     d_task_total);
       }
@@ -523,8 +515,8 @@ int fm_match(fm_ctx* c, const uint32_t* pair_first, const uint32_t* pair_second,
           match_all_kernel<kD, true><<<b.blocks, kExactRows, smem, c->stream>>>(d_images, d_tasks, d_blk, n_tasks, dist, nullptr, nullptr,
                                                                                 row_carry, row_off, d_task_base, r->d_out.as<uint2>());
         else
-          match_all_kernel<0, true><<<b.blocks, kExactRows, smem, c->stream>>>(d_images, d_tasks, d_blk, n_tasks, dist, nullptr, nullptr,
-                                                                               row_carry, row_off, d_task_base, r->d_out.as<uint2>());
+          exact_generic_kernel<2><<<b.blocks, kExactRows, 0, c->stream>>>(d_images, d_tasks, d_blk, n_tasks, dist, 1.f, 0u, nullptr, nullptr,
+                                                                          nullptr, row_carry, row_off, d_task_base, r->d_out.as<uint2>());
       }
       FM_CUDA_R(cudaStreamSynchronize(c->stream));  // task_base (pageable) must outlive the copy
       c->stats.kernel_launches += 3;
@@ -570,11 +562,11 @@ int fm_match(fm_ctx* c, const uint32_t* pair_first, const uint32_t* pair_second,
       if (b.any_exact) {
         Span sp(&c->ev_match, c->stream, kPhExact);
         if (c->dim == (uint32_t)kD)
-          exact_match_kernel<kD><<<b.blocks, kExactRows, exact_smem_bytes(kD, false), c->stream>>>(
+          exact_match_kernel<kD><<<b.blocks, kExactRows, exact_smem_bytes(kD), c->stream>>>(
               d_images, d_tasks + b.t0, blk, nt, dist, dist2second, kTaskExact, d_rowres);
         else
-          exact_match_kernel<0><<<b.blocks, kExactRows, exact_smem_bytes((int)c->dim, true), c->stream>>>(
-              d_images, d_tasks + b.t0, blk, nt, dist, dist2second, kTaskExact, d_rowres);
+          exact_generic_kernel<0><<<b.blocks, kExactRows, 0, c->stream>>>(d_images, d_tasks + b.t0, blk, nt, dist, dist2second, kTaskExact,
+                                                                          d_rowres, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
         c->stats.kernel_launches++;
         for (uint32_t t = b.t0; t < b.t1; t++)
           if (tasks[t].flags & kTaskExact) c->stats.rows_exact += c->images[tasks[t].row_img].n;

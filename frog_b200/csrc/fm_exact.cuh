@@ -8,7 +8,8 @@
 //   top-2      match.cpp:303-313, strict '<'
 //   accept     match.cpp:320-321, float sqrt/div
 // It serves (a) images the tensor-core path is not certified for, (b) rows whose candidate list
-// overflowed there, (c) FM_FLAG_FORCE_EXACT, and (d) any descriptor length d != 48.
+// overflowed there and (c) FM_FLAG_FORCE_EXACT; descriptor lengths other than 48 go through the
+// K-chunked kernel of fm_generic.cuh.
 #pragma once
 #include "fm_common.cuh"
 
@@ -37,8 +38,7 @@ __device__ __forceinline__ uint32_t find_segment(const uint32_t* __restrict__ of
   return lo;
 }
 
-// D_T > 0: descriptor length known at compile time, row descriptor lives in registers.
-// D_T == 0: runtime d, row descriptor re-read from shared memory (slow, any d).
+// D_T: descriptor length, known at compile time; the row's descriptor lives in registers.
 // require_flags: only tasks whose flags contain these bits are processed (0 = every task).
 template <int D_T>
 __global__ void __launch_bounds__(kExactRows)
@@ -51,29 +51,24 @@ exact_match_kernel(const ImageDev* __restrict__ images, const Task* __restrict__
   if ((task.flags & require_flags) != require_flags) return;  // CTA-uniform
   const ImageDev A = images[task.col_img];
   const ImageDev B = images[task.row_img];
-  const int d = D_T > 0 ? D_T : (int)A.d;
+  constexpr int d = D_T;
   float* s_desc = smem;                          // [kExactCols][d]
   float* s_scale = s_desc + kExactCols * d;      // [kExactCols]
   float* s_lap = s_scale + kExactCols;           // [kExactCols]
-  float* s_row = s_lap + kExactCols;             // D_T == 0 only: [kExactRows][d + 1]
 
   const uint32_t row = (blockIdx.x - task_blk_off[t]) * kExactRows + threadIdx.x;
   const bool active = row < B.n;
 
-  float r[D_T > 0 ? D_T : 1];
+  float r[D_T];
   float sc = 1.f, lp = 0.f;
   if (active) {
     sc = B.scale[row];
     lp = B.lap[row];
-    if (D_T > 0) {
-      const float4* src = reinterpret_cast<const float4*>(B.desc + (size_t)row * D_T);
+    const float4* src = reinterpret_cast<const float4*>(B.desc + (size_t)row * D_T);
 #pragma unroll
-      for (int q = 0; q < D_T / 4; q++) {
-        float4 v = __ldg(src + q);
-        r[4 * q] = v.x; r[4 * q + 1] = v.y; r[4 * q + 2] = v.z; r[4 * q + 3] = v.w;
-      }
-    } else {
-      for (int k = 0; k < d; k++) s_row[threadIdx.x * (d + 1) + k] = B.desc[(size_t)row * d + k];
+    for (int q = 0; q < D_T / 4; q++) {
+      float4 v = __ldg(src + q);
+      r[4 * q] = v.x; r[4 * q + 1] = v.y; r[4 * q + 2] = v.z; r[4 * q + 3] = v.w;
     }
   }
 
@@ -94,24 +89,15 @@ exact_match_kernel(const ImageDev* __restrict__ images, const Task* __restrict__
       if (lp != s_lap[c]) continue;
       if (scale_gate_fails(sc, s_scale[c])) continue;
       float acc = 0.f;
-      if (D_T > 0) {
-        const float4* col = reinterpret_cast<const float4*>(s_desc + c * D_T);
+      const float4* col = reinterpret_cast<const float4*>(s_desc + c * D_T);
 #pragma unroll
-        for (int q = 0; q < D_T / 4; q++) {
-          float4 v = col[q];
-          float e;
-          e = __fsub_rn(r[4 * q], v.x);     acc = __fadd_rn(acc, __fmul_rn(e, e));
-          e = __fsub_rn(r[4 * q + 1], v.y); acc = __fadd_rn(acc, __fmul_rn(e, e));
-          e = __fsub_rn(r[4 * q + 2], v.z); acc = __fadd_rn(acc, __fmul_rn(e, e));
-          e = __fsub_rn(r[4 * q + 3], v.w); acc = __fadd_rn(acc, __fmul_rn(e, e));
-        }
-      } else {
-        const float* col = s_desc + c * d;
-        const float* rr = s_row + threadIdx.x * (d + 1);
-        for (int k = 0; k < d; k++) {
-          float e = __fsub_rn(rr[k], col[k]);
-          acc = __fadd_rn(acc, __fmul_rn(e, e));
-        }
+      for (int q = 0; q < D_T / 4; q++) {
+        float4 v = col[q];
+        float e;
+        e = __fsub_rn(r[4 * q], v.x);     acc = __fadd_rn(acc, __fmul_rn(e, e));
+        e = __fsub_rn(r[4 * q + 1], v.y); acc = __fadd_rn(acc, __fmul_rn(e, e));
+        e = __fsub_rn(r[4 * q + 2], v.z); acc = __fadd_rn(acc, __fmul_rn(e, e));
+        e = __fsub_rn(r[4 * q + 3], v.w); acc = __fadd_rn(acc, __fmul_rn(e, e));
       }
       if (acc < d1) { d2 = d1; d1 = acc; match = c0 + c; }
       else if (acc < d2) { d2 = acc; }
@@ -120,10 +106,6 @@ exact_match_kernel(const ImageDev* __restrict__ images, const Task* __restrict__
   if (active) rowres[task.row_off + row] = accept_rule(d1, d2, thr, ratio) ? match : kNone;
 }
 
-inline size_t exact_smem_bytes(int d, bool generic) {
-  size_t f = (size_t)kExactCols * d + 2 * kExactCols;
-  if (generic) f += (size_t)kExactRows * (d + 1);
-  return f * sizeof(float);
-}
+inline size_t exact_smem_bytes(int d) { return ((size_t)kExactCols * d + 2 * kExactCols) * sizeof(float); }
 
 }  // namespace fm

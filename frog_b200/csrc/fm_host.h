@@ -141,6 +141,6 @@ struct fm_ctx {
   unsigned long long* h_pinned = nullptr;  // 8 x u64 scratch for small D2H reads
   fm::EventPool ev_match, ev_prep;
   fm_stats stats{};
-  bool exact_attr_set = false, score_attr_set = false, all_attr_set = false;
+  bool score_attr_set = false;
   std::string err;
 };

@@ -74,7 +74,8 @@ int fm_synchronize(fm_ctx* ctx);
  * Host memory, pageable or pinned; copies are queued on the context's stream, so PINNED buffers
  * must stay valid until the next fm_synchronize() / fm_match() on this context (pageable buffers
  * may be reused as soon as the call returns).  Re-uploading an index replaces the image.  All images of one
- * context must share d (match.cpp:575 prints one descriptor size for the group).
+ * context must share d (match.cpp:575 prints one descriptor size for the group).  d = 48 (SURF3D) runs on the
+ * tensor-core path; any other d (surf3d -type 1/2: 24 r^3 or 8 r^3 values) on the exact FP32 kernels.
  */
 int fm_upload_image(fm_ctx* ctx, uint32_t img, const float* desc, const float* scale, const float* lap,
                     uint32_t n, uint32_t d);

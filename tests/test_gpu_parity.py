@@ -121,16 +121,24 @@ def test_uncertified_images_route_to_exact(env):
 
 
 def test_other_descriptor_lengths(env):
-    """d != 48 (surf3d descriptor types 1/2, vtkOpenSURF3D/surf3d.cxx:36-39) runs on the generic exact kernel."""
+    """d != 48 (surf3d descriptor types 1/2: 24 r^3 or 8 r^3 values, vtkOpenSURF3D/surf3d.cxx:36-39 -- 1000 and 3000
+    at the default radius 5) runs on the K-chunked exact kernel: lengths below, equal to, not a multiple of and far
+    above the 64-value chunk."""
     m, port = env
     rng = np.random.default_rng(5)
-    for d in (24, 64, 192):
+    for d in (1, 24, 64, 72, 192, 1000, 3000):
         images = []
         for i in range(3):
             x = rng.standard_normal((300 + 7 * i, d)).astype(np.float32)
             x /= np.linalg.norm(x, axis=1, keepdims=True)
             images.append((x, rng.uniform(1, 2, x.shape[0]).astype(np.float32), rng.integers(0, 2, x.shape[0]).astype(np.float32)))
-        run_both(m, port, images, [0, 0, 1], [1, 2, 2], 1.2, 0.95, engines=(False,))
+        run_both(m, port, images, [0, 0, 1], [1, 2, 2], 1.2, 0.95, sym=(d == 72), engines=(False,))
+        want = port.match_pairs_all(images, [0, 1], [1, 2], 1.3, d == 1000)
+        res = m.match([0, 1], [1, 2], 1.3, 1.0, sym=(d == 1000), match_all=True)  # images are still resident
+        assert res.total == sum(len(w) for w in want)
+        for g, w in zip(res.all_pairs(), want):
+            assert np.array_equal(g, w)
+        res.free()
 
 
 def test_api_errors(env):

@@ -92,3 +92,22 @@ def test_fast_decimal_parser_is_strtof(built):
         n_bad = L.fmio_fuzz_floats(seed, 400_000, C.byref(n_fast), bad, 128)
         assert n_bad == 0, f"first mismatching cell: {bad.value!r}"
         assert n_fast.value > 200_000  # the fast path really carries the common formats
+
+
+def test_csv_long_descriptors_through_cli_readers(tmp_path):
+    """surf3d -type 2 writes 8 r^3 = 1000 values per keypoint at the default radius (vtkOpenSURF3D/surf3d.cxx:36-39);
+    the CSV readers take whatever length the rows have (match.cpp:160-168)."""
+    import gzip
+    rng = np.random.default_rng(3)
+    n, d = 17, 1000
+    rec = np.concatenate([rng.uniform(0, 100, (n, 6)), rng.standard_normal((n, d))], axis=1).astype(np.float32)
+    text = "\n".join(",".join("%f" % v for v in row) for row in rec) + "\n"
+    p_csv, p_gz = tmp_path / "long.csv", tmp_path / "long.csv.gz"
+    p_csv.write_text(text)
+    with gzip.open(p_gz, "wt") as f:
+        f.write(text)
+    want = np.array([[np.float32(float("%f" % v)) for v in row] for row in rec], np.float32)
+    for p in (p_csv, p_gz):
+        head, desc = hostio.read_keypoints(str(p))
+        assert head.shape == (n, 6) and desc.shape == (n, d)
+        assert np.array_equal(head, want[:, :6]) and np.array_equal(desc, want[:, 6:])
