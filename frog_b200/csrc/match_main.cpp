@@ -8,6 +8,7 @@
 // readers, same stdout protocol, byte-identical pairs.bin.  The pairing phase (match.cpp:638-652)
 // runs on B200s through the C ABI of libfrogmatch.so; there is no CPU fallback.
 #include <omp.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <array>
@@ -246,23 +247,6 @@ int main(int argc, char* argv[]) {
   }
   if (writePoints) cerr << "match: -p (debug CSV dump) is ignored by the B200 build" << endl;
 
-  // Bring the GPUs up in the background while the keypoint files load (no CPU fallback: a machine
-  // without a CUDA device fails below, before any pairing).
-  int n_dev = 0;
-  const bool have_dev = fm_device_count(&n_dev) == FM_OK && n_dev > 0;
-  const int G_max = have_dev ? std::max(1, gpus > 0 ? std::min(gpus, n_dev) : n_dev) : 0;
-  std::vector<GpuJob> jobs(G_max);
-  std::vector<std::thread> warmers;
-  for (int g = 0; g < G_max; g++) {
-    jobs[g].device = g;
-    warmers.emplace_back(create_context, std::ref(jobs[g]));
-  }
-  auto join_warmers = [&]() { for (auto& t : warmers) if (t.joinable()) t.join(); };
-  struct Joiner {  // early `return`s below must not leave a joinable thread behind
-    std::vector<std::thread>& t;
-    ~Joiner() { for (auto& x : t) if (x.joinable()) x.join(); }
-  } joiner{warmers};
-
   std::vector<std::array<double, 3>> rigids;
   std::vector<string> filenames;
   if (fs::is_directory(full_path)) {  // match.cpp:439-452
@@ -299,24 +283,83 @@ int main(int argc, char* argv[]) {
     return 1;
   }
 
-  // The NCCL communicators (one per GPU that will get image pairs) come up on their own thread, under the file
-  // loading and the matching; it is joined just before the gather.
-#ifdef FM_WITH_NCCL
-  NcclGather gatherer;  // declared before the thread's joiner: destroyed after the thread has been joined
-#endif
-  std::thread nccl_thread;
-  struct NcclJoiner {
-    std::thread& t;
-    ~NcclJoiner() { if (t.joinable()) t.join(); }
-  } nccl_joiner{nccl_thread};
-#ifdef FM_WITH_NCCL
-  {
-    const size_t n_load = std::min<size_t>(filenames.size(), (size_t)std::max(N, 0));
-    const size_t planned_pairs = n_load < 2 ? 0 : (target >= 0 ? n_load - 1 : n_load * (n_load - 1) / 2);
-    const int G_plan = (int)std::min<size_t>((size_t)G_max, std::max<size_t>(planned_pairs, 1));
-    if (G_plan > 1 && strcmp(gatherMode, "nccl") == 0) nccl_thread = std::thread([&gatherer, G_plan]() { gatherer.init(G_plan); });
+  // ---- GPU bring-up, planned before the first CUDA call ---------------------------------------------
+  // CUDA start-up is per VISIBLE device (driver initialisation, then a context each): on an 8-GPU box it costs
+  // seconds, more than matching a 200 x 20k group on one GPU.  So the number of GPUs is chosen first -- -gpus G, or
+  // one GPU per ~4e12 descriptor pairs estimated from the keypoint file sizes -- the process restricts itself to
+  // those devices (a prefix of CUDA_VISIBLE_DEVICES when the caller set it; measured on an 8-GPU box: cuInit 5.2 s
+  // with 8 visible devices, 0.6 s with one), and everything CUDA happens on a background thread while the keypoint
+  // files load.  No CPU fallback: without a device the run fails below.
+  const size_t n_load = std::min<size_t>(filenames.size(), (size_t)std::max(N, 0));
+  const size_t planned_pairs = n_load < 2 ? 0 : (target >= 0 ? n_load - 1 : n_load * (n_load - 1) / 2);
+  int G_want = gpus;
+  if (G_want <= 0) {
+    double pts = 0, pts2 = 0;  // sum n_i, sum n_i^2 -> sum_{i<j} n_i n_j
+    for (size_t i = 0; i < n_load; i++) {
+      std::error_code ec;
+      const double bytes = (double)fs::file_size(filenames[i], ec);
+      if (ec) continue;
+      const string& f = filenames[i];
+      const bool gz = f.size() > 3 && f.compare(f.size() - 3, 3, ".gz") == 0;
+      const bool bin = f.size() > 4 && f.compare(f.size() - 4, 4, ".bin") == 0;
+      const double n_est = bytes / (bin ? 216.0 : gz ? 220.0 : 500.0);  // 54 floats; "%f" text; the same gzipped
+      pts += n_est;
+      pts2 += n_est * n_est;
+    }
+    const double est_pairs = target >= 0 ? pts * pts / std::max<double>(n_load, 1) : (pts * pts - pts2) / 2;
+    G_want = (int)std::min(64.0, std::max(1.0, std::ceil(est_pairs / 4e12)));
   }
+  G_want = (int)std::max<size_t>(1, std::min<size_t>((size_t)G_want, std::max<size_t>(planned_pairs, 1)));
+  if (const char* vis_env = getenv("CUDA_VISIBLE_DEVICES")) {
+    // the caller's list stays authoritative: keep its first G_want entries
+    std::vector<string> ids;
+    std::stringstream ss(vis_env);
+    for (string tok; std::getline(ss, tok, ',');)
+      if (!tok.empty()) ids.push_back(tok);
+    if ((int)ids.size() > G_want) {
+      string vis;
+      for (int g = 0; g < G_want; g++) vis += (g ? "," : "") + ids[g];
+      setenv("CUDA_VISIBLE_DEVICES", vis.c_str(), 1);
+    }
+  } else {
+    int n_phys = 0;
+    for (std::error_code ec; n_phys < 64 && fs::exists("/dev/nvidia" + std::to_string(n_phys), ec);) n_phys++;
+    if (n_phys > G_want) {
+      string vis;
+      for (int g = 0; g < G_want; g++) vis += (g ? "," : "") + std::to_string(g);
+      setenv("CUDA_VISIBLE_DEVICES", vis.c_str(), 1);
+    }
+  }
+  int n_dev = 0, G_max = 0;
+  bool have_dev = false;
+  string dev_error;  // fm_last_error(NULL) is per thread: fetched on the thread that made the failing call
+  std::vector<GpuJob> jobs;
+#ifdef FM_WITH_NCCL
+  NcclGather gatherer;  // declared before the threads' joiners: destroyed after they have been joined
 #endif
+  std::thread nccl_thread;  // NCCL communicators: joined just before the gather (they come up under the matching too)
+  const bool want_nccl = strcmp(gatherMode, "nccl") == 0;
+  std::thread bringup([&]() {
+    have_dev = fm_device_count(&n_dev) == FM_OK && n_dev > 0;
+    if (!have_dev) dev_error = fm_last_error(nullptr);
+    G_max = have_dev ? std::max(1, std::min(G_want, n_dev)) : 0;
+    jobs.resize(G_max);
+    std::vector<std::thread> warmers;
+    for (int g = 0; g < G_max; g++) {
+      jobs[g].device = g;
+      warmers.emplace_back(create_context, std::ref(jobs[g]));
+    }
+#ifdef FM_WITH_NCCL
+    if (G_max > 1 && want_nccl) nccl_thread = std::thread([&gatherer, G_max]() { gatherer.init(G_max); });
+#endif
+    for (auto& t : warmers) t.join();
+  });
+  auto join_warmers = [&]() { if (bringup.joinable()) bringup.join(); };
+  struct Joiner {  // early `return`s below must not leave a joinable thread behind
+    std::thread &a, &b;
+    ~Joiner() { if (a.joinable()) a.join(); if (b.joinable()) b.join(); }
+  } joiner{bringup, nccl_thread};
+  (void)want_nccl;
   cout << "Found " << filenames.size() << " files, loading : " << fmin(N, filenames.size()) << endl;
   start = std::chrono::system_clock::now();
   if (filenames.size() > (size_t)N) filenames.resize(N);
@@ -383,7 +426,7 @@ int main(int argc, char* argv[]) {
   cout << "Pairing... " << endl;
   join_warmers();
   if (!have_dev) {
-    cerr << "match: no CUDA device available (" << fm_last_error(nullptr) << "); this build has no CPU path" << endl;
+    cerr << "match: no CUDA device available (" << dev_error << "); this build has no CPU path" << endl;
     return 1;
   }
   const int G = std::max(1, std::min<int>(G_max, std::max<size_t>(indices.size(), 1)));
@@ -513,9 +556,10 @@ int main(int argc, char* argv[]) {
 #endif
        << "}" << endl;
   }
-  for (auto& j : jobs) {
-    fm_result_free(j.res);
-    fm_destroy(j.ctx);
-  }
-  return 0;
+  // pairs.bin and the stats file are closed.  Tearing down one CUDA context per GPU (and NCCL) costs a one-shot
+  // process up to seconds and frees nothing the operating system does not reclaim anyway: leave at once.
+  cout << std::flush;
+  cerr << std::flush;
+  fflush(nullptr);
+  _exit(0);
 }
