@@ -425,7 +425,7 @@ score_kernel(const ImageDev* __restrict__ images, const Task* __restrict__ tasks
   // ONE row costs its whole warp the slow path.  Visiting the first tiles once without capturing establishes
   // the threshold of a 64 * n_pre column prefix before the first column is captured: a few tiles of extra
   // MMA work (the tensor pipe has slack) for about a third fewer slow-path entries and no list overflow handling.
-  const uint32_t n_pre = kDump ? 0u : min(pre_tiles, n_tiles / 4);
+  const uint32_t n_pre = min(pre_tiles, n_tiles / 4);  // (the single-unit debug launch passes pre_tiles = 0)
   const uint32_t n_sched = n_tiles + n_pre;
 
   RowScan st;
