@@ -2,7 +2,7 @@
 //
 //   match <listfile-or-directory> [-o out] [-d dist] [-d2 ratio] [-n N] [-sp thr] [-np n] [-nt threads]
 //         [-zmin z] [-zmax z] [-sym] [-targ k] [-all x]   (reference keys, same meaning)
-//         [-gpus G] [-exact 1] [-stats file.json] [-gather nccl|host]   (new keys; unknown to the reference)
+//         [-gpus G] [-exact 1] [-stats file.json] [-gather nccl|host] [-plan 1]   (new keys; unknown to the reference)
 //
 // Same argv quirks (every key consumes two tokens except -sym, match.cpp:365-431), same keypoint
 // readers, same stdout protocol, byte-identical pairs.bin.  The pairing phase (match.cpp:638-652)
@@ -207,6 +207,7 @@ int main(int argc, char* argv[]) {
   int target = -1;
   int gpus = -1;
   const char* statsFile = nullptr;
+  bool planOnly = false;  // -plan 1: print the GPU plan (no CUDA call is made) and exit
   // How the lists of GPUs 1.. reach the writer: "host" = every GPU copies its own lists over its own PCIe link,
   // "nccl" = GPU-to-GPU over NVLink to GPU 0, then one device-to-host copy.  Bringing the communicators up
   // (ncclCommInitAll, 1.5-2 s measured) costs a one-shot process more than matching a 50 x 50k group, so "host"
@@ -234,6 +235,7 @@ int main(int argc, char* argv[]) {
       if (has("-exact")) forceExact = atoi(value) != 0;
       if (has("-stats")) statsFile = value;
       if (has("-gather")) gatherMode = value;
+      if (has("-plan")) planOnly = atoi(value) != 0;
     }
     if (has("-all")) matchAll = true;
     if (has("-p")) writePoints = true;
@@ -310,6 +312,10 @@ int main(int argc, char* argv[]) {
     G_want = (int)std::min(64.0, std::max(1.0, std::ceil(est_pairs / 4e12)));
   }
   G_want = (int)std::max<size_t>(1, std::min<size_t>((size_t)G_want, std::max<size_t>(planned_pairs, 1)));
+  if (planOnly) {
+    cout << "Planned GPUs : " << G_want << " (" << planned_pairs << " image pairs)" << endl;
+    return 0;
+  }
   if (const char* vis_env = getenv("CUDA_VISIBLE_DEVICES")) {
     // the caller's list stays authoritative: keep its first G_want entries
     std::vector<string> ids;

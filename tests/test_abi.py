@@ -54,3 +54,34 @@ def test_cli_usage(built):
     assert r.returncode == 1 and r.stdout.startswith("Usage : match pointFiles.txt")  # match.cpp:347-350
     r = subprocess.run([build.BIN, "/nonexistent/list.txt"], capture_output=True, text=True)
     assert r.returncode == 1 and "Bad argument" in r.stderr  # match.cpp:494-498
+
+
+def test_cli_gpu_plan(built, golden_dir, tmp_path):
+    """The executable chooses its GPU count BEFORE the first CUDA call (cuInit costs seconds per visible device on
+    a multi-GPU box): -gpus G, else one GPU per ~4e12 descriptor pairs estimated from the keypoint file sizes,
+    never more than there are image pairs.  `-plan 1` prints the plan without touching CUDA."""
+    lst = os.path.join(golden_dir, "list_bin.txt")  # 4 images x 221 records: 6 image pairs
+
+    def plan(*extra):
+        r = subprocess.run([build.BIN, lst, "-plan", "1"] + list(extra), capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        m = re.search(r"Planned GPUs : (\d+) \((\d+) image pairs\)", r.stdout)
+        return int(m.group(1)), int(m.group(2))
+
+    assert plan() == (1, 6)                      # tiny group: one GPU
+    assert plan("-gpus", "4") == (4, 6)
+    assert plan("-gpus", "16") == (6, 6)         # never more GPUs than image pairs
+    assert plan("-gpus", "8", "-targ", "0") == (3, 3)
+    assert plan("-gpus", "8", "-n", "2") == (1, 1)
+    # file-size estimate: 40 sparse 54 MB .bin files (250k records each) = 780 pairs x 6.25e10 = 4.9e13 pairs -> 13 GPUs
+    big = tmp_path / "big"
+    big.mkdir()
+    names = []
+    for i in range(40):
+        p = big / f"p{i}.bin"
+        with open(p, "wb") as f:
+            f.truncate(250000 * 216)
+        names.append(str(p))
+    (big / "list.txt").write_text("\n".join(names) + "\n")
+    r = subprocess.run([build.BIN, str(big / "list.txt"), "-plan", "1"], capture_output=True, text=True)
+    assert "Planned GPUs : 13 (780 image pairs)" in r.stdout
