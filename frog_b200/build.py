@@ -52,7 +52,7 @@ def build_cli(force: bool = False) -> str:
         return BIN
     os.makedirs(os.path.dirname(BIN), exist_ok=True)
     cmd = ["g++", "-O2", "-std=c++17", "-fopenmp", "-I", os.path.join(ROOT, "include"),
-           os.path.join(CSRC, "match_main.cpp"), os.path.join(CSRC, "keypoint_io.cpp"),
+           os.path.join(CSRC, "match_main.cpp"), os.path.join(CSRC, "keypoint_io.cpp"), os.path.join(CSRC, "fast_inflate.cpp"),
            "-o", BIN, "-L", os.path.dirname(LIB), "-lfrogmatch", "-lz",
            "-Wl,-rpath,$ORIGIN/../frog_b200"]
     # multi-GPU list gather over NCCL (system libnccl; only the executable links it, never libfrogmatch.so, so a
@@ -70,7 +70,8 @@ def build_fmio(force: bool = False) -> str:
     if not force and _newer(FMIO, srcs):
         return FMIO
     cmd = ["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-I", os.path.join(ROOT, "include"),
-           os.path.join(CSRC, "fmio_capi.cpp"), os.path.join(CSRC, "keypoint_io.cpp"), "-o", FMIO, "-lz"]
+           os.path.join(CSRC, "fmio_capi.cpp"), os.path.join(CSRC, "keypoint_io.cpp"), os.path.join(CSRC, "fast_inflate.cpp"),
+           "-o", FMIO, "-lz"]
     subprocess.run(cmd, check=True, cwd=ROOT)
     return FMIO
 

@@ -5,9 +5,22 @@
 #include <cstdlib>
 #include <cstring>
 
+#include "fast_inflate.h"
 #include "keypoint_io.h"
 
 extern "C" {
+
+// Test hook for fast_inflate.cpp: 1 and *produced bytes in out (cap permitting) when the decoder accepted the
+// member, 0 when it declined (the readers then use zlib), -2 when cap is too small.
+int fmio_fast_inflate(const unsigned char* src, size_t n, char* out, size_t cap, size_t* produced) {
+  std::vector<char> buf;
+  size_t got = 0;
+  if (!fmio::fast_inflate_gzip(src, n, buf, &got)) return 0;
+  *produced = got;
+  if (got > cap) return -2;
+  memcpy(out, buf.data(), got);
+  return 1;
+}
 
 // Reads a keypoint file by extension (match.cpp:514,528-536).  Returns the number of records,
 // -1 on failure (message in err), -2 if the caller's buffers are too small.

@@ -3,6 +3,8 @@
 
 #include <zlib.h>
 
+#include "fast_inflate.h"
+
 #include <algorithm>
 #include <cerrno>
 #include <cstdio>
@@ -168,6 +170,15 @@ bool read_csv_gz(const std::string& path, KeypointSet& out, std::string& err) {
   std::vector<char> raw;
   if (!slurp(path, raw, err)) return false;
   std::vector<char> text;
+  {
+    // one well-formed gzip member (what surf3d writes): the table-driven decoder; anything else: zlib below
+    size_t got = 0;
+    if (raw.size() > 1 && fast_inflate_gzip(reinterpret_cast<const uint8_t*>(raw.data()), raw.size() - 1, text, &got)) {
+      text.resize(got + 1);
+      text[got] = 0;
+      return parse_csv_text(text.data(), got, out, err);
+    }
+  }
   z_stream zs{};
   if (inflateInit2(&zs, 15 + 32) != Z_OK) { err = "zlib init failed"; return false; }
   zs.next_in = reinterpret_cast<Bytef*>(raw.data());

@@ -111,3 +111,88 @@ def test_csv_long_descriptors_through_cli_readers(tmp_path):
         head, desc = hostio.read_keypoints(str(p))
         assert head.shape == (n, 6) and desc.shape == (n, d)
         assert np.array_equal(head, want[:, :6]) and np.array_equal(desc, want[:, 6:])
+
+
+def _fast_inflate(raw: bytes, cap: int):
+    import ctypes as C
+    from frog_b200 import build
+    L = C.CDLL(build.FMIO)
+    L.fmio_fast_inflate.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]
+    out = C.create_string_buffer(cap + 1)
+    got = C.c_size_t(0)
+    rc = L.fmio_fast_inflate(raw, len(raw), out, cap, C.byref(got))
+    return rc, out.raw[:got.value]
+
+
+def test_fast_inflate_equals_zlib(built):
+    """fast_inflate.cpp (the decoder behind the .csv.gz reader) against zlib: every block type (stored, fixed, dynamic),
+    every compression level and strategy, code lengths up to 15 bits, sync/full flush points, a gzip header with a
+    file name, sizes around the 258-byte match and 64 KiB stored-block limits."""
+    import gzip
+    import io
+    import zlib
+    rng = np.random.default_rng(2)
+    probs = np.array([2.0 ** -i for i in range(1, 40)])
+    probs /= probs.sum()
+    fib = [1, 1]
+    while len(fib) < 30:
+        fib.append(fib[-1] + fib[-2])
+    corpus = [b"", b"a", b"hello, hello, hello, hello\n" * 3, bytes(range(256)) * 5,
+              rng.integers(0, 256, 100000, dtype=np.uint8).tobytes(), rng.integers(0, 4, 300000, dtype=np.uint8).tobytes(),
+              b"\0" * 1000000, ("%f,%f,%d\n" % (1.5, -2.25, 7)).encode() * 50000,
+              ",".join("%f" % v for v in rng.standard_normal(100000)).encode(),
+              bytes(rng.choice(39, 400000, p=probs).astype(np.uint8) + 40),
+              b"".join(bytes([65 + i]) * f for i, f in enumerate(fib))]
+    corpus += [bytes(rng.integers(97, 101, n, dtype=np.uint8)) for n in (1, 2, 3, 7, 8, 9, 257, 258, 259, 65535, 65536, 65537)]
+    n_ok = 0
+    for data in corpus:
+        for level in (0, 1, 6, 9):
+            for strategy in (zlib.Z_DEFAULT_STRATEGY, zlib.Z_FIXED, zlib.Z_HUFFMAN_ONLY, zlib.Z_RLE):
+                co = zlib.compressobj(level, zlib.DEFLATED, 31, 9, strategy)
+                raw = co.compress(data) + co.flush()
+                rc, got = _fast_inflate(raw, len(data) + 16)
+                assert rc == 1 and got == data, (len(data), level, strategy)
+                n_ok += 1
+        bio = io.BytesIO()
+        with gzip.GzipFile(filename="points.csv", mode="wb", fileobj=bio, compresslevel=6) as f:
+            f.write(data)
+        rc, got = _fast_inflate(bio.getvalue(), len(data) + 16)
+        assert rc == 1 and got == data
+        co = zlib.compressobj(6, zlib.DEFLATED, 31)
+        step = max(1, len(data) // 7)
+        raw = b"".join(co.compress(data[i:i + step]) + co.flush(zlib.Z_SYNC_FLUSH if (i // step) % 2 else zlib.Z_FULL_FLUSH)
+                       for i in range(0, len(data), step)) + co.flush()
+        rc, got = _fast_inflate(raw, len(data) + 16)
+        assert rc == 1 and got == data
+    assert n_ok == len(corpus) * 16
+
+
+def test_fast_inflate_declines_what_it_cannot_vouch_for(built, tmp_path):
+    """Truncated, corrupted, multi-member or trailing-garbage input: the fast decoder says no (or, for a flipped bit
+    zlib does not mind either, yields zlib's bytes) and the reader falls back to zlib -- same keypoints as before."""
+    import random
+    import zlib
+    co = zlib.compressobj(6, zlib.DEFLATED, 31)
+    text = b"".join(b"%d.5,2,3,1.5,0,9,0.25,0.5\n" % i for i in range(3000))
+    good = co.compress(text) + co.flush()
+    bad = [good[:-1], good[:len(good) // 2], good + good, good + b"x", good[:-8] + b"\0\0\0\0" + good[-4:],
+           good[:-4] + b"\1\0\0\0", b"\x1f\x8b\x08", b"", b"not gzip at all" * 10]
+    r = random.Random(1)
+    for _ in range(60):
+        b = bytearray(good)
+        b[r.randrange(10, len(good) - 8)] ^= 1 << r.randrange(8)
+        bad.append(bytes(b))
+    declined = 0
+    for b in bad:
+        rc, got = _fast_inflate(b, 400000)
+        if rc == 1:
+            assert zlib.decompress(b, 47) == got
+        else:
+            declined += 1
+    assert declined >= len(bad) - 3
+    # two members: zlib (and this reader) stop after the first; trailing garbage: the first member is still read
+    for name, payload in (("two.csv.gz", good + good), ("junk.csv.gz", good + b"garbage")):
+        p = tmp_path / name
+        p.write_bytes(payload)
+        head, desc = hostio.read_keypoints(str(p))
+        assert head.shape == (3000, 6) and desc.shape == (3000, 2) and head[7, 0] == 7.5
