@@ -103,15 +103,16 @@ rescore_kernel(const ImageDev* __restrict__ images, const Task* __restrict__ tas
       float4 v = __ldg(src + q);
       r[4 * q] = v.x; r[4 * q + 1] = v.y; r[4 * q + 2] = v.z; r[4 * q + 3] = v.w;
     }
-    const float sc = B.scale[row], lp = B.lap[row];
     float d1 = FLT_MAX, d2 = FLT_MAX;
     uint32_t best = 0;
     for (uint32_t e = 0; e < L; e++) {
       const Cand cd = c[e];
       if (!(cd.t > -INFINITY) || !(cd.t >= band)) continue;
+      // Both gates (match.cpp:270, :273-275) hold for every captured column: the scoring kernel only captures inside
+      // the row's interval [lo, hi), which bands_kernel built with the reference's own predicates (and which
+      // tests/test_gpu_stages.py compares with the gate matrix).  Not re-reading lap / scale of the row and of each
+      // column saves a fifth of this kernel's L2 sector traffic.
       const uint32_t j = A.perm[cd.col & ~kCandTruncated];
-      if (lp != A.lap[j]) continue;                    // match.cpp:270
-      if (scale_gate_fails(sc, A.scale[j])) continue;  // match.cpp:273-275
       const float dist = exact_norm48(r, A.desc + (size_t)j * kD);
       n_eval++;
       top2_merge_one(dist, j, d1, d2, best);
