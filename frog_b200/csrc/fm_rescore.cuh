@@ -53,7 +53,7 @@ __device__ __forceinline__ void top2_merge_sets(float od1, float od2, uint32_t o
 }
 
 // One thread per sorted row of the task.
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 6)
 rescore_kernel(const ImageDev* __restrict__ images, const Task* __restrict__ tasks,
                const uint32_t* __restrict__ task_blk_off, uint32_t n_tasks, uint32_t segs,
                const Cand* __restrict__ cands, float thr, float ratio, uint32_t* __restrict__ rowres,
