@@ -85,3 +85,23 @@ def test_cli_gpu_plan(built, golden_dir, tmp_path):
     (big / "list.txt").write_text("\n".join(names) + "\n")
     r = subprocess.run([build.BIN, str(big / "list.txt"), "-plan", "1"], capture_output=True, text=True)
     assert "Planned GPUs : 13 (780 image pairs)" in r.stdout
+
+
+def test_bench_reference_arm_contract(built, tmp_path):
+    """`bench.py --impl reference` (the reference's own CPU matcher on a bounded sample) prints one JSON line with the
+    keys the driver reads; it needs no GPU."""
+    import json
+    import sys
+    from oracle import oracle as O
+    if not os.path.exists(O.REF_BIN):
+        pytest.skip("oracle/_ref/match_ref not built here")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    j = json.loads(lines[0])
+    assert j["impl"] == "reference" and j["unit"] == "descriptor pairs/s" and j["higher_is_better"] is True
+    assert j["value"] > 1e6 and j["cpu_baseline"]["kind"] == "reference" and j["cpu_baseline"]["cores"] >= 1
+    assert j["e2e"] == {"value": j["value"], "unit": j["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert j["config"]["workload"].startswith("c2:")
