@@ -42,24 +42,21 @@ inline bool fast_strtof(const char* c, const char* ce, float& v, const char*& en
   const char* p = c;
   bool neg = false;
   if (p < ce && (*p == '-' || *p == '+')) { neg = *p == '-'; p++; }
+  // At most 19 digits in all (leading zeros included): m cannot overflow 64 bits, so the digit loops carry no
+  // bookkeeping; longer cells are left to strtof.
   uint64_t m = 0;
-  int digits = 0, sig = 0, frac = 0;
-  const char* d0 = p;
-  while (p < ce && *p >= '0' && *p <= '9') {
-    if (sig || *p != '0') { if (++sig > 19) return false; }
-    m = m * 10 + (uint64_t)(*p - '0');
-    digits++; p++;
-  }
+  const char* const d0 = p;
+  while (p < ce && (unsigned)(*p - '0') <= 9u) { m = m * 10 + (uint64_t)(*p - '0'); p++; }
+  int digits = (int)(p - d0), frac = 0;
   if (p < ce && *p == '.') {
     p++;
-    while (p < ce && *p >= '0' && *p <= '9') {
-      if (sig || *p != '0') { if (++sig > 19) return false; }
-      m = m * 10 + (uint64_t)(*p - '0');
-      digits++; frac++; p++;
-    }
+    const char* const f0 = p;
+    while (p < ce && (unsigned)(*p - '0') <= 9u) { m = m * 10 + (uint64_t)(*p - '0'); p++; }
+    frac = (int)(p - f0);
+    digits += frac;
   }
   if (digits == 0) return false;  // "inf", "nan", ".", junk: strtof decides
-  (void)d0;
+  if (digits > 19) return false;
   int e10 = -frac;
   if (p < ce && (*p == 'e' || *p == 'E')) {
     const char* q = p + 1;
@@ -131,10 +128,23 @@ bool parse_csv_text(const char* text, size_t len, KeypointSet& out, std::string&
     // std::getline(lineStream, cell, ',') loop of match.cpp:150: an exhausted stream yields no
     // further (empty) cell, a cell starting with CR ends the row.
     while (c < end) {
-      const char* comma = static_cast<const char*>(memchr(c, ',', (size_t)(end - c)));
-      const char* ce = comma ? comma : end;
       if (*c == 13) break;
       float v;
+      {
+        // Common case, no search for the cell's end: the number runs right up to the next ',' (or the end of the
+        // line).  Then the cell-limited conversion below would see exactly the same characters.
+        const char* q = c;
+        while (q < end && (*q == ' ' || (*q >= '\t' && *q <= '\r'))) q++;
+        const char* fe = nullptr;
+        if (q < end && fast_strtof(q, end, v, fe) && (fe == end || *fe == ',')) {
+          row.push_back(v);
+          if (fe == end) break;
+          c = fe + 1;
+          continue;
+        }
+      }
+      const char* comma = static_cast<const char*>(memchr(c, ',', (size_t)(end - c)));
+      const char* ce = comma ? comma : end;
       if (!cell_to_float(c, ce, v)) {
         err = "stof failed at line " + std::to_string(line_no) + " cell " + std::to_string(row.size());
         return false;
