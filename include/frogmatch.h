@@ -45,7 +45,9 @@ typedef enum fm_status {
                                  * `dist` emits a pair naming the running nearest column that was NOT under it; dist2second is
                                  * ignored; lists can hold up to N_first * N_second pairs.  Exact FP32 kernels only. */
 #define FM_FLAG_ASYNC 8u        /* return as soon as the work is queued on the context's stream; fm_result_wait()
-                                 * completes the result.  Several results may be in flight on one context. */
+                                 * completes the result.  Several results may be in flight on one context.  (Images
+                                 * uploaded since the previous fm_match are prepared first, and the call waits for
+                                 * that; FM_FLAG_MATCH_ALL sizes its lists on the host and is synchronous.) */
 
 /* ---- context --------------------------------------------------------------------------------- */
 
