@@ -11,6 +11,8 @@ the first column on -- the floor for any threshold-seeding scheme at this vote g
 with votes over 16 or 8 rows instead of 32 (what a finer vote granularity would buy).
 Scores are computed in float32 from the float32 descriptors (the FP16 rounding moves them by < eps and does not change
 the statistics).  Prints one JSON object.
+
+    python scripts/sim_capture.py [keypoints_per_image [look-ahead depths, comma separated]]
 """
 import json
 import os
@@ -21,7 +23,9 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from frog_b200 import synth  # noqa: E402
 
-N, EPS2, UNIT, TILE, STEP = 20000, 1.3e-3, 256, 64, 32
+N = int(sys.argv[1]) if len(sys.argv) > 1 else 20000  # keypoints per image (20000 = C2 / C4, 50000 = C3)
+PRES = [int(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else [8]  # look-ahead depths (tiles) to replay
+EPS2, UNIT, TILE, STEP = 1.3e-3, 256, 64, 32
 a, b = synth.make("iid", N, 0), synth.make("iid", N, 1)  # columns = image `first`, rows = image `second`
 
 
@@ -35,7 +39,8 @@ sa, sb, la, lb = a.scale[pa], b.scale[pb], a.lap[pa], b.lap[pb]
 half_norm = 0.5 * (A.astype(np.float64) ** 2).sum(1).astype(np.float32)
 rng = np.random.default_rng(0)
 units = rng.choice(N // UNIT, 12, replace=False)
-tot = {k: dict(entries=0, steps=0, captured=0, rows=0) for k in ("no_lookahead", "lookahead8", "oracle32", "oracle16", "oracle8")}
+KEYS = ["no_lookahead"] + [f"lookahead{p}" for p in PRES] + ["oracle32", "oracle16", "oracle8"]
+tot = {k: dict(entries=0, steps=0, captured=0, rows=0) for k in KEYS}
 
 for u in units:
     r0 = u * UNIT
@@ -76,7 +81,7 @@ for u in units:
                 above = ts[:, s] > thr[:, None]
                 captured += above.sum(1)
                 entries += above.any(1).reshape(-1, 32).any(1)
-        return entries.sum(), captured.sum(), (n_steps + 0) * (UNIT // 32)
+        return entries.sum(), captured.sum(), n_steps * (UNIT // 32)
 
     def oracle(group):
         above = ts > final_thr[:, None, None]
@@ -84,7 +89,9 @@ for u in units:
         ent = any_row.reshape(UNIT // group, group, n_steps).any(1).sum()
         return ent, above.sum(), n_steps * (UNIT // group)
 
-    for key, (e, c, s) in (("no_lookahead", replay(0)), ("lookahead8", replay(8)), ("oracle32", oracle(32)), ("oracle16", oracle(16)), ("oracle8", oracle(8))):
+    results = [("no_lookahead", replay(0))] + [(f"lookahead{p}", replay(p)) for p in PRES]
+    results += [("oracle32", oracle(32)), ("oracle16", oracle(16)), ("oracle8", oracle(8))]
+    for key, (e, c, s) in results:
         tot[key]["entries"] += int(e)
         tot[key]["captured"] += int(c)
         tot[key]["steps"] += int(s)
