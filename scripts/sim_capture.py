@@ -40,7 +40,7 @@ half_norm = 0.5 * (A.astype(np.float64) ** 2).sum(1).astype(np.float32)
 rng = np.random.default_rng(0)
 units = rng.choice(N // UNIT, 12, replace=False)
 KEYS = ["no_lookahead"] + [f"lookahead{p}" for p in PRES] + ["oracle32", "oracle16", "oracle8"]
-tot = {k: dict(entries=0, steps=0, captured=0, rows=0) for k in KEYS}
+tot = {k: dict(entries=0, steps=0, captured=0, rows=0, hit_rows=0) for k in KEYS}
 
 for u in units:
     r0 = u * UNIT
@@ -68,6 +68,7 @@ for u in units:
         g2 = np.full(UNIT, -np.inf, np.float32)
         entries = np.zeros(UNIT // 32, np.int64)
         captured = np.zeros(UNIT, np.int64)
+        hit_rows = 0
         visits = [(s, True, False) for s in range(n_pre)] + [(s, s >= n_pre, True) for s in range(n_steps)]
         for s, upd, cap in visits:
             if upd:
@@ -81,22 +82,26 @@ for u in units:
                 above = ts[:, s] > thr[:, None]
                 captured += above.sum(1)
                 entries += above.any(1).reshape(-1, 32).any(1)
-        return entries.sum(), captured.sum(), n_steps * (UNIT // 32)
+                hit_rows += int(above.any(1).sum())
+        return entries.sum(), captured.sum(), n_steps * (UNIT // 32), hit_rows
 
     def oracle(group):
         above = ts > final_thr[:, None, None]
         any_row = above.any(2)  # [row][step]
         ent = any_row.reshape(UNIT // group, group, n_steps).any(1).sum()
-        return ent, above.sum(), n_steps * (UNIT // group)
+        return ent, above.sum(), n_steps * (UNIT // group), int(any_row.sum())
 
     results = [("no_lookahead", replay(0))] + [(f"lookahead{p}", replay(p)) for p in PRES]
     results += [("oracle32", oracle(32)), ("oracle16", oracle(16)), ("oracle8", oracle(8))]
-    for key, (e, c, s) in results:
+    for key, (e, c, s, h) in results:
+        tot[key]["hit_rows"] += int(h)
         tot[key]["entries"] += int(e)
         tot[key]["captured"] += int(c)
         tot[key]["steps"] += int(s)
         tot[key]["rows"] += UNIT
 
-out = {k: {"entry_rate": round(v["entries"] / v["steps"], 3), "captured_per_row": round(v["captured"] / v["rows"], 2), "vote_steps": v["steps"]}
+out = {k: {"entry_rate": round(v["entries"] / v["steps"], 3), "captured_per_row": round(v["captured"] / v["rows"], 2),
+           "hitting_rows_per_entry": round(v["hit_rows"] / max(v["entries"], 1), 2),
+           "captured_columns_per_entry": round(v["captured"] / max(v["entries"], 1), 2), "vote_steps": v["steps"]}
        for k, v in tot.items()}
 print(json.dumps(out, indent=1))
