@@ -1,19 +1,26 @@
 #!/usr/bin/env python
-"""bench.py -- descriptor pairs/sec of the keypoint-matching hot path (BASELINE.json metric).
+"""bench.py -- descriptor pairs/sec and match wall-time of the keypoint-matching hot path (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c1|c3]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c4|c3|c2|c1|dense]
 
-A step = one pass of the hot path (match.cpp:638-652: every image pair of a group through
-ComputeMatches) over one synthetic keypoint group.  Workload at N = 1 is BASELINE.json
-configs[1]: 10 images x 20 000 keypoints, random SURF3D-format descriptors (`iid` set,
-SURVEY.md 8d), -d 1 -d2 1.  For N > 1 the scaling is WEAK: every rank matches its own
-10 x 20k group (image pairs are independent units, sharded by group, no data-path collective);
-only the compacted match lists are gathered to rank 0 over NCCL.
+A step = one pass of the hot path (match.cpp:638-652: every image pair of a group through ComputeMatches)
+over ONE synthetic keypoint group.  Default workload: BASELINE.json configs[3], the configuration the
+north star is quoted on -- 200 images x 20 000 keypoints, random SURF3D-format descriptors (`iid` set,
+SURVEY.md 8d), -d 1 -d2 0.8, all 19 900 image pairs = 7.96e12 descriptor pairs per step.
 
-One JSON line on rank 0:  value = descriptor pairs/s with keypoints resident in HBM;
-e2e = the same through the C ABI from pinned HOST buffers (H2D upload + prep + match + D2H);
-roofline = tensor-core FLOP rate of the scoring kernel (96 FLOP per descriptor pair);
-cpu_baseline = the verbatim reference match.cpp (oracle/_ref/match_ref) on this box's cores.
+N > 1 is STRONG scaling of that one group: every rank holds all images (replicated, uploaded over its own
+PCIe link), the image pairs are sharded over the ranks longest-processing-time-first (frog_b200.dist.shard_pairs,
+the loop match.cpp:638-652 runs under OpenMP), no data-path collective; only the compacted match lists travel,
+exact-size, to rank 0 over NCCL (NVLink).
+
+One JSON line on rank 0:
+  value     descriptor pairs/s, keypoints resident in HBM when the timed region starts (lists end on rank 0's GPU)
+  e2e       the same through the C ABI from pinned HOST buffers: per step H2D upload of every image on every rank +
+            preparation + matching + gather + D2H of all lists to rank 0's host memory
+  roofline  tensor-core FLOP rate of the scoring kernel (96 FLOP per descriptor pair)
+  wall      `bin/match` (the drop-in executable) process start -> exit on the same group at N GPUs, .bin and .csv.gz
+  cpu_baseline  the verbatim reference match.cpp (oracle/_ref/match_ref) on this box's cores (N = 1 only)
+`--impl reference` times that reference binary alone (rank 0), on images of the workload's real size.
 """
 from __future__ import annotations
 
@@ -40,18 +47,24 @@ WORKLOADS = {
     "c2": (10, 20000, "iid", 1.0, 1.0),
     "c3": (50, 50000, "iid", 1.0, 1.0),
     "c4": (200, 20000, "iid", 1.0, 0.8),
+    # every keypoint in one laplacian class and at one scale: no column is gated out, the scoring kernel
+    # executes every algorithmic pair (scored_fraction 1.0)
+    "dense": (10, 20000, "dense", 1.0, 1.0),
 }
 FLOP_PER_PAIR = 96.0  # 2 * D, D = 48
+METRIC = "descriptor pairs/sec (keypoint matching, match.cpp ComputeMatches)"
 
 
 def measured_traffic(workload):
     """dram__bytes_read.sum + dram__bytes_write.sum of one scoring-kernel launch, from the committed ncu capture
     of this workload (profiles/); None for workloads that were not captured."""
-    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
-    if not os.path.exists(p):
-        return None
-    j = json.load(open(p))
-    return float(j["dram_bytes_read"] + j["dram_bytes_write"]) if j.get("workload") == workload else None
+    for name in ("r2_traffic.json", "r1_traffic.json"):
+        p = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(p):
+            j = json.load(open(p))
+            if j.get("workload") == workload:
+                return float(j["dram_bytes_read"] + j["dram_bytes_write"])
+    return None
 
 
 def peaks():
@@ -62,22 +75,26 @@ def peaks():
     return 1590.0, 6650.0, "fallback"
 
 
+def workload_name(w, gpus):
+    n_img, n_pts, kind, dist, ratio = WORKLOADS[w]
+    s = (f"{w}: {n_img} images x {n_pts} keypoints, {kind} SURF3D descriptors (D=48), -d {dist:g} -d2 {ratio:g}, "
+         f"all {n_img * (n_img - 1) // 2} image pairs of ONE group")
+    if gpus > 1:
+        s += f", sharded over {gpus} GPUs (images replicated, match lists gathered to rank 0 over NCCL)"
+    return s
+
+
 # --------------------------------------------------------------------------------------------------
-# reference arm / cpu baseline: the unmodified reference binary on a bounded sample
-
-
-def cpu_sample_group(tmpdir, kind, n_images, n_points):
-    from frog_b200 import synth
-    return synth.write_group(tmpdir, kind, n_images, n_points, fmt="bin")
+# reference arm / cpu baseline: the unmodified reference binary on a bounded sample of the workload
 
 
 def run_reference(list_path, dist, ratio, threads):
     from frog_b200 import pairsbin
     from oracle import oracle
     out = os.path.join(os.path.dirname(list_path), "ref_pairs.bin")
-    t0 = time.time()
+    t0 = time.perf_counter()
     res = oracle.run_ref_binary([list_path, "-o", out, "-d", dist, "-d2", ratio], threads=threads)
-    wall = time.time() - t0
+    wall = time.perf_counter() - t0
     # the reference prints " : <seconds>s" after each phase; the third one is "Pairing" (match.cpp:655)
     secs = [float(x) for x in re.findall(r" : ([0-9.eE+-]+)s$", res.stdout, flags=re.M)]
     pairing = secs[2] if len(secs) >= 3 else wall
@@ -88,68 +105,111 @@ def run_reference(list_path, dist, ratio, threads):
     return pairs, pairing, wall
 
 
-def sample_size(cores):
-    """Bounded CPU sample: ~3 s of wall-clock per run at ~6.4e7 descriptor pairs/s/core,
-    with at least as many image pairs as cores (the reference parallelises over image pairs only)."""
-    n_img = int(np.ceil(np.sqrt(15.0 * cores))) + 1
-    return max(8, min(64, n_img)), 5000
+def sample_images(cores, n_points, budget_s=14.0):
+    """How many REAL-SIZE images of the workload the CPU sample holds.  The reference parallelises over image pairs
+    only (match.cpp:638), one image pair of 20k x 20k keypoints is ~4-6 s on a core, so the sample is the image
+    count whose n(n-1)/2 image pairs keep the cores busiest (fewest idle cores in the last OpenMP wave) within about
+    `budget_s` seconds per run."""
+    per_pair_s = float(n_points) ** 2 / 9.0e7
+    best, best_eff = 3, -1.0
+    for n in range(3, 65):
+        p = n * (n - 1) // 2
+        waves = -(-p // cores)
+        if n > 3 and waves * per_pair_s > budget_s:
+            break
+        eff = p / float(waves * cores)
+        if eff > best_eff + 1e-9:
+            best, best_eff = n, eff
+    return best
 
 
-def cpu_baseline(workload):
-    _, _, kind, dist, ratio = WORKLOADS[workload]
+def reference_sample(workload, tmp):
+    from frog_b200 import synth
+    n_img, n_pts, kind, dist, ratio = WORKLOADS[workload]
     cores = os.cpu_count() or 1
-    sample_images, sample_points = sample_size(cores)
-    tmp = tempfile.mkdtemp(prefix="fm_cpu_")
+    s_img = min(n_img, sample_images(cores, n_pts))
+    lst = synth.write_group(tmp, kind, s_img, n_pts, fmt="bin")
+    text = (f"{s_img} of the workload's {n_img} images, {n_pts} keypoints each ({kind}), "
+            f"{s_img * (s_img - 1) // 2} image pairs, -d {dist:g} -d2 {ratio:g}, -nt {cores}")
+    return lst, dist, ratio, cores, text
+
+
+def parity_on_sample(list_path, ref_pairs_path, dist, ratio, device):
+    """Checker leg: the product (C ABI, cuda:`device`) on the very keypoint files the reference binary just matched,
+    lists compared block by block with the reference's pairs.bin (oracle/compare.py classifies differences)."""
+    from frog_b200 import capi, hostio, pairsbin
+    from oracle import compare
+    files = [l.split(",")[0] for l in open(list_path).read().split("\n") if l.strip()]
+    images = []
+    for f in files:
+        head, desc = hostio.read_keypoints(f)  # phantom record of .bin files included, as the reference loads them
+        images.append((desc, np.ascontiguousarray(head[:, 3]), np.ascontiguousarray(head[:, 4])))
+    ref = pairsbin.parse(ref_pairs_path).block_map()
+    keys = sorted(ref)
+    m = capi.Matcher(device)
     try:
-        lst = cpu_sample_group(tmp, kind, sample_images, sample_points)
-        pairs, pairing, _ = run_reference(lst, dist, ratio, cores)
+        for i, (d, sc, lp) in enumerate(images):
+            m.upload(i, d, sc, lp)
+        res = m.match([k[0] for k in keys], [k[1] for k in keys], dist, ratio)
+        ours = dict(zip(keys, res.all_pairs()))
+        res.free()
+    finally:
+        m.close()
+    rep = compare.compare_blocks(ours, ref, images, dist, ratio)
+    rep["what"] = "product vs reference pairs.bin on the cpu_baseline sample, every image pair"
+    return rep
+
+
+def cpu_baseline(workload, parity_device=None):
+    tmp = tempfile.mkdtemp(prefix="fm_cpu_")
+    parity = None
+    try:
+        lst, dist, ratio, cores, text = reference_sample(workload, tmp)
+        pairs, pairing, wall = run_reference(lst, dist, ratio, cores)
+        if parity_device is not None:
+            try:
+                parity = parity_on_sample(lst, os.path.join(tmp, "ref_pairs.bin"), dist, ratio, parity_device)
+            except Exception as e:
+                parity = {"error": str(e)[:300]}
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
-    return {"value": pairs / pairing, "unit": "descriptor pairs/s", "cores": cores, "kind": "reference",
-            "sample": f"{sample_images} images x {sample_points} keypoints ({kind}), {sample_images * (sample_images - 1) // 2} "
-                      f"image pairs, reference's own Pairing timer, -nt {cores}",
-            "seconds": pairing}
+    out = {"value": pairs / pairing, "unit": "descriptor pairs/s", "cores": cores, "kind": "reference",
+           "sample": text + "; reference's own Pairing timer (match.cpp:655)", "seconds": pairing, "wall_s": wall}
+    if parity is not None:
+        out["parity"] = parity
+    return out
 
 
 def bench_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n_img, n_pts, kind, dist, ratio = WORKLOADS[args.workload]
-    cores = os.cpu_count() or 1
-    s_img, s_pts = sample_size(cores)
     tmp = tempfile.mkdtemp(prefix="fm_ref_")
     try:
-        lst = cpu_sample_group(tmp, kind, s_img, s_pts)
-        times, pairs = [], 0.0
+        lst, dist, ratio, cores, text = reference_sample(args.workload, tmp)
+        times, walls, pairs = [], [], 0.0
         for it in range(args.warmup + args.steps):
-            pairs, pairing, _ = run_reference(lst, dist, ratio, cores)
+            pairs, pairing, wall = run_reference(lst, dist, ratio, cores)
             if it >= args.warmup:
                 times.append(pairing)
+                walls.append(wall)
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
     t = float(np.mean(times))
     val = pairs / t
-    sample = f"{s_img} images x {s_pts} keypoints ({kind}) per step = {pairs:.3g} descriptor pairs"
+    sample = f"{text} per step = {pairs:.3g} descriptor pairs"
     line = {
-        "impl": "reference", "metric": "descriptor pairs/sec (keypoint matching, match.cpp ComputeMatches)",
+        "impl": "reference", "metric": METRIC,
         "value": val, "unit": "descriptor pairs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
         "config": {"workload": workload_name(args.workload, args.gpus), "reference_sample": sample},
         "cpu_baseline": {"value": val, "unit": "descriptor pairs/s", "cores": cores, "kind": "reference", "sample": sample},
         "e2e": {"value": val, "unit": "descriptor pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "wall": {"unit": "s", "what": "match_ref process start -> exit on the sample (.bin inputs)", "seconds": float(np.mean(walls))},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
-
-
-def workload_name(w, gpus):
-    n_img, n_pts, kind, dist, ratio = WORKLOADS[w]
-    s = f"{w}: {n_img} images x {n_pts} keypoints, {kind} SURF3D descriptors (D=48), -d {dist:g} -d2 {ratio:g}, all {n_img * (n_img - 1) // 2} image pairs"
-    if gpus > 1:
-        s += f"; one such group per GPU ({gpus} groups), match lists gathered to rank 0 over NCCL"
-    return s
 
 
 # --------------------------------------------------------------------------------------------------
@@ -199,6 +259,39 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def bin_match_wall(kps, kind, thr, ratio, gpus, formats):
+    """Wall time of the drop-in executable on the same group: `bin/match list -o pairs.bin -d .. -d2 .. -gpus N`,
+    process start to exit (the reference prints the same three phase timers, match.cpp:572-573, 611-612, 654-655)."""
+    from frog_b200 import build, synth
+    out = {"unit": "s", "what": "bin/match process start -> exit on the workload's group (files in the page cache)", "gpus": gpus}
+    cores = os.cpu_count() or 1
+    for fmt in formats:
+        tmp = tempfile.mkdtemp(prefix="fm_wall_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+        try:
+            lst = synth.write_group(tmp, kind, len(kps), kps[0].n, fmt=fmt, threads=min(cores, 32), keypoints=kps)
+            stats = os.path.join(tmp, "stats.json")
+            env = dict(os.environ)  # the executable narrows CUDA_VISIBLE_DEVICES to the devices it plans to use
+            runs = []
+            for _ in range(2):  # the first run also pays for the cold start of the CUDA driver state on this box
+                t0 = time.perf_counter()
+                r = subprocess.run([build.BIN, lst, "-o", os.path.join(tmp, "pairs.bin"), "-d", repr(thr), "-d2", repr(ratio),
+                                    "-gpus", str(gpus), "-stats", stats], capture_output=True, text=True, env=env)
+                wall = time.perf_counter() - t0
+                if r.returncode != 0:
+                    raise RuntimeError(f"bin/match failed ({r.returncode}): {r.stderr[-300:]}")
+                secs = [float(x) for x in re.findall(r" : ([0-9.eE+-]+)s$", r.stdout, flags=re.M)]
+                st = json.load(open(stats))
+                runs.append({"seconds": wall, "load_s": secs[0] if secs else None, "prune_s": secs[1] if len(secs) > 1 else None,
+                             "pairing_s": secs[2] if len(secs) > 2 else None, "gpu_ms_max": st.get("gpu_ms_max"),
+                             "matches": st.get("matches"), "gpus_used": st.get("gpus")})
+            best = min(runs, key=lambda x: x["seconds"])
+            best["first_run_seconds"] = runs[0]["seconds"]
+            out[fmt.replace(".", "_")] = best
+        finally:
+            shutil.rmtree(tmp, ignore_errors=True)
+    return out
+
+
 def bench_ours(args):
     import torch
     import torch.distributed as dist
@@ -219,29 +312,36 @@ def bench_ours(args):
     json_out = os.fdopen(os.dup(1), "w")
     os.dup2(2, 1)
     if world > 1:
-        # NCCL on a high-priority stream: the list transfer of one group runs while the next group's scoring kernel
+        # NCCL on a high-priority stream: the list transfer of one step runs while the next step's scoring kernel
         # still has thread blocks waiting to be dispatched, and must not queue behind them
         opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
         dist.init_process_group("nccl", device_id=dev, pg_options=opts)
+        host_group = dist.new_group(backend="gloo")  # CPU-side barrier: idle ranks must not spin a kernel on their GPU
     n_img, n_pts, kind, thr, ratio = WORKLOADS[args.workload]
 
-    # ---- synthetic group of this rank, in pinned host memory -----------------------------------
-    kps = [synth.make(kind, n_pts, rank * n_img + i) for i in range(n_img)]
+    # ---- the synthetic group (the same on every rank), in pinned host memory -----------------------
+    kps = [synth.make(kind, n_pts, i) for i in range(n_img)]
     host = []
     for k in kps:
-        d = torch.from_numpy(k.desc).pin_memory()
-        s = torch.from_numpy(k.scale).pin_memory()
-        l = torch.from_numpy(k.lap).pin_memory()
-        host.append((d, s, l))
-    h2d_bytes = sum(d.numel() * 4 + s.numel() * 4 + l.numel() * 4 for d, s, l in host)
-    pf = [i for i in range(n_img) for j in range(i + 1, n_img)]
-    ps = [j for i in range(n_img) for j in range(i + 1, n_img)]
-    desc_pairs_rank = float(sum(kps[i].n * kps[j].n for i, j in zip(pf, ps)))
-
-    # a real (non-default) stream: handle 0 would mean "the context's own stream" to fm_set_stream
-    stream = torch.cuda.Stream(device=dev)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+        host.append((torch.from_numpy(k.desc).pin_memory(), torch.from_numpy(k.scale).pin_memory(),
+                     torch.from_numpy(k.lap).pin_memory()))
+    pf_all = [i for i in range(n_img) for j in range(i + 1, n_img)]
+    ps_all = [j for i in range(n_img) for j in range(i + 1, n_img)]
+    weights = [float(kps[i].n) * float(kps[j].n) for i, j in zip(pf_all, ps_all)]
+    total_pairs = float(sum(weights))
+    # ---- this rank's share of the image pairs (match.cpp:638-652 is the loop being sharded) ---------
+    shards = fdist.shard_pairs(weights, world)
+    mine = shards[rank]
+    pf = [pf_all[p] for p in mine]
+    ps = [ps_all[p] for p in mine]
+    needed = sorted(set(pf) | set(ps))
+    h2d_bytes = sum(host[i][0].numel() * 4 + host[i][1].numel() * 4 + host[i][2].numel() * 4 for i in needed)
     rows_rank = sum(kps[j].n for j in ps)  # one outer-loop row per keypoint of image `second`, per image pair
+
+    # real (non-default) streams: handle 0 would mean "the context's own stream" to fm_set_stream
+    stream = torch.cuda.Stream(device=dev)
+    comm = torch.cuda.Stream(device=dev, priority=-1)  # list hand-off: NCCL transfers and D2H copies
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
     def barrier():
         if world > 1:
@@ -249,97 +349,53 @@ def bench_ours(args):
         torch.cuda.synchronize()
 
     def upload_all(mm):
-        for i, (d, s, l) in enumerate(host):
+        for i in needed:
+            d, s, l = host[i]
             mm.upload_raw(i, d.data_ptr(), s.data_ptr(), l.data_ptr(), d.shape[0], d.shape[1])
 
+    class PinnedLists:
+        """Rank 0's host-side landing area for the match lists; grows on demand."""
+
+        def __init__(self):
+            self.buf = torch.empty(1 << 20, dtype=torch.int32).pin_memory()
+
+        def view(self, off, n):
+            if off + n > self.buf.numel():
+                nb = torch.empty(max(off + n, 2 * self.buf.numel()), dtype=torch.int32).pin_memory()
+                nb[:off].copy_(self.buf[:off])
+                self.buf = nb
+            return self.buf[off:off + n]
+
+    landing = PinnedLists()
+
+    def hand_off(res, to_host):
+        """Lists of a finished step to rank 0 (device; and on to pinned host memory with to_host).  The step's kernels
+        are done (res.wait() returned), so nothing here waits for the compute stream: transfers run on `comm` beside
+        the next step's kernels.  Returns the D2H bytes this rank copied."""
+        d2h = 0
+        cptr, pptr = res.device_pointers()
+        counts = fdist.as_torch_u32(cptr, res.n_pairs, dev)
+        pairs = fdist.as_torch_u32(pptr, 2 * int(res.total), dev)
+        with torch.cuda.stream(comm):
+            got = fdist.gather_match_lists(counts, pairs, 0) if world > 1 else ([counts], [pairs])
+            if to_host and rank == 0:
+                off = 0
+                for c, p in zip(*got):
+                    for t in (c, p):
+                        if t.numel():
+                            landing.view(off, t.numel()).copy_(t, non_blocking=True)
+                            off += t.numel()
+                d2h = off * 4
+        comm.synchronize()  # lists have left this GPU / reached rank 0: the result's buffers may be reused
+        return d2h
+
     # ---- resident: keypoints stay in HBM, K asynchronous fm_match calls back to back ---------------
-    # Every call is queued with FM_FLAG_ASYNC (no host synchronisation inside the timed region); for N > 1 the
-    # compacted lists go GPU-to-GPU to rank 0 in fixed-capacity buffers right behind the kernels that wrote them,
-    # and the stream waits for that transfer one step later (it overlaps the next group's scoring).
     m = capi.Matcher(local)
     m.set_stream(stream.cuda_stream)
     upload_all(m)
     m.synchronize()
-    recv = fdist.FixedGather(len(pf), 2 * rows_rank, dev, slots=2) if world > 1 else None
-    pending, retired = collections.deque(), []
-
-    def retire(keep):
-        while len(pending) > keep:
-            res, works = pending.popleft()
-            for w in works:
-                w.wait()  # stream-level: the compute stream waits for the NCCL transfer before the buffers are reused
-            retired.append((res.stats(), res.total))
-            res.free()
-
-    step_no = [0]
-
-    def step_resident():
-        retire(1)
-        res = m.match(pf, ps, thr, ratio, device_only=True, asynchronous=True)
-        works = []
-        if world > 1:
-            cptr, pptr = res.device_pointers()
-            works = recv.start(fdist.as_torch_u32(cptr, len(pf), dev), fdist.as_torch_u32(pptr, 2 * rows_rank, dev),
-                               step_no[0] % 2)
-        step_no[0] += 1
-        pending.append((res, works))
-
-    def timed_resident(steps, warmup):
-        for _ in range(warmup):
-            step_resident()
-        retire(0)
-        retired.clear()
-        evs = []
-        barrier()
-        t0 = time.time()
-        for k in range(steps + 1):
-            if k < steps:
-                flush.zero_()  # evict the group (38 MB at c2) from the 126 MB L2 between timed steps
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record(stream)
-            if k < steps:
-                step_resident()
-            else:
-                retire(0)  # the last transfers, inside a bracket of their own
-            b.record(stream)
-            evs.append((a, b))
-        barrier()
-        t1 = time.time()
-        ms = sum(a.elapsed_time(b) for a, b in evs)
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item()), t0, t1
-
-    sampler = ClockSampler(local) if rank == 0 else None
-    with torch.cuda.stream(stream):
-        ms_res, t0, t1 = timed_resident(args.steps, args.warmup)
-    clocks = sampler.stop(t0, t1) if sampler else None
-    stats = [o[0] for o in retired]
-    matches = retired[-1][1]
-    m.close()
-
-    # ---- end to end: host buffers in, host lists out, through the C ABI ---------------------------
-    # Two contexts on two streams, used alternately as a three-stage pipeline: while one runs group k's prep +
-    # kernels, the other first hands group k-1's lists to pinned host memory (D2H; for N > 1 after the NCCL gather
-    # to rank 0) and then uploads group k+1 (H2D).  Every step's H2D and D2H is inside the timed region, which is
-    # ONE CUDA-event bracket around all K steps (L2 flush writes included).
-    streams = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]
-    ctxs = [capi.Matcher(local), capi.Matcher(local)]
-    for mm, st in zip(ctxs, streams):
-        mm.set_stream(st.cuda_stream)
-    e2e_gather = fdist.FixedGather(len(pf), 2 * rows_rank, dev, slots=2) if world > 1 else None
-    e2e_no = [0]
-    pinned_out = [(torch.empty(len(pf), dtype=torch.int32).pin_memory(), torch.empty(2 * rows_rank, dtype=torch.int32).pin_memory())
-                  for _ in range(world if (world > 1 and rank == 0) else 0)]
-
-    def e2e_start(mm, st):
-        with torch.cuda.stream(st):
-            flush.zero_()
-            # prep + kernels queued, call returns; lists go to pinned host memory in e2e_finish (world == 1)
-            return mm.match(pf, ps, thr, ratio, device_only=world > 1, asynchronous=True)
-
-    host_ms = collections.defaultdict(float)  # host wall-clock per e2e phase (this rank), timed steps only
+    retired = []
+    host_ms = collections.defaultdict(float)
 
     class phase:
         def __init__(self, name):
@@ -351,47 +407,74 @@ def bench_ours(args):
         def __exit__(self, *a):
             host_ms[self.name] += (time.perf_counter() - self.t) * 1e3
 
-    # N > 1: list transfers of a finished group run beside the next group's upload, on streams of their own
-    drain = [torch.cuda.Stream(device=dev) for _ in range(world if rank == 0 else 1)]
-
-    def e2e_finish(res, st):
-        if world == 1:
-            with phase("wait_fetch"):
-                res.wait()  # counts, then the lists to pinned host memory (D2H on the context's stream)
-            d2h = res.total * 8 + res.n_pairs * 4
-            res.free()
-            return d2h
+    def finish_resident(res):
         with phase("wait_kernels"):
-            res.wait()  # the group's kernels are done; its lists sit in the result's own device buffers
+            res.wait()  # this step's kernels are done; the next step's are already queued behind them
+        if world > 1:
+            with phase("gather"):
+                hand_off(res, to_host=False)
+        retired.append((res.stats(), int(res.total)))
+        res.free()
+
+    def timed_resident(steps, warmup):
+        prev = None
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = 0.0
+        for k in range(warmup + steps):
+            if k == warmup:
+                if prev is not None:
+                    finish_resident(prev)
+                    prev = None
+                retired.clear()
+                host_ms.clear()
+                barrier()
+                t0 = time.time()
+                e0.record(stream)
+            with torch.cuda.stream(stream):
+                flush.zero_()  # evict the group from the 126 MB L2 between steps
+                res = m.match(pf, ps, thr, ratio, device_only=True, asynchronous=True)
+            if prev is not None:
+                finish_resident(prev)
+            prev = res
+        finish_resident(prev)
+        stream.wait_stream(comm)
+        e1.record(stream)
+        barrier()
+        t1 = time.time()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), t0, t1
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms_res, t0, t1 = timed_resident(args.steps, args.warmup)
+    clocks = sampler.stop(t0, t1) if sampler else None
+    stats = [o[0] for o in retired]
+    matches_rank = retired[-1][1]
+    res_host_ms = {k: round(v / args.steps, 4) for k, v in host_ms.items()}
+    m.close()
+
+    # ---- end to end: host buffers in, host lists out, through the C ABI ---------------------------
+    # Two contexts on two streams, used alternately as a three-stage pipeline: while one runs step k's prep +
+    # kernels, the other first hands step k-1's lists to rank 0's pinned host memory (NCCL gather for N > 1, then D2H)
+    # and then uploads step k+1's images (H2D).  Every step's H2D and D2H is inside the timed region, which is
+    # ONE CUDA-event bracket around all K steps (L2 flush writes included).
+    streams = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]
+    ctxs = [capi.Matcher(local), capi.Matcher(local)]
+    for mm, st in zip(ctxs, streams):
+        mm.set_stream(st.cuda_stream)
+
+    def e2e_start(mm, st):
+        with torch.cuda.stream(st):
+            flush.zero_()
+            # prep + kernels queued, call returns; the lists reach the host in e2e_finish
+            return mm.match(pf, ps, thr, ratio, device_only=True, asynchronous=True)
+
+    def e2e_finish(res):
+        with phase("wait_kernels"):
+            res.wait()
         with phase("gather_d2h"):
-            cptr, pptr = res.device_pointers()
-            pairs_cap = fdist.as_torch_u32(pptr, 2 * rows_rank, dev)
-            slot = e2e_no[0] % 2
-            e2e_no[0] += 1
-            with torch.cuda.stream(drain[0]):
-                works = e2e_gather.start(fdist.as_torch_u32(cptr, res.n_pairs, dev), pairs_cap, slot, per_peer=True)
-            d2h = 0
-            if rank == 0:
-                # rank 0: its own lists, then every peer's counts and (capacity-sized) list buffer to pinned host memory,
-                # each peer on a stream of its own so that its D2H copy starts as soon as ITS lists have arrived
-                with torch.cuda.stream(drain[0]):
-                    n = 2 * res.total
-                    pinned_out[0][1][:n].copy_(pairs_cap[:n], non_blocking=True)
-                    d2h += n * 4 + res.n_pairs * 4
-                for r in range(1, world):
-                    with torch.cuda.stream(drain[r]):
-                        for w in works[r]:
-                            w.wait()
-                        pinned_out[r][0].copy_(e2e_gather.counts[slot][r], non_blocking=True)
-                        pinned_out[r][1].copy_(e2e_gather.pairs[slot][r], non_blocking=True)
-                    d2h += (len(pf) + 2 * rows_rank) * 4
-                for st_r in drain:
-                    st_r.synchronize()  # lists are on the host
-            else:
-                with torch.cuda.stream(drain[0]):
-                    for w in works[0]:
-                        w.wait()
-                drain[0].synchronize()  # lists have left this GPU
+            d2h = hand_off(res, to_host=True)
         res.free()
         return d2h
 
@@ -404,28 +487,30 @@ def bench_ours(args):
             cur, st = ctxs[k % 2], streams[k % 2]
             if k == warmup:
                 if prev is not None:
-                    d2h.append(e2e_finish(*prev))
+                    d2h.append(e2e_finish(prev))
                     prev = None
                 barrier()  # every stream of every rank is idle: start the clock
                 host_ms.clear()
                 e0.record(st)
                 cur.clear()
-                upload_all(cur)  # pipeline fill: the first timed group's own upload is inside the region
+                upload_all(cur)  # pipeline fill: the first timed step's own upload is inside the region
             with phase("start_prep"):
-                res = e2e_start(cur, st)  # group k: prep + kernels queued
+                res = e2e_start(cur, st)  # step k: prep + kernels queued
             if k + 1 < total and k + 1 != warmup:
-                # group k+1: H2D from pinned host memory, under group k's kernels.  Its context is the one that ran
-                # group k-1; that group's lists live in the result's own buffers, not in the image arena.
+                # step k+1: H2D from pinned host memory, under step k's kernels.  Its context is the one that ran
+                # step k-1; that step's lists live in the result's own buffers, not in the image arena.
                 nxt = ctxs[(k + 1) % 2]
                 with phase("clear"):
                     nxt.clear()
                 with phase("upload_enqueue"):
                     upload_all(nxt)
             if prev is not None:
-                d2h.append(e2e_finish(*prev))  # group k-1: lists to (rank 0's) pinned host memory, under group k's kernels
-            prev = (res, st)
-        d2h.append(e2e_finish(*prev))
-        e1.record(streams[(total - 1) % 2])
+                d2h.append(e2e_finish(prev))  # step k-1: lists to rank 0's pinned host memory, under step k's kernels
+            prev = res
+        d2h.append(e2e_finish(prev))
+        last = streams[(total - 1) % 2]
+        last.wait_stream(comm)
+        e1.record(last)
         barrier()
         ms = e0.elapsed_time(e1)
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
@@ -435,63 +520,80 @@ def bench_ours(args):
 
     ms_e2e, d2h_list = timed_e2e(args.steps, max(1, args.warmup))
     d2h_bytes = float(np.mean(d2h_list))
+    e2e_host_ms = {k: round(v / args.steps, 4) for k, v in host_ms.items()}
     for mm in ctxs:
         mm.close()
 
     # whole-job aggregates
-    agg = torch.tensor([desc_pairs_rank, float(h2d_bytes), d2h_bytes, float(sum(s["kernel_launches"] for s in stats)),
-                        float(matches)], dtype=torch.float64, device=dev)
+    agg = torch.tensor([float(h2d_bytes), d2h_bytes, float(sum(s["kernel_launches"] for s in stats)), float(matches_rank)],
+                       dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(agg, op=dist.ReduceOp.SUM)
-    total_pairs, h2d_all, d2h_all, launches, matches_all = agg.tolist()
+    h2d_all, d2h_all, launches, matches_all = agg.tolist()
 
+    torch.cuda.synchronize()
     if rank == 0:
         peak_tf, peak_gbs, which = peaks()
+        n_launch = float(np.mean([s["score_launches"] for s in stats]))
         sc_ms = float(np.mean([s["ms_score"] / max(1, s["score_launches"]) for s in stats]))
         pairs_per_launch = float(np.mean([s["descriptor_pairs"] / max(1, s["score_launches"]) for s in stats]))
         scored_per_launch = float(np.mean([s["scored_pairs"] / max(1, s["score_launches"]) for s in stats]))
         achieved = FLOP_PER_PAIR * pairs_per_launch / (sc_ms * 1e-3) / 1e12 if sc_ms > 0 else 0.0
         executed = 2.0 * 64.0 * scored_per_launch / (sc_ms * 1e-3) / 1e12 if sc_ms > 0 else 0.0
         s0 = stats[-1]
+        comp_bytes = 4.0 * s0["rows"] + 8.0 * matches_rank  # one 4-byte read per outer-loop row, one 8-byte write per match
         line = {
-            "metric": "descriptor pairs/sec (keypoint matching, match.cpp ComputeMatches)",
+            "metric": METRIC,
             "value": total_pairs * args.steps / (ms_res * 1e-3), "unit": "descriptor pairs/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_res / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16 operands / f32 accumulate + exact f32 rescoring",
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f16 operands / f32 accumulate + exact f32 rescoring",
             "data": "synthetic",
             "config": {"workload": workload_name(args.workload, world), "l2": "256 MiB flush buffer written between timed steps",
-                       "timing": "value: CUDA events per step on the launch stream, summed over steps (asynchronous fm_match calls, no host "
-                                 "synchronisation between steps), max over ranks; e2e: one CUDA-event bracket around all steps, two contexts "
-                                 "used alternately so a group's H2D upload overlaps the previous group's kernels",
-                       "matches_per_step": matches_all},
+                       "timing": "value and e2e: one CUDA-event bracket around all steps (asynchronous fm_match calls, a step's "
+                                 "list hand-off overlaps the next step's kernels), max over ranks; e2e alternates two contexts so "
+                                 "a step's H2D upload overlaps the previous step's kernels",
+                       "image_pairs_per_rank": [len(s) for s in shards], "matches_per_step": matches_all},
             "e2e": {"value": total_pairs * args.steps / (ms_e2e * 1e-3), "unit": "descriptor pairs/s",
                     "h2d_bytes_per_step": h2d_all, "d2h_bytes_per_step": d2h_all, "ms_per_step": ms_e2e / args.steps,
-                    "rank0_host_ms_per_step": {k: round(v / args.steps, 4) for k, v in host_ms.items()}},
+                    "rank0_host_ms_per_step": e2e_host_ms},
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": achieved / peak_tf, "traffic": measured_traffic(args.workload), "peak_source": which + " (cuBLAS bf16 burst)",
-                         "kernel": "fm::score_kernel<false>", "kernel_ms": sc_ms,
+                         "kernel": "fm::score_kernel<false>", "kernel_ms": sc_ms, "launches_per_step": n_launch,
                          "algorithmic_flop_per_launch": FLOP_PER_PAIR * pairs_per_launch,
-                         "executed_tflops": executed, "scored_fraction": scored_per_launch / max(1.0, pairs_per_launch)},
-            # stream compaction (HBM-bound): 4 B read per row by each of the count and scatter passes,
-            # 8 B written per match, over the CUDA-event time of the three compaction kernels
+                         "executed_tflops": executed, "executed_frac": executed / peak_tf,
+                         "scored_fraction": scored_per_launch / max(1.0, pairs_per_launch), "rank": 0},
+            # stream compaction (HBM-bound), rank 0's share, over the CUDA-event time of its kernel(s)
             "compaction": {"bound": "hbm", "unit": "GB/s", "peak": peak_gbs, "peak_source": which,
-                           "achieved": (8.0 * s0["rows"] + 8.0 * matches) / max(s0["ms_compact"] * 1e-3, 1e-12) / 1e9,
-                           "frac": (8.0 * s0["rows"] + 8.0 * matches) / max(s0["ms_compact"] * 1e-3, 1e-12) / 1e9 / peak_gbs,
-                           "kernel_ms": s0["ms_compact"]},
+                           "achieved": comp_bytes / max(s0["ms_compact"] * 1e-3, 1e-12) / 1e9,
+                           "frac": comp_bytes / max(s0["ms_compact"] * 1e-3, 1e-12) / 1e9 / peak_gbs,
+                           "kernel_ms": s0["ms_compact"], "bytes": comp_bytes},
             "phases_ms": {k: s0[k] for k in ("ms_total", "ms_score", "ms_rescore", "ms_exact", "ms_compact", "ms_prep")},
+            "rank0_host_ms_per_step": res_host_ms,
             "rows_exact_frac": s0["rows_exact"] / max(1, s0["rows"]), "candidates_per_row": s0["candidates"] / max(1, s0["rows"]),
+            # differences from the reference whose distance / ratio sits within 4 ulp of -d / -d2, counted on the
+            # cpu_baseline sample (N = 1 runs; null when that leg did not run)
+            "threshold_eps_count": None,
             "clocks": clocks,
         }
+        if not args.no_wall:
+            try:
+                line["wall"] = bin_match_wall(kps, kind, thr, ratio, world, ["bin"] + ([] if args.no_wall_gz else ["csv.gz"]))
+            except Exception as e:
+                line["wall"] = {"unit": "s", "error": str(e)[:300]}
         if not args.no_cpu_baseline and world == 1:
             try:
-                line["cpu_baseline"] = cpu_baseline(args.workload)
+                line["cpu_baseline"] = cpu_baseline(args.workload, parity_device=local)
+                par = line["cpu_baseline"].get("parity") or {}
+                if "threshold_eps_count" in par:
+                    line["threshold_eps_count"] = par["threshold_eps_count"]
             except Exception as e:  # the baseline must never take the GPU numbers down with it
                 line["cpu_baseline"] = {"value": None, "unit": "descriptor pairs/s", "cores": os.cpu_count(), "kind": "reference",
                                         "sample": f"failed: {e}"}
         print(json.dumps(line), file=json_out, flush=True)
     if world > 1:
-        dist.barrier()
+        dist.barrier(group=host_group)  # ranks > 0 wait here (on the CPU) while rank 0 times bin/match and the CPU baseline
         dist.destroy_process_group()
 
 
@@ -501,8 +603,10 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-wall", action="store_true")
+    ap.add_argument("--no-wall-gz", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -19,12 +19,13 @@ FLAG_FORCE_EXACT = 2
 FLAG_DEVICE_ONLY = 4
 FLAG_ASYNC = 8
 FLAG_MATCH_ALL = 16
+FLAG_DISTANCES = 32
 
 # every symbol include/frogmatch.h declares (checked by tests/test_abi.py)
 PUBLIC_SYMBOLS = [
     "fm_device_count", "fm_create", "fm_destroy", "fm_last_error", "fm_set_stream", "fm_synchronize", "fm_upload_image",
     "fm_clear_images", "fm_image_points", "fm_match", "fm_result_wait", "fm_result_num_pairs", "fm_result_total",
-    "fm_result_count", "fm_result_pairs", "fm_result_fetch", "fm_result_device_counts",
+    "fm_result_count", "fm_result_pairs", "fm_result_distances", "fm_result_fetch", "fm_result_device_counts",
     "fm_result_device_pairs", "fm_result_free", "fm_get_stats", "fm_result_stats", "fm_version",
 ]
 DEBUG_SYMBOLS = ["fm_debug_image", "fm_debug_score_unit"]
@@ -78,6 +79,8 @@ def load():
     L.fm_result_count.restype = C.c_uint32
     L.fm_result_pairs.argtypes = [vp, C.c_size_t]
     L.fm_result_pairs.restype = u32p
+    L.fm_result_distances.argtypes = [vp, C.c_size_t]
+    L.fm_result_distances.restype = f32p
     L.fm_result_fetch.argtypes = [vp]
     L.fm_result_wait.argtypes = [vp]
     L.fm_result_stats.argtypes = [vp, C.POINTER(Stats)]
@@ -104,6 +107,7 @@ class Result:
 
     def __init__(self, matcher: "Matcher", handle, pending: bool = False):
         self._m, self._h = matcher, handle
+        matcher._live.add(self)
         self.n_pairs = matcher._L.fm_result_num_pairs(handle)
         self.total, self.counts = None, None
         if not pending:
@@ -146,6 +150,18 @@ class Result:
             raise FrogMatchError("result not fetched to the host yet (FM_FLAG_DEVICE_ONLY)")
         return np.ctypeslib.as_array(ptr, shape=(n, 2)).copy()
 
+    def distances(self, p: int) -> np.ndarray:
+        """[count] float32 squared distances of pair p's matches (FM_FLAG_DISTANCES), in list order."""
+        if self.counts is None:
+            self.wait()
+        n = int(self.counts[p])
+        if n == 0:
+            return np.zeros(0, np.float32)
+        ptr = self._m._L.fm_result_distances(self._h, p)
+        if not ptr:
+            raise FrogMatchError("no distances: pass distances=True to match() (and fetch device-only results)")
+        return np.ctypeslib.as_array(ptr, shape=(n,)).copy()
+
     def all_pairs(self):
         return [self.pairs(p) for p in range(self.n_pairs)]
 
@@ -156,7 +172,9 @@ class Result:
 
     def free(self) -> None:
         if self._h:
-            self._m._L.fm_result_free(self._h)
+            if self._m._h:  # a closed Matcher has already released everything its results own (fm_destroy)
+                self._m._L.fm_result_free(self._h)
+            self._m._live.discard(self)
             self._h = None
 
     def __del__(self):
@@ -178,6 +196,7 @@ class Matcher:
             raise FrogMatchError(f"fm_create failed ({rc}): {self._L.fm_last_error(None).decode()}")
         self._h = h
         self._keep = []
+        self._live = set()  # results that still own native buffers: freed before the context goes away
 
     def _check(self, rc: int) -> None:
         if rc != 0:
@@ -185,6 +204,8 @@ class Matcher:
 
     def close(self) -> None:
         if self._h:
+            for r in list(self._live):
+                r.free()
             self._L.fm_destroy(self._h)
             self._h = None
 
@@ -218,12 +239,12 @@ class Matcher:
 
     def match(self, pair_first, pair_second, dist: float = 0.22, ratio: float = 1.0, sym: bool = False,
               force_exact: bool = False, device_only: bool = False, asynchronous: bool = False,
-              match_all: bool = False) -> Result:
+              match_all: bool = False, distances: bool = False) -> Result:
         pf = np.ascontiguousarray(pair_first, np.uint32)
         ps = np.ascontiguousarray(pair_second, np.uint32)
         flags = (FLAG_SYM if sym else 0) | (FLAG_FORCE_EXACT if force_exact else 0) | \
                 (FLAG_DEVICE_ONLY if device_only else 0) | (FLAG_ASYNC if asynchronous else 0) | \
-                (FLAG_MATCH_ALL if match_all else 0)
+                (FLAG_MATCH_ALL if match_all else 0) | (FLAG_DISTANCES if distances else 0)
         h = C.c_void_p()
         self._check(self._L.fm_match(self._h, _ptr(pf), _ptr(ps), pf.shape[0], dist, ratio, flags, C.byref(h)))
         return Result(self, h, pending=asynchronous)

@@ -316,7 +316,7 @@ bool fast_inflate_gzip(const uint8_t* src, size_t n, std::vector<char>& out, siz
 #undef FM_TAKE
   // ---- trailer: CRC-32 and size of the uncompressed data ----
   in -= bitcnt >> 3;  // whole bytes still in the bit buffer belong to the trailer
-  if (in + 8 > in_end) return false;
+  if (in + 8 != in_end) return false;  // the member must end where the file ends: further members / trailing bytes are zlib's business
   const uint32_t crc = (uint32_t)in[0] | ((uint32_t)in[1] << 8) | ((uint32_t)in[2] << 16) | ((uint32_t)in[3] << 24);
   const uint32_t size = (uint32_t)in[4] | ((uint32_t)in[5] << 8) | ((uint32_t)in[6] << 16) | ((uint32_t)in[7] << 24);
   const size_t got = (size_t)(o - out_begin);

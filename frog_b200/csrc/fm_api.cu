@@ -22,9 +22,10 @@ struct fm_result {
   uint32_t flags = 0;
   std::vector<uint32_t> counts;
   std::vector<uint64_t> offsets;
-  DevBuf d_out, d_counts;
+  DevBuf d_out, d_counts, d_dist;
   uint32_t* h_pairs = nullptr;  // pinned
   size_t h_cap = 0;
+  float* h_dist = nullptr;  // pinned, FM_FLAG_DISTANCES only
   bool fetched = false;
   // completion: the call's DeviceCounters and per-pair counts land in a pinned block, `done` fires behind them
   void* h_block = nullptr;
@@ -70,6 +71,13 @@ int sync_images(fm_ctx* c) {
     }
     FM_CUDA(c, cudaMemcpyAsync(c->h_metas.data(), c->d_metas.p, n * sizeof(ImageMeta), cudaMemcpyDeviceToHost, c->stream));
     FM_CUDA(c, cudaStreamSynchronize(c->stream));
+    // the bracket above has completed: fold it into the running sum and recycle its events (a long-lived context that
+    // re-uploads images without ever clearing must not accumulate events)
+    for (auto& sp : c->ev_prep.spans) {
+      float ms = 0;
+      if (cudaEventElapsedTime(&ms, sp.a, sp.b) == cudaSuccess) c->ms_prep_acc += ms;
+    }
+    c->ev_prep.reset();
   }
   c->images_dirty = false;
   return FM_OK;
@@ -213,11 +221,12 @@ void fm_destroy(fm_ctx* c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   c->arena.release();
-  DevBuf* bufs[] = {&c->s_keys, &c->s_keys_sorted, &c->s_idx, &c->s_idx_sorted, &c->s_norm2, &c->s_sort, &c->s_segs, &c->d_images, &c->d_metas, &c->d_meta_blob, &c->d_rowres, &c->d_chunk_count, &c->d_chunk_out,
+  DevBuf* bufs[] = {&c->s_keys, &c->s_keys_sorted, &c->s_idx, &c->s_idx_sorted, &c->s_norm2, &c->s_sort, &c->s_segs, &c->d_images, &c->d_metas, &c->d_meta_blob, &c->d_rowres, &c->d_rowdist, &c->d_chunk_status, &c->d_ticket,
                     &c->d_totals, &c->d_bands, &c->d_cands, &c->d_redo, &c->d_taskinfo, &c->d_all, &c->d_all_tasks};
   for (auto* b : bufs) b->release();
   for (auto& b : c->out_free) b.release();
   for (auto& b : c->counts_free) b.release();
+  for (auto& b : c->dist_free) b.release();
   for (auto& pb : c->pin_free) cudaFreeHost(pb.first);
   if (c->cache_pinned) cudaFreeHost(c->cache_pinned);
   if (c->h_pinned) cudaFreeHost(c->h_pinned);
@@ -251,10 +260,12 @@ int fm_clear_images(fm_ctx* c) {
   c->dirty.clear();
   c->images_dirty = true;
   c->dim = 0;
-  cudaSetDevice(c->device);
-  cudaStreamSynchronize(c->stream);
+  // the arena is handed out again right away: everything that still reads the old tensors must have finished
+  FM_CUDA(c, cudaSetDevice(c->device));
+  FM_CUDA(c, cudaStreamSynchronize(c->stream));
   c->arena.reset();
   c->ev_prep.reset();
+  c->ms_prep_acc = 0.f;
   return FM_OK;
 }
 
@@ -402,6 +413,8 @@ int fm_match(fm_ctx* c, const uint32_t* pair_first, const uint32_t* pair_second,
   r->flags = flags;
   r->d_out = take_buf(c->out_free, std::max<uint64_t>(total_rows, 1) * sizeof(uint2));
   r->d_counts = take_buf(c->counts_free, std::max<size_t>(n_pairs, 1) * sizeof(uint32_t));
+  const bool want_dist = (flags & FM_FLAG_DISTANCES) && !match_all;
+  if (want_dist) r->d_dist = take_buf(c->dist_free, std::max<uint64_t>(total_rows, 1) * sizeof(float));
 #define FM_CUDA_R(expr)                       \
   do {                                        \
     cudaError_t e__ = (expr);                 \
@@ -457,8 +470,19 @@ int fm_match(fm_ctx* c, const uint32_t* pair_first, const uint32_t* pair_second,
   uint32_t max_rows = 1, max_chunks = 1;
   for (auto& b : batches) { max_rows = std::max(max_rows, b.rows); max_chunks = std::max(max_chunks, b.chunks); }
   FM_CUDA_R(c->d_rowres.ensure((size_t)max_rows * sizeof(uint32_t)));
-  FM_CUDA_R(c->d_chunk_count.ensure((size_t)max_chunks * sizeof(uint32_t)));
-  FM_CUDA_R(c->d_chunk_out.ensure((size_t)max_chunks * sizeof(uint64_t)));
+  if (want_dist) {
+    FM_CUDA_R(c->d_rowdist.ensure((size_t)max_rows * sizeof(float)));
+    FM_CUDA_R(r->d_dist.ensure(std::max<uint64_t>(total_rows, 1) * sizeof(float)));
+  }
+  if (c->d_chunk_status.cap < (size_t)max_chunks * sizeof(unsigned long long)) {
+    // fresh memory may hold anything: clear it once, then the launch epoch tells stale words from current ones
+    FM_CUDA_R(c->d_chunk_status.ensure((size_t)max_chunks * sizeof(unsigned long long) * 2));
+    FM_CUDA_R(cudaMemsetAsync(c->d_chunk_status.p, 0, c->d_chunk_status.cap, c->stream));
+  }
+  if (!c->d_ticket.p) {
+    FM_CUDA_R(c->d_ticket.ensure(256));
+    FM_CUDA_R(cudaMemsetAsync(c->d_ticket.p, 0, 256, c->stream));
+  }
   FM_CUDA_R(c->d_totals.ensure(sizeof(DeviceCounters)));
   FM_CUDA_R(r->d_out.ensure(std::max<uint64_t>(total_rows, 1) * sizeof(uint2)));
   FM_CUDA_R(r->d_counts.ensure(std::max<size_t>(n_pairs, 1) * sizeof(uint32_t)));
@@ -467,6 +491,7 @@ int fm_match(fm_ctx* c, const uint32_t* pair_first, const uint32_t* pair_second,
 
   const ImageDev* d_images = c->d_images.as<ImageDev>();
   uint32_t* d_rowres = c->d_rowres.as<uint32_t>();
+  float* d_rowdist = want_dist ? c->d_rowdist.as<float>() : nullptr;
   DeviceCounters* d_counters = c->d_totals.as<DeviceCounters>();
   if (match_all) {
     // ---- -all: count pass, per-task scan, emit pass (fm_all.cuh); list sizes are data-dependent ----
@@ -494,7 +519,7 @@ int fm_match(fm_ctx* c, const uint32_t* pair_first, const uint32_t* pair_second,
                                                                                  row_final, nullptr, nullptr, nullptr, nullptr);
         else
           exact_generic_kernel<1><<<b.blocks, kExactRows, 0, c->stream>>>(d_images, d_tasks, d_blk, n_tasks, dist, 1.f, 0u, nullptr, row_count,
-                                                                          row_final, nullptr, nullptr, nullptr, nullptr);
+                                                                          row_final, nullptr, nullptr, nullptr, nullptr, nullptr);
         all_scan_kernel<<<(n_tasks + 63) / 64, 64, 0, c->stream>>>(d_images, d_tasks, n_tasks, row_count, row_final, row_carry, row_off,
                                                                     d_task_total);
       }
@@ -516,7 +541,7 @@ int fm_match(fm_ctx* c, const uint32_t* pair_first, const uint32_t* pair_second,
                                                                                 row_carry, row_off, d_task_base, r->d_out.as<uint2>());
         else
           exact_generic_kernel<2><<<b.blocks, kExactRows, 0, c->stream>>>(d_images, d_tasks, d_blk, n_tasks, dist, 1.f, 0u, nullptr, nullptr,
-                                                                          nullptr, row_carry, row_off, d_task_base, r->d_out.as<uint2>());
+                                                                          nullptr, row_carry, row_off, d_task_base, r->d_out.as<uint2>(), nullptr);
       }
       FM_CUDA_R(cudaStreamSynchronize(c->stream));  // task_base (pageable) must outlive the copy
       c->stats.kernel_launches += 3;
@@ -551,6 +576,7 @@ int fm_match(fm_ctx* c, const uint32_t* pair_first, const uint32_t* pair_second,
         fa.thr = dist;
         fa.ratio = dist2second;
         fa.rowres = d_rowres;
+        fa.rowdist = d_rowdist;
         fa.counters = d_counters;
         cudaError_t e = fast_match_batch(c, fa);
         if (e != cudaSuccess) {
@@ -563,25 +589,36 @@ int fm_match(fm_ctx* c, const uint32_t* pair_first, const uint32_t* pair_second,
         Span sp(&c->ev_match, c->stream, kPhExact);
         if (c->dim == (uint32_t)kD)
           exact_match_kernel<kD><<<b.blocks, kExactRows, exact_smem_bytes(kD), c->stream>>>(
-              d_images, d_tasks + b.t0, blk, nt, dist, dist2second, kTaskExact, d_rowres);
+              d_images, d_tasks + b.t0, blk, nt, dist, dist2second, kTaskExact, d_rowres, d_rowdist);
         else
           exact_generic_kernel<0><<<b.blocks, kExactRows, 0, c->stream>>>(d_images, d_tasks + b.t0, blk, nt, dist, dist2second, kTaskExact,
-                                                                          d_rowres, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+                                                                          d_rowres, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, d_rowdist);
         c->stats.kernel_launches++;
         for (uint32_t t = b.t0; t < b.t1; t++)
           if (tasks[t].flags & kTaskExact) c->stats.rows_exact += c->images[tasks[t].row_img].n;
       }
       {
         Span sp(&c->ev_match, c->stream, kPhCompact);
-        compact_count_kernel<<<b.chunks, kCompactThreads, 0, c->stream>>>(d_images, d_tasks + b.t0, chk, nt, d_rowres,
-                                                                         c->d_chunk_count.as<uint32_t>());
-        compact_scan_kernel<<<1, 1024, 0, c->stream>>>(c->d_chunk_count.as<uint32_t>(), b.chunks, chk, nt, d_pot + b.t0,
-                                                       c->d_chunk_out.as<uint64_t>(), r->d_counts.as<uint32_t>(),
-                                                       &d_counters->running_total);
-        compact_scatter_kernel<<<b.chunks, kCompactThreads, 0, c->stream>>>(d_images, d_tasks + b.t0, chk, nt, d_rowres,
-                                                                           c->d_chunk_out.as<uint64_t>(),
-                                                                           r->d_out.as<uint2>());
-        c->stats.kernel_launches += 3;
+        CompactArgs ca{};
+        ca.images = d_images;
+        ca.tasks = d_tasks + b.t0;
+        ca.chunk_off = chk;
+        ca.n_tasks = nt;
+        ca.n_chunks = b.chunks;
+        ca.pair_of_task = d_pot + b.t0;
+        ca.rowres = d_rowres;
+        ca.rowdist = d_rowdist;
+        ca.status = c->d_chunk_status.as<unsigned long long>();
+        ca.ticket = c->d_ticket.as<uint32_t>();
+        c->compact_epoch = (c->compact_epoch % 0x3FFFFFFEu) + 1u;  // 1 .. 2^30 - 2: never the cleared value 0
+        ca.epoch = c->compact_epoch;
+        ca.pair_count = r->d_counts.as<uint32_t>();
+        ca.running_total = &d_counters->running_total;
+        ca.out_pairs = r->d_out.as<uint2>();
+        ca.out_dist = want_dist ? r->d_dist.as<float>() : nullptr;
+        if (want_dist) compact_kernel<true><<<b.chunks, kCompactThreads, 0, c->stream>>>(ca);
+        else compact_kernel<false><<<b.chunks, kCompactThreads, 0, c->stream>>>(ca);
+        c->stats.kernel_launches += 1;
       }
     }
   }
@@ -633,8 +670,10 @@ int fm_result_fetch(fm_result* r) {
     FM_CUDA(c, cudaMallocHost(reinterpret_cast<void**>(&r->h_pairs), want));
     r->h_cap = want;
   }
+  if (r->d_dist.p && !r->h_dist) FM_CUDA(c, cudaMallocHost(reinterpret_cast<void**>(&r->h_dist), std::max<uint64_t>(r->total, 1) * sizeof(float)));
   if (r->total) {
     FM_CUDA(c, cudaMemcpyAsync(r->h_pairs, r->d_out.p, r->total * sizeof(uint2), cudaMemcpyDeviceToHost, c->stream));
+    if (r->h_dist) FM_CUDA(c, cudaMemcpyAsync(r->h_dist, r->d_dist.p, r->total * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     FM_CUDA(c, cudaStreamSynchronize(c->stream));
   }
   r->fetched = true;
@@ -648,6 +687,10 @@ const uint32_t* fm_result_pairs(const fm_result* r, size_t p) {
   if (!r || p >= r->n_pairs || !r->fetched) return nullptr;
   return r->h_pairs + 2 * r->offsets[p];
 }
+const float* fm_result_distances(const fm_result* r, size_t p) {
+  if (!r || p >= r->n_pairs || !r->fetched || !r->h_dist) return nullptr;
+  return r->h_dist + r->offsets[p];
+}
 const uint32_t* fm_result_device_counts(const fm_result* r) { return r ? r->d_counts.as<uint32_t>() : nullptr; }
 const uint32_t* fm_result_device_pairs(const fm_result* r) { return r ? r->d_out.as<uint32_t>() : nullptr; }
 
@@ -660,6 +703,8 @@ void fm_result_free(fm_result* r) {
   // hand the buffers and events back to the context so the next call does not reallocate
   give_buf(c->out_free, r->d_out);
   give_buf(c->counts_free, r->d_counts);
+  give_buf(c->dist_free, r->d_dist);
+  if (r->h_dist) cudaFreeHost(r->h_dist);
   give_pinned(c, r->h_block, r->h_block_cap);
   if (!r->ev.pool.empty()) {
     if (c->ev_free.size() < 8) c->ev_free.push_back(std::move(r->ev));
@@ -685,12 +730,7 @@ int fm_get_stats(fm_ctx* c, fm_stats* out) {
     int rc = finalize(c->last);
     if (rc != FM_OK) return rc;
   }
-  float ms_prep = 0;
-  for (auto& s : c->ev_prep.spans) {
-    float ms = 0;
-    if (cudaEventElapsedTime(&ms, s.a, s.b) == cudaSuccess) ms_prep += ms;
-  }
-  c->stats.ms_prep = ms_prep;
+  c->stats.ms_prep = c->ms_prep_acc;
   *out = c->stats;
   return FM_OK;
 }

@@ -44,7 +44,7 @@ template <int D_T>
 __global__ void __launch_bounds__(kExactRows)
 exact_match_kernel(const ImageDev* __restrict__ images, const Task* __restrict__ tasks,
                    const uint32_t* __restrict__ task_blk_off, uint32_t n_tasks, float thr, float ratio,
-                   uint32_t require_flags, uint32_t* __restrict__ rowres) {
+                   uint32_t require_flags, uint32_t* __restrict__ rowres, float* __restrict__ rowdist) {
   extern __shared__ float smem[];
   const uint32_t t = find_segment(task_blk_off, n_tasks, blockIdx.x);
   const Task task = tasks[t];
@@ -103,7 +103,10 @@ exact_match_kernel(const ImageDev* __restrict__ images, const Task* __restrict__
       else if (acc < d2) { d2 = acc; }
     }
   }
-  if (active) rowres[task.row_off + row] = accept_rule(d1, d2, thr, ratio) ? match : kNone;
+  if (active) {
+    rowres[task.row_off + row] = accept_rule(d1, d2, thr, ratio) ? match : kNone;
+    if (rowdist) rowdist[task.row_off + row] = d1;  // FM_FLAG_DISTANCES: the reference's norm() of the emitted pair
+  }
 }
 
 inline size_t exact_smem_bytes(int d) { return ((size_t)kExactCols * d + 2 * kExactCols) * sizeof(float); }

@@ -118,6 +118,7 @@ struct FastBatchArgs {
   uint32_t segs;
   float thr, ratio;
   uint32_t* rowres;
+  float* rowdist;  // null unless FM_FLAG_DISTANCES
   DeviceCounters* counters;
 };
 
@@ -157,9 +158,9 @@ inline cudaError_t fast_match_batch(fm_ctx* c, const FastBatchArgs& a) {
     Span sp(&c->ev_match, c->stream, kPhRescore);
     rescore_kernel<<<a.blocks128, 128, 0, c->stream>>>(a.images, a.tasks, a.blk_off, a.n_tasks, a.segs,
                                                        c->d_cands.as<Cand>(), a.thr, a.ratio, a.rowres,
-                                                       c->d_redo.as<uint2>(), &a.counters->rescore);
+                                                       c->d_redo.as<uint2>(), &a.counters->rescore, a.rowdist);
     exact_rows_kernel<<<c->sm_count, kRedoThreads, 0, c->stream>>>(a.images, a.tasks, c->d_bands.as<uint2>(), c->d_redo.as<uint2>(),
-                                                             &a.counters->rescore, a.thr, a.ratio, a.rowres);
+                                                             &a.counters->rescore, a.thr, a.ratio, a.rowres, a.rowdist);
     fold_redo_kernel<<<1, 1, 0, c->stream>>>(a.counters);
   }
   c->stats.kernel_launches += 5;

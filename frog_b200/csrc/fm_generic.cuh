@@ -36,7 +36,7 @@ exact_generic_kernel(const ImageDev* __restrict__ images, const Task* __restrict
                      uint32_t require_flags, uint32_t* __restrict__ rowres, uint32_t* __restrict__ row_count,
                      uint32_t* __restrict__ row_final, const uint32_t* __restrict__ row_carry,
                      const unsigned long long* __restrict__ row_off, const unsigned long long* __restrict__ task_base,
-                     uint2* __restrict__ out) {
+                     uint2* __restrict__ out, float* __restrict__ rowdist) {
   __shared__ GenSmem sm;
   const uint32_t t = find_segment(task_blk_off, n_tasks, blockIdx.x);
   const Task task = tasks[t];
@@ -110,7 +110,10 @@ exact_generic_kernel(const ImageDev* __restrict__ images, const Task* __restrict
     }
   }
   if (!active) return;
-  if (kMode == 0) rowres[task.row_off + row] = accept_rule(d1, d2, thr, ratio) ? match : kNone;
+  if (kMode == 0) {
+    rowres[task.row_off + row] = accept_rule(d1, d2, thr, ratio) ? match : kNone;
+    if (rowdist) rowdist[task.row_off + row] = d1;
+  }
   if (kMode == 1) {
     row_count[task.row_off + row] = count;
     row_final[task.row_off + row] = d1 != FLT_MAX ? match : kNone;

@@ -128,11 +128,12 @@ struct fm_ctx {
   bool images_dirty = true;
   uint32_t dim = 0;
   // per-call scratch
-  fm::DevBuf d_meta_blob, d_rowres, d_chunk_count, d_chunk_out, d_totals;
+  fm::DevBuf d_meta_blob, d_rowres, d_rowdist, d_chunk_status, d_ticket, d_totals;
+  uint32_t compact_epoch = 0;  // tags the look-back status words of a compaction launch (fm_compact.cuh)
   fm::DevBuf d_bands, d_cands, d_redo, d_taskinfo;
   fm::DevBuf d_all, d_all_tasks;  // -all mode: per-row count / final / carry / offset, per-task totals and bases
   // free lists handed to results (several results may be in flight: FM_FLAG_ASYNC)
-  std::vector<fm::DevBuf> out_free, counts_free;
+  std::vector<fm::DevBuf> out_free, counts_free, dist_free;
   std::vector<std::pair<void*, size_t>> pin_free;  // pinned blocks: DeviceCounters + per-pair counts
   std::vector<fm::EventPool> ev_free;
   fm_result* last = nullptr;  // most recent result of fm_match (cleared when it is freed)
@@ -140,6 +141,7 @@ struct fm_ctx {
   size_t cache_pinned_cap = 0;
   unsigned long long* h_pinned = nullptr;  // 8 x u64 scratch for small D2H reads
   fm::EventPool ev_match, ev_prep;
+  float ms_prep_acc = 0.f;  // CUDA-event time of the preparation batches since the last fm_clear_images
   fm_stats stats{};
   bool score_attr_set = false;
   std::string err;

@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(128, 6)
 rescore_kernel(const ImageDev* __restrict__ images, const Task* __restrict__ tasks,
                const uint32_t* __restrict__ task_blk_off, uint32_t n_tasks, uint32_t segs,
                const Cand* __restrict__ cands, float thr, float ratio, uint32_t* __restrict__ rowres,
-               uint2* __restrict__ redo_list, RescoreCounters* __restrict__ counters) {
+               uint2* __restrict__ redo_list, RescoreCounters* __restrict__ counters, float* __restrict__ rowdist) {
   const uint32_t t = find_segment(task_blk_off, n_tasks, blockIdx.x);
   const Task task = tasks[t];
   if (task.flags & kTaskExact) return;
@@ -118,6 +118,7 @@ rescore_kernel(const ImageDev* __restrict__ images, const Task* __restrict__ tas
       top2_merge_one(dist, j, d1, d2, best);
     }
     if (accept_rule(d1, d2, thr, ratio)) match = best;
+    if (rowdist) rowdist[task.row_off + row] = d1;
   }
   rowres[task.row_off + row] = match;
   if (overflow) {
@@ -141,7 +142,7 @@ __global__ void __launch_bounds__(kRedoThreads)
 exact_rows_kernel(const ImageDev* __restrict__ images, const Task* __restrict__ tasks,
                   const uint2* __restrict__ bands, const uint2* __restrict__ redo_list,
                   const RescoreCounters* __restrict__ counters, float thr, float ratio,
-                  uint32_t* __restrict__ rowres) {
+                  uint32_t* __restrict__ rowres, float* __restrict__ rowdist) {
   __shared__ float s_d1[kRedoThreads / 32], s_d2[kRedoThreads / 32];
   __shared__ uint32_t s_m[kRedoThreads / 32];
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -182,6 +183,7 @@ exact_rows_kernel(const ImageDev* __restrict__ images, const Task* __restrict__ 
     if (threadIdx.x == 0) {
       for (int k = 1; k < kRedoThreads / 32; k++) top2_merge_sets(s_d1[k], s_d2[k], s_m[k], d1, d2, match);
       rowres[task.row_off + row] = accept_rule(d1, d2, thr, ratio) ? match : kNone;
+      if (rowdist) rowdist[task.row_off + row] = d1;
     }
     __syncthreads();
   }

@@ -1,9 +1,15 @@
 // fmio_capi.cpp -- C wrappers over the host-side readers / pruning / pairs.bin writer so the
 // CPU test-suite (and Python callers) can exercise exactly the code bin/match runs.
 #include <cerrno>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+
+#include <zlib.h>
+
+#include <string>
+#include <vector>
 
 #include "fast_inflate.h"
 #include "keypoint_io.h"
@@ -81,6 +87,95 @@ int fmio_write_pairs_bin(const char* path, int n_images, const char* const* file
     blocks[b].pairs = pairs + 2 * pair_offsets[b];
   }
   return fmio::write_pairs_bin(path, names, rg, images, blocks) ? 0 : 1;
+}
+
+// Synthetic-data writer for the tests and the bench (not used by bin/match): the .csv / .csv.gz text surf3d writes
+// (vtkOpenSURF3D/vtk3DSURF.cxx:451-484): "%f" per value, the laplacian sign as "%d", one keypoint per line.
+// head: n x 6 floats, desc: n x d floats.  gz_level < 0: plain text; else gzip at that level.  Returns 0 on success.
+// printf("%f", (double)v) without printf.  A float is k * 2^e with k < 2^24 and 10^6 = 2^6 * 5^6 (5^6 < 2^14), so
+// v * 1e6 is exact in double; rounding that to an integer with ties-to-even is what glibc's correctly rounded "%f"
+// prints.  Values the shortcut does not cover (>= 1e12, inf, nan) go through snprintf.
+static inline char* fmt_f6(char* o, float v) {
+  const double x = (double)v * 1e6;
+  const double ax = x < 0 ? -x : x;
+  if (!(ax < 1e18)) return o + snprintf(o, 64, "%f", (double)v);
+  if (std::signbit(v)) *o++ = '-';
+  unsigned long long q = (unsigned long long)std::nearbyint(ax);
+  unsigned long long ip = q / 1000000ull;
+  unsigned fp = (unsigned)(q % 1000000ull);
+  char tmp[24];
+  int k = 0;
+  do { tmp[k++] = (char)('0' + ip % 10); ip /= 10; } while (ip);
+  while (k) *o++ = tmp[--k];
+  *o++ = '.';
+  for (int i = 5; i >= 0; i--) { o[i] = (char)('0' + fp % 10); fp /= 10; }
+  return o + 6;
+}
+
+// Test hook: fmt_f6 against snprintf on n random floats of the magnitudes keypoint files hold; returns mismatches.
+int64_t fmio_fuzz_fmt(uint64_t seed, int64_t n) {
+  uint64_t s = seed * 0x9E3779B97F4A7C15ull + 7;
+  int64_t bad = 0;
+  char a[80], b[80];
+  for (int64_t i = 0; i < n; i++) {
+    s = s * 6364136223846793005ull + 1442695040888963407ull;
+    uint32_t bits = (uint32_t)(s >> 32);
+    float v;
+    if (i & 1) {  // any finite bit pattern
+      memcpy(&v, &bits, 4);
+      if (!std::isfinite(v)) v = 0.5f;
+    } else {  // typical magnitudes, many of them 6-decimal ties
+      const double scale[4] = {1.0, 10.0, 2000.0, 1e4};
+      v = (float)(((double)(bits >> 8) / 16777216.0 - 0.5) * 2 * scale[(s >> 20) & 3]);
+      if ((s >> 24) & 1) v = (float)(std::nearbyint((double)v * 2e6) / 2e6);
+    }
+    *fmt_f6(a, v) = 0;
+    snprintf(b, sizeof b, "%f", (double)v);
+    if (strcmp(a, b) != 0) bad++;
+  }
+  return bad;
+}
+
+int fmio_write_csv(const char* path, const float* head, const float* desc, int64_t n, uint32_t d, int gz_level) {
+  std::vector<char> text((size_t)n * ((size_t)d + 6) * 11 + 4096);  // typical cell: "-0.123456," ; grown when a row may not fit
+  const size_t row_max = ((size_t)d + 6) * 48 + 16;
+  char* o = text.data();
+  for (int64_t r = 0; r < n; r++) {
+    if ((size_t)(text.data() + text.size() - o) < row_max) {
+      const size_t used = (size_t)(o - text.data());
+      text.resize(text.size() + text.size() / 2 + row_max);
+      o = text.data() + used;
+    }
+    const float* h = head + r * 6;
+    for (int k = 0; k < 4; k++) { o = fmt_f6(o, h[k]); *o++ = ','; }
+    o += snprintf(o, 16, "%d", (int)h[4]);
+    *o++ = ',';
+    o = fmt_f6(o, h[5]);
+    const float* dd = desc + r * (int64_t)d;
+    for (uint32_t k = 0; k < d; k++) { *o++ = ','; o = fmt_f6(o, dd[k]); }
+    *o++ = '\n';
+  }
+  text.resize((size_t)(o - text.data()));
+  FILE* f = fopen(path, "wb");
+  if (!f) return 1;
+  bool ok = true;
+  if (gz_level < 0) {
+    ok = fwrite(text.data(), 1, text.size(), f) == text.size();
+  } else {
+    z_stream zs{};
+    if (deflateInit2(&zs, gz_level, Z_DEFLATED, 15 + 16, 8, Z_DEFAULT_STRATEGY) != Z_OK) { fclose(f); return 2; }
+    std::vector<unsigned char> out(deflateBound(&zs, (uLong)text.size()) + 64);
+    zs.next_in = reinterpret_cast<Bytef*>(const_cast<char*>(text.data()));
+    zs.avail_in = (uInt)text.size();
+    zs.next_out = out.data();
+    zs.avail_out = (uInt)out.size();
+    ok = deflate(&zs, Z_FINISH) == Z_STREAM_END;
+    const size_t got = out.size() - zs.avail_out;
+    deflateEnd(&zs);
+    ok = ok && fwrite(out.data(), 1, got, f) == got;
+  }
+  ok = (fclose(f) == 0) && ok;
+  return ok ? 0 : 3;
 }
 
 // Fuzz the libc-free decimal parser against strtof: `n` random cells in the formats surf3d and

@@ -176,38 +176,56 @@ bool read_csv(const std::string& path, KeypointSet& out, std::string& err) {
   return parse_csv_text(buf.data(), buf.size() - 1, out, err);
 }
 
+// Inflate every gzip member of `raw` (n bytes) into `text`.  boost::iostreams::gzip_decompressor -- what the reference
+// reads .csv.gz through, match.cpp:55-58 -- continues into the members that follow the first one, so concatenated
+// gzip files load as the concatenation of their texts.  *clean = false when the stream ended in an error (truncated
+// file, corrupt data, trailing bytes that are not a gzip member).
+static void inflate_members(const char* raw, size_t n, std::vector<char>& text, size_t& produced, bool& clean) {
+  produced = 0;
+  clean = true;
+  size_t pos = 0;
+  {
+    // one well-formed member spanning the file (what surf3d writes): the table-driven decoder; anything else: zlib
+    size_t got = 0;
+    if (n > 0 && fast_inflate_gzip(reinterpret_cast<const uint8_t*>(raw), n, text, &got)) { produced = got; return; }
+    text.resize(std::max<size_t>(n * 4, 1 << 16));
+  }
+  while (pos < n) {
+    z_stream zs{};
+    if (inflateInit2(&zs, 15 + 16) != Z_OK) { clean = false; return; }
+    zs.next_in = reinterpret_cast<Bytef*>(const_cast<char*>(raw + pos));
+    zs.avail_in = (uInt)std::min<size_t>(n - pos, 0xFFFFFFF0u);
+    const size_t in0 = zs.avail_in;
+    int rc = Z_OK;
+    while (rc != Z_STREAM_END) {
+      if (produced == text.size()) text.resize(text.size() * 2);
+      const size_t chunk = std::min<size_t>(text.size() - produced, 1u << 30);
+      zs.next_out = reinterpret_cast<Bytef*>(text.data() + produced);
+      zs.avail_out = (uInt)chunk;
+      rc = inflate(&zs, Z_NO_FLUSH);
+      produced += chunk - zs.avail_out;
+      if (rc != Z_OK && rc != Z_STREAM_END) break;                      // corrupt: keep what was inflated
+      if (rc == Z_OK && zs.avail_in == 0 && zs.avail_out != 0) break;   // truncated: keep what was inflated
+    }
+    pos += in0 - zs.avail_in;
+    inflateEnd(&zs);
+    if (rc != Z_STREAM_END) { clean = false; return; }
+  }
+}
+
 bool read_csv_gz(const std::string& path, KeypointSet& out, std::string& err) {
   std::vector<char> raw;
   if (!slurp(path, raw, err)) return false;
   std::vector<char> text;
-  {
-    // one well-formed gzip member (what surf3d writes): the table-driven decoder; anything else: zlib below
-    size_t got = 0;
-    if (raw.size() > 1 && fast_inflate_gzip(reinterpret_cast<const uint8_t*>(raw.data()), raw.size() - 1, text, &got)) {
-      text.resize(got + 1);
-      text[got] = 0;
-      return parse_csv_text(text.data(), got, out, err);
-    }
-  }
-  z_stream zs{};
-  if (inflateInit2(&zs, 15 + 32) != Z_OK) { err = "zlib init failed"; return false; }
-  zs.next_in = reinterpret_cast<Bytef*>(raw.data());
-  zs.avail_in = (uInt)(raw.size() - 1);
   size_t produced = 0;
-  text.resize(std::max<size_t>(raw.size() * 4, 1 << 16));
-  int rc = Z_OK;
-  while (rc != Z_STREAM_END) {
-    if (produced == text.size()) text.resize(text.size() * 2);
-    const size_t chunk = std::min<size_t>(text.size() - produced, 1u << 30);
-    zs.next_out = reinterpret_cast<Bytef*>(text.data() + produced);
-    zs.avail_out = (uInt)chunk;
-    rc = inflate(&zs, Z_NO_FLUSH);
-    produced += chunk - zs.avail_out;
-    if (rc != Z_OK && rc != Z_STREAM_END) break;  // truncated / corrupt: keep what was inflated
-    if (rc == Z_OK && zs.avail_in == 0 && zs.avail_out != 0) break;
+  bool clean = true;
+  inflate_members(raw.data(), raw.size() - 1, text, produced, clean);
+  if (!clean) {
+    // The reference's getline loop (match.cpp:61) ends when the decompressor throws inside the stream: the line being
+    // read at that moment -- the unterminated tail of what could be inflated -- is never processed.
+    while (produced > 0 && text[produced - 1] != '\n') produced--;
   }
-  inflateEnd(&zs);
-  text.resize(produced + 1);
+  if (text.size() < produced + 1) text.resize(produced + 1);
   text[produced] = 0;
   return parse_csv_text(text.data(), produced, out, err);
 }

@@ -29,6 +29,10 @@ def load():
         L.fmio_write_pairs_bin.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_char_p), C.c_void_p, C.c_void_p,
                                            C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                            C.c_void_p]
+        L.fmio_write_csv.restype = C.c_int
+        L.fmio_write_csv.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_uint32, C.c_int]
+        L.fmio_fuzz_fmt.restype = C.c_int64
+        L.fmio_fuzz_fmt.argtypes = [C.c_uint64, C.c_int64]
         _lib = L
     return _lib
 
@@ -80,3 +84,13 @@ def write_pairs_bin(path, filenames, rigids, heads, blocks) -> None:
                                 second.ctypes.data, counts.ctypes.data, poff.ctypes.data, pairs.ctypes.data)
     if rc != 0:
         raise IOError(f"write error : {path}")
+
+
+def write_csv(path: str, head, desc, gz_level: int = -1) -> None:
+    """surf3d's text format (vtk3DSURF.cxx:451-484), plain or gzipped; the GIL is released while the C code runs."""
+    L = load()
+    head = np.ascontiguousarray(head, np.float32)
+    desc = np.ascontiguousarray(desc, np.float32)
+    rc = L.fmio_write_csv(path.encode(), head.ctypes.data, desc.ctypes.data, head.shape[0], desc.shape[1], gz_level)
+    if rc != 0:
+        raise IOError(f"write error {rc}: {path}")

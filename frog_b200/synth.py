@@ -114,9 +114,18 @@ def make_bank(n: int, image: int, noise: float = 0.02, outliers: float = 0.10) -
     return Keypoints(_r6(xyz), _r6(scale), lap.astype(np.float32), _r6(response), _r6(desc))
 
 
+def make_dense(n: int, image: int) -> Keypoints:
+    """`dense` set (kernel study): iid descriptors, ONE laplacian class and ONE scale, so no column is gated out
+    (match.cpp:270-275 pass for every pair) and the scoring kernel executes every algorithmic pair."""
+    kp = make_iid(n, image)
+    return Keypoints(kp.xyz, np.full(n, 2.0, np.float32), np.zeros(n, np.float32), kp.response, kp.desc)
+
+
 def make(kind: str, n: int, image: int) -> Keypoints:
     if kind == "iid":
         return make_iid(n, image)
+    if kind == "dense":
+        return make_dense(n, image)
     if kind == "bank":
         return make_bank(n, image)
     raise ValueError(f"unknown synthetic set {kind!r}")
@@ -152,19 +161,40 @@ def write_csv_gz(kp: Keypoints, path: str) -> None:
 WRITERS = {"bin": write_bin, "csv": write_csv, "csv.gz": write_csv_gz}
 
 
+def _write_fast(kp: Keypoints, path: str, fmt: str) -> None:
+    """Same bytes (.bin) / same text (.csv, .csv.gz) as WRITERS, through libfmio's C writer."""
+    if fmt == "bin":
+        write_bin(kp, path)
+        return
+    from . import hostio
+    rec = kp.records()
+    hostio.write_csv(path, rec[:, :6], rec[:, 6:], gz_level=1 if fmt == "csv.gz" else -1)
+
+
 def write_group(dirpath: str, kind: str, n_images: int, n_points: int, fmt: str = "bin",
-                rigid: bool = False, first_image: int = 0) -> str:
+                rigid: bool = False, first_image: int = 0, threads: int = 1, keypoints=None) -> str:
     """Write `n_images` keypoint files plus the list file `bin/match` takes; returns the list path.
 
     List lines are absolute paths (as run.sh:86-88 writes them), optionally followed by a rigid
-    translation `,x,y,z` (match.cpp:478-490).
+    translation `,x,y,z` (match.cpp:478-490).  threads > 1 (or ready-made `keypoints`) writes through
+    libfmio's C text writer from a thread pool -- big groups for the bench.
     """
     os.makedirs(dirpath, exist_ok=True)
+    paths = [os.path.abspath(os.path.join(dirpath, f"points{i}.{fmt}")) for i in range(n_images)]
+    if threads > 1 or keypoints is not None:
+        from concurrent.futures import ThreadPoolExecutor
+
+        def one(i):
+            kp = keypoints[i] if keypoints is not None else make(kind, n_points, first_image + i)
+            _write_fast(kp, paths[i], fmt)
+
+        with ThreadPoolExecutor(max(1, threads)) as ex:
+            list(ex.map(one, range(n_images)))
+    else:
+        for i in range(n_images):
+            WRITERS[fmt](make(kind, n_points, first_image + i), paths[i])
     lines = []
-    for i in range(n_images):
-        kp = make(kind, n_points, first_image + i)
-        p = os.path.abspath(os.path.join(dirpath, f"points{i}.{fmt}"))
-        WRITERS[fmt](kp, p)
+    for i, p in enumerate(paths):
         if rigid:
             lines.append(f"{p},{0.5 * i:.3f},{-0.25 * i:.3f},{1.0 * i:.3f}")
         else:

@@ -44,6 +44,10 @@ typedef enum fm_status {
 #define FM_FLAG_MATCH_ALL 16u    /* the reference's -all mode, bug-compatible (match.cpp:295-300): every gated-in column under
                                  * `dist` emits a pair naming the running nearest column that was NOT under it; dist2second is
                                  * ignored; lists can hold up to N_first * N_second pairs.  Exact FP32 kernels only. */
+#define FM_FLAG_DISTANCES 32u    /* also keep, per emitted match, the squared distance d1 the decision was taken on -- the
+                                 * value the reference's norm() returns for that pair (match.cpp:243-251, :293).  pairs.bin
+                                 * carries no distances; this is the side output the parity checks compare.  Ignored with
+                                 * FM_FLAG_MATCH_ALL. */
 #define FM_FLAG_ASYNC 8u        /* return as soon as the work is queued on the context's stream; fm_result_wait()
                                  * completes the result.  Several results may be in flight on one context.  (Images
                                  * uploaded since the previous fm_match are prepared first, and the call waits for
@@ -55,6 +59,8 @@ typedef enum fm_status {
 int fm_device_count(int* n);
 /* Create a context on CUDA device `device`.  Replaces: process start-up of bin/match. */
 int fm_create(int device, fm_ctx** out);
+/* Destroy a context.  Every fm_result it produced must have been freed first (a result returns its buffers to its
+ * context in fm_result_free). */
 void fm_destroy(fm_ctx* ctx);
 /* Text of the most recent error on this context (or, with ctx == NULL, of the last failed
  * fm_create on this thread).  Never NULL. */
@@ -114,6 +120,9 @@ uint32_t fm_result_count(const fm_result* r, size_t p);
 /* Host pointer to pair p's matches: 2 * count uint32, (first, second) interleaved -- the bytes
  * match.cpp:738 writes.  NULL until fetched when FM_FLAG_DEVICE_ONLY was used. */
 const uint32_t* fm_result_pairs(const fm_result* r, size_t p);
+/* With FM_FLAG_DISTANCES: host pointer to pair p's `count` squared distances, in list order.  NULL otherwise, or
+ * until fetched. */
+const float* fm_result_distances(const fm_result* r, size_t p);
 /* Copy a device-only result to (pinned) host memory. */
 int fm_result_fetch(fm_result* r);
 /* Device views, for callers that gather match lists GPU-to-GPU (NCCL) before the host copy:

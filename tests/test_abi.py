@@ -104,4 +104,4 @@ def test_bench_reference_arm_contract(built, tmp_path):
     assert j["impl"] == "reference" and j["unit"] == "descriptor pairs/s" and j["higher_is_better"] is True
     assert j["value"] > 1e6 and j["cpu_baseline"]["kind"] == "reference" and j["cpu_baseline"]["cores"] >= 1
     assert j["e2e"] == {"value": j["value"], "unit": j["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-    assert j["config"]["workload"].startswith("c2:")
+    assert j["config"]["workload"].startswith("c4:") and j["scaling"] == "strong" and j["wall"]["seconds"] > 0

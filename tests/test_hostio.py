@@ -4,6 +4,7 @@ import gzip
 import os
 
 import numpy as np
+import pytest
 
 from frog_b200 import hostio, pairsbin, synth
 from oracle import oracle as O
@@ -190,9 +191,53 @@ def test_fast_inflate_declines_what_it_cannot_vouch_for(built, tmp_path):
         else:
             declined += 1
     assert declined >= len(bad) - 3
-    # two members: zlib (and this reader) stop after the first; trailing garbage: the first member is still read
-    for name, payload in (("two.csv.gz", good + good), ("junk.csv.gz", good + b"garbage")):
+    # Two members: like boost's gzip_decompressor (match.cpp:55-58) the reader continues into the second one.
+    # Trailing garbage / a truncated member: everything that could be inflated, minus an unterminated last line.
+    for name, payload, rows in (("two.csv.gz", good + good, 6000), ("junk.csv.gz", good + b"garbage", 3000)):
         p = tmp_path / name
         p.write_bytes(payload)
         head, desc = hostio.read_keypoints(str(p))
-        assert head.shape == (3000, 6) and desc.shape == (3000, 2) and head[7, 0] == 7.5
+        assert head.shape == (rows, 6) and desc.shape == (rows, 2) and head[7, 0] == 7.5
+        assert head[rows - 1, 0] == 2999.5
+    p = tmp_path / "cut.csv.gz"
+    p.write_bytes(good[:len(good) // 2])
+    head, desc = hostio.read_keypoints(str(p))
+    n = head.shape[0]
+    assert 0 < n < 3000 and np.array_equal(head[:, 0], np.arange(n) + 0.5) and desc.shape == (n, 2)
+
+
+def test_multi_member_gzip_matches_the_reference_build(built, tmp_path):
+    """A .csv.gz made of two concatenated members loads as the concatenation of both texts -- in this reader and in the
+    verbatim reference build (whose Boost stand-in, oracle/shim, continues into following members as Boost does)."""
+    import gzip
+    from frog_b200 import pairsbin, synth
+    from oracle import oracle as O
+    if not os.path.exists(O.REF_BIN):
+        pytest.skip("oracle/_ref/match_ref not built here")
+    a, b = synth.make("bank", 40, 0), synth.make("bank", 25, 1)
+    two = tmp_path / "two.csv.gz"
+    two.write_bytes(gzip.compress(synth._text_lines(a), 6) + gzip.compress(synth._text_lines(b), 1))
+    other = tmp_path / "other.csv.gz"
+    synth.write_csv_gz(synth.make("bank", 50, 2), str(other))
+    lst = tmp_path / "list.txt"
+    lst.write_text(f"{two}\n{other}\n")
+    head, desc = hostio.read_keypoints(str(two))
+    assert desc.shape == (65, 48) and np.array_equal(desc[40:], b.desc)
+    O.run_ref_binary([str(lst), "-o", str(tmp_path / "ref.bin"), "-d", "1"])
+    ref = pairsbin.parse(str(tmp_path / "ref.bin"))
+    assert ref.points[0].shape[0] == 65 and np.array_equal(ref.points[0], head)
+
+
+def test_text_writer_matches_printf(built, tmp_path):
+    """The bench's C text writer (fmio_write_csv) prints "%f" exactly as printf does; the files it writes hold the same
+    text as the Python writer's."""
+    import gzip
+    from frog_b200 import synth
+    assert hostio.load().fmio_fuzz_fmt(3, 2_000_000) == 0
+    kp = synth.make("iid", 300, 5)
+    synth.write_csv_gz(kp, str(tmp_path / "a.csv.gz"))
+    synth._write_fast(kp, str(tmp_path / "b.csv.gz"), "csv.gz")
+    assert gzip.open(tmp_path / "a.csv.gz").read() == gzip.open(tmp_path / "b.csv.gz").read()
+    synth.write_csv(kp, str(tmp_path / "a.csv"))
+    synth._write_fast(kp, str(tmp_path / "b.csv"), "csv")
+    assert (tmp_path / "a.csv").read_bytes() == (tmp_path / "b.csv").read_bytes()
