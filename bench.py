@@ -318,6 +318,9 @@ def bench_ours(args):
         dist.init_process_group("nccl", device_id=dev, pg_options=opts)
         host_group = dist.new_group(backend="gloo")  # CPU-side barrier: idle ranks must not spin a kernel on their GPU
     n_img, n_pts, kind, thr, ratio = WORKLOADS[args.workload]
+    for kv in args.debug_opt:
+        k, v = kv.split("=")
+        capi.debug_set_option(k, int(v))
 
     # ---- the synthetic group (the same on every rank), in pinned host memory -----------------------
     kps = [synth.make(kind, n_pts, i) for i in range(n_img)]
@@ -577,6 +580,8 @@ def bench_ours(args):
             "threshold_eps_count": None,
             "clocks": clocks,
         }
+        if args.debug_opt:
+            line["config"]["debug_opt"] = args.debug_opt
         if not args.no_wall:
             try:
                 line["wall"] = bin_match_wall(kps, kind, thr, ratio, world, ["bin"] + ([] if args.no_wall_gz else ["csv.gz"]))
@@ -607,6 +612,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-wall", action="store_true")
     ap.add_argument("--no-wall-gz", action="store_true")
+    ap.add_argument("--debug-opt", action="append", default=[], metavar="NAME=VALUE",
+                    help="kernel-study switch (include/frogmatch_debug.h), e.g. variant=1; not for reported numbers")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

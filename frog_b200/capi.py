@@ -28,7 +28,7 @@ PUBLIC_SYMBOLS = [
     "fm_result_count", "fm_result_pairs", "fm_result_distances", "fm_result_fetch", "fm_result_device_counts",
     "fm_result_device_pairs", "fm_result_free", "fm_get_stats", "fm_result_stats", "fm_version",
 ]
-DEBUG_SYMBOLS = ["fm_debug_image", "fm_debug_score_unit"]
+DEBUG_SYMBOLS = ["fm_debug_image", "fm_debug_score_unit", "fm_debug_set_option"]
 
 
 class Stats(C.Structure):
@@ -94,6 +94,7 @@ def load():
     L.fm_version.restype = C.c_char_p
     L.fm_debug_image.argtypes = [vp, C.c_uint32, u32p, u32p, f32p, u32p, f32p, vp, vp, vp, vp]
     L.fm_debug_score_unit.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32, vp, C.c_uint32, vp, vp, vp]
+    L.fm_debug_set_option.argtypes = [C.c_char_p, C.c_int]
     _lib = L
     return L
 
@@ -282,6 +283,12 @@ class Matcher:
         self._check(self._L.fm_debug_score_unit(self._h, first_img, second_img, row_block, _ptr(t), ld,
                                                 _ptr(bands), _ptr(ct), _ptr(cc)))
         return dict(t=t, bands=bands, cand_t=ct, cand_col=cc)
+
+
+def debug_set_option(name: str, value: int) -> None:
+    """Experiment switch of the scoring kernel (include/frogmatch_debug.h); not part of the boundary."""
+    if load().fm_debug_set_option(name.encode(), int(value)) != 0:
+        raise FrogMatchError(f"unknown debug option {name!r}")
 
 
 def version() -> str:

@@ -221,7 +221,7 @@ void fm_destroy(fm_ctx* c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   c->arena.release();
-  DevBuf* bufs[] = {&c->s_keys, &c->s_keys_sorted, &c->s_idx, &c->s_idx_sorted, &c->s_norm2, &c->s_sort, &c->s_segs, &c->d_images, &c->d_metas, &c->d_meta_blob, &c->d_rowres, &c->d_rowdist, &c->d_chunk_status, &c->d_ticket,
+  DevBuf* bufs[] = {&c->s_keys, &c->s_keys_sorted, &c->s_idx, &c->s_idx_sorted, &c->s_norm2, &c->s_sort, &c->s_segs, &c->d_images, &c->d_metas, &c->d_meta_blob, &c->d_rowres, &c->d_rowdist, &c->d_chunk_status,
                     &c->d_totals, &c->d_bands, &c->d_cands, &c->d_redo, &c->d_taskinfo, &c->d_all, &c->d_all_tasks};
   for (auto* b : bufs) b->release();
   for (auto& b : c->out_free) b.release();
@@ -382,16 +382,21 @@ int fm_match(fm_ctx* c, const uint32_t* pair_first, const uint32_t* pair_second,
   if (match_all && total_rows > 0xFFFFFFF0ull) return fail(c, FM_ERR_UNSUPPORTED, "fm_match: -all supports at most 2^32 outer-loop rows per call");
   const uint32_t kMaxBatchRows = match_all ? 0xFFFFFFF0u : (24u << 20);  // -all: one batch (its scan spans all rows)
   std::vector<Batch> batches;
-  std::vector<uint32_t> blk_off, chunk_off, unit_off;
+  std::vector<uint32_t> blk_off, unit_off;
+  std::vector<ChunkDesc> chunk_desc;  // compaction chunks of every batch, batch after batch (fm_compact.cuh)
+  std::vector<size_t> chunk_cursor;   // first chunk of each batch in chunk_desc
   for (uint32_t t = 0; t < n_tasks;) {
+    chunk_cursor.push_back(chunk_desc.size());
     Batch b{t, t, 0, 0, 0, 0, blk_off.size(), false, false};
     while (b.t1 < n_tasks) {
       const uint32_t nr = c->images[tasks[b.t1].row_img].n;
       if (b.t1 > b.t0 && (uint64_t)b.rows + nr > kMaxBatchRows) break;
       tasks[b.t1].row_off = b.rows;
       blk_off.push_back(b.blocks);
-      chunk_off.push_back(b.chunks);
       unit_off.push_back(b.units);
+      for (uint32_t r0 = 0; r0 < nr; r0 += kCompactChunk)
+        chunk_desc.push_back(ChunkDesc{b.rows + r0, std::min<uint32_t>(kCompactChunk, nr - r0) | ((tasks[b.t1].flags & kTaskSwap) ? 0x80000000u : 0u),
+                                       r0, pair_of_task[b.t1]});
       b.rows += nr;
       b.blocks += (nr + 127) / 128;
       b.chunks += (nr + kCompactChunk - 1) / kCompactChunk;
@@ -400,7 +405,6 @@ int fm_match(fm_ctx* c, const uint32_t* pair_first, const uint32_t* pair_second,
       b.t1++;
     }
     blk_off.push_back(b.blocks);
-    chunk_off.push_back(b.chunks);
     unit_off.push_back(b.units);
     batches.push_back(b);
     t = b.t1;
@@ -436,12 +440,11 @@ int fm_match(fm_ctx* c, const uint32_t* pair_first, const uint32_t* pair_second,
   c->stats.descriptor_pairs = desc_pairs;
   c->stats.rows = total_rows;
 
-  // metadata blob: tasks | pair_of_task | blk_off | chunk_off | unit_off
+  // metadata blob: tasks | chunk descriptors | blk_off | unit_off   (16-byte records first: alignment)
   const size_t np = blk_off.size();
-  const size_t off_pot = sizeof(Task) * n_tasks;
-  const size_t off_blk = off_pot + sizeof(uint32_t) * n_tasks;
-  const size_t off_chunk = off_blk + sizeof(uint32_t) * np;
-  const size_t off_unit = off_chunk + sizeof(uint32_t) * np;
+  const size_t off_chunk = sizeof(Task) * n_tasks;
+  const size_t off_blk = off_chunk + sizeof(ChunkDesc) * chunk_desc.size();
+  const size_t off_unit = off_blk + sizeof(uint32_t) * np;
   const size_t blob_bytes = off_unit + sizeof(uint32_t) * np;
   // The blob is staged in the result's pinned block (behind the counters and per-pair counts the device
   // writes back) so that the copy is asynchronous whatever its size: a pageable source would make
@@ -449,22 +452,18 @@ int fm_match(fm_ctx* c, const uint32_t* pair_first, const uint32_t* pair_second,
   const size_t off_blob = (sizeof(DeviceCounters) + std::max<size_t>(n_pairs, 1) * sizeof(uint32_t) + 15) & ~(size_t)15;
   FM_CUDA_R(take_pinned(c, off_blob + std::max<size_t>(blob_bytes, 16), &r->h_block, &r->h_block_cap));
   unsigned char* blob = static_cast<unsigned char*>(r->h_block) + off_blob;
-  if (n_tasks) {
-    memcpy(blob, tasks.data(), sizeof(Task) * n_tasks);
-    memcpy(blob + off_pot, pair_of_task.data(), sizeof(uint32_t) * n_tasks);
-  }
+  if (n_tasks) memcpy(blob, tasks.data(), sizeof(Task) * n_tasks);
+  if (!chunk_desc.empty()) memcpy(blob + off_chunk, chunk_desc.data(), sizeof(ChunkDesc) * chunk_desc.size());
   if (np) {
     memcpy(blob + off_blk, blk_off.data(), sizeof(uint32_t) * np);
-    memcpy(blob + off_chunk, chunk_off.data(), sizeof(uint32_t) * np);
     memcpy(blob + off_unit, unit_off.data(), sizeof(uint32_t) * np);
   }
   FM_CUDA_R(c->d_meta_blob.ensure(std::max<size_t>(blob_bytes, 16)));
   FM_CUDA_R(cudaMemcpyAsync(c->d_meta_blob.p, blob, std::max<size_t>(blob_bytes, 16), cudaMemcpyHostToDevice, c->stream));
   const unsigned char* blob_d = c->d_meta_blob.as<unsigned char>();
   const Task* d_tasks = reinterpret_cast<const Task*>(blob_d);
-  const uint32_t* d_pot = reinterpret_cast<const uint32_t*>(blob_d + off_pot);
+  const ChunkDesc* d_chunk = reinterpret_cast<const ChunkDesc*>(blob_d + off_chunk);
   const uint32_t* d_blk = reinterpret_cast<const uint32_t*>(blob_d + off_blk);
-  const uint32_t* d_chunk = reinterpret_cast<const uint32_t*>(blob_d + off_chunk);
   const uint32_t* d_unit = reinterpret_cast<const uint32_t*>(blob_d + off_unit);
 
   uint32_t max_rows = 1, max_chunks = 1;
@@ -479,9 +478,13 @@ int fm_match(fm_ctx* c, const uint32_t* pair_first, const uint32_t* pair_second,
     FM_CUDA_R(c->d_chunk_status.ensure((size_t)max_chunks * sizeof(unsigned long long) * 2));
     FM_CUDA_R(cudaMemsetAsync(c->d_chunk_status.p, 0, c->d_chunk_status.cap, c->stream));
   }
-  if (!c->d_ticket.p) {
-    FM_CUDA_R(c->d_ticket.ensure(256));
-    FM_CUDA_R(cudaMemsetAsync(c->d_ticket.p, 0, 256, c->stream));
+  if (!c->compact_grid) {
+    // persistent CTAs: never more than are resident at once (their look-back waits rely on it)
+    int per_sm = 0;
+    FM_CUDA_R(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, compact_kernel<false>, kCompactThreads, 0));
+    int per_sm_d = 0;
+    FM_CUDA_R(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_d, compact_kernel<true>, kCompactThreads, 0));
+    c->compact_grid = (uint32_t)std::max(1, std::min(per_sm, per_sm_d)) * (uint32_t)c->sm_count;
   }
   FM_CUDA_R(c->d_totals.ensure(sizeof(DeviceCounters)));
   FM_CUDA_R(r->d_out.ensure(std::max<uint64_t>(total_rows, 1) * sizeof(uint2)));
@@ -556,10 +559,10 @@ int fm_match(fm_ctx* c, const uint32_t* pair_first, const uint32_t* pair_second,
     FM_CUDA_R(cudaStreamSynchronize(c->stream));
   } else {
     Span total_span(&c->ev_match, c->stream, kPhTotal);
-    for (auto& b : batches) {
+    for (size_t bi = 0; bi < batches.size(); bi++) {
+      const Batch& b = batches[bi];
       const uint32_t nt = b.t1 - b.t0;
       const uint32_t* blk = d_blk + b.cursor;
-      const uint32_t* chk = d_chunk + b.cursor;
       const uint32_t* unt = d_unit + b.cursor;
       if (b.rows == 0) continue;
       if (b.any_fast) {
@@ -600,24 +603,20 @@ int fm_match(fm_ctx* c, const uint32_t* pair_first, const uint32_t* pair_second,
       {
         Span sp(&c->ev_match, c->stream, kPhCompact);
         CompactArgs ca{};
-        ca.images = d_images;
-        ca.tasks = d_tasks + b.t0;
-        ca.chunk_off = chk;
-        ca.n_tasks = nt;
+        ca.chunks = d_chunk + chunk_cursor[bi];
         ca.n_chunks = b.chunks;
-        ca.pair_of_task = d_pot + b.t0;
         ca.rowres = d_rowres;
         ca.rowdist = d_rowdist;
         ca.status = c->d_chunk_status.as<unsigned long long>();
-        ca.ticket = c->d_ticket.as<uint32_t>();
         c->compact_epoch = (c->compact_epoch % 0x3FFFFFFEu) + 1u;  // 1 .. 2^30 - 2: never the cleared value 0
         ca.epoch = c->compact_epoch;
         ca.pair_count = r->d_counts.as<uint32_t>();
         ca.running_total = &d_counters->running_total;
         ca.out_pairs = r->d_out.as<uint2>();
         ca.out_dist = want_dist ? r->d_dist.as<float>() : nullptr;
-        if (want_dist) compact_kernel<true><<<b.chunks, kCompactThreads, 0, c->stream>>>(ca);
-        else compact_kernel<false><<<b.chunks, kCompactThreads, 0, c->stream>>>(ca);
+        const uint32_t grid = std::min(b.chunks, c->compact_grid);
+        if (want_dist) compact_kernel<true><<<grid, kCompactThreads, 0, c->stream>>>(ca);
+        else compact_kernel<false><<<grid, kCompactThreads, 0, c->stream>>>(ca);
         c->stats.kernel_launches += 1;
       }
     }
@@ -745,6 +744,15 @@ int fm_result_stats(fm_result* r, fm_stats* out) {
 
 // ---- debug / test hooks (include/frogmatch_debug.h) ---------------------------------------------
 
+int fm_debug_set_option(const char* name, int value) {
+  if (!name) return FM_ERR_INVALID;
+  if (!strcmp(name, "probe")) g_debug.probe = value;
+  else if (!strcmp(name, "variant")) g_debug.variant = value;
+  else if (!strcmp(name, "pre_tiles")) g_debug.pre_tiles = value;
+  else return FM_ERR_INVALID;
+  return FM_OK;
+}
+
 int fm_debug_image(fm_ctx* c, uint32_t img, uint32_t* flags, uint32_t* n_classes, float* class_lap,
                    uint32_t* class_begin, float* max_norm2, uint32_t* perm, float* scale_sorted,
                    uint16_t* rowop, uint16_t* colop) {
@@ -799,10 +807,10 @@ int fm_debug_score_unit(fm_ctx* c, uint32_t first_img, uint32_t second_img, uint
   FM_CUDA(c, cudaMemcpyAsync(d_task.p, &task, sizeof task, cudaMemcpyHostToDevice, c->stream));
   FM_CUDA(c, cudaMemcpyAsync(d_meta.p, meta, sizeof meta, cudaMemcpyHostToDevice, c->stream));
   FM_CUDA(c, cudaMemsetAsync(d_dump.p, 0xFF, (size_t)kUnitRows * ld * sizeof(float), c->stream));  // NaN = "not written"
-  FM_CUDA(c, cudaFuncSetAttribute(score_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kScoreSmemBytes));
+  FM_CUDA(c, cudaFuncSetAttribute(score_kernel<true, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kScoreSmemBytes));
   bands_kernel<<<blocks, 128, 0, c->stream>>>(c->d_images.as<ImageDev>(), d_task.as<Task>(), d_meta.as<uint32_t>(), 1,
                                               c->d_bands.as<uint2>());
-  score_kernel<true><<<1, kScoreThreads, kScoreSmemBytes, c->stream>>>(
+  score_kernel<true, 0, 0><<<1, kScoreThreads, kScoreSmemBytes, c->stream>>>(
       c->d_images.as<ImageDev>(), d_task.as<Task>(), d_meta.as<uint32_t>() + 2, 1, 1, c->d_bands.as<uint2>(),
       c->d_cands.as<Cand>(), nullptr, d_dump.as<float>(), ld, row_block, 0);
   FM_CUDA(c, cudaGetLastError());

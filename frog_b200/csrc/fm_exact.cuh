@@ -38,6 +38,32 @@ __device__ __forceinline__ uint32_t find_segment(const uint32_t* __restrict__ of
   return lo;
 }
 
+// The same, starting from a guess: the segments a kernel walks are nearly uniform in size (images of a group hold about
+// the same number of keypoints), so proportional interpolation lands on or next to the answer and two or three loads
+// replace the ~log2(n) DEPENDENT global loads of the bisection (0.5 us each: 5 us of prologue for a 1000-task batch).
+// Galloping keeps the worst case logarithmic.  off[n] = total.
+__device__ __forceinline__ uint32_t find_segment_near(const uint32_t* __restrict__ off, uint32_t n, uint32_t b, uint32_t total) {
+  uint32_t g = (uint32_t)(((uint64_t)b * n) / (total ? total : 1u));
+  g = min(g, n - 1);
+  uint32_t lo, hi;  // invariant: off[lo] <= b < off[hi]
+  if (off[g] <= b) {
+    lo = g;
+    uint32_t step = 1;
+    hi = min(n, lo + step);
+    while (hi < n && off[hi] <= b) { lo = hi; step <<= 1; hi = min(n, lo + step); }
+  } else {
+    hi = g;
+    uint32_t step = 1;
+    lo = hi > step ? hi - step : 0u;
+    while (lo > 0 && off[lo] > b) { hi = lo; step <<= 1; lo = hi > step ? hi - step : 0u; }
+  }
+  while (hi - lo > 1) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (off[mid] <= b) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
 // D_T: descriptor length, known at compile time; the row's descriptor lives in registers.
 // require_flags: only tasks whose flags contain these bits are processed (0 = every task).
 template <int D_T>

@@ -1,7 +1,6 @@
 // fm_fast.cuh -- host-side driver of the tensor-core path: per-image preparation at upload and
 // the bands -> score -> rescore -> redo kernel sequence for one batch of tasks.
 #pragma once
-#include <cstdlib>
 
 #include "fm_host.h"
 #include "fm_prep.cuh"
@@ -106,6 +105,15 @@ inline cudaError_t fast_prepare_dirty(fm_ctx* c) {
   return cudaGetLastError();
 }
 
+// Experiment switches (fm_debug_set_option, frogmatch_debug.h).  Process-wide, explicit calls only: no environment
+// variable changes what the production kernel does.
+struct DebugOptions {
+  int probe = 0;       // 1 | 2: timing-attribution builds of score_kernel (results are garbage)
+  int variant = 0;     // experiment builds of score_kernel (results are exact)
+  int pre_tiles = -1;  // look-ahead depth override; -1 = kPreTiles
+};
+inline DebugOptions g_debug;
+
 struct FastBatchArgs {
   const ImageDev* images;
   const Task* tasks;        // device, this batch
@@ -134,10 +142,13 @@ inline cudaError_t fast_match_batch(fm_ctx* c, const FastBatchArgs& a) {
       if (e != cudaSuccess) return e;
       return cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     };
-    if ((e = prep(score_kernel<false, 0>)) != cudaSuccess) return e;
-    if ((e = prep(score_kernel<false, 1>)) != cudaSuccess) return e;
-    if ((e = prep(score_kernel<false, 2>)) != cudaSuccess) return e;
-    if ((e = prep(score_kernel<true, 0>)) != cudaSuccess) return e;
+    if ((e = prep(score_kernel<false, 0, 0>)) != cudaSuccess) return e;
+    if ((e = prep(score_kernel<false, 1, 0>)) != cudaSuccess) return e;
+    if ((e = prep(score_kernel<false, 2, 0>)) != cudaSuccess) return e;
+    if ((e = prep(score_kernel<false, 0, 1>)) != cudaSuccess) return e;
+    if ((e = prep(score_kernel<false, 0, 2>)) != cudaSuccess) return e;
+    if ((e = prep(score_kernel<false, 0, 3>)) != cudaSuccess) return e;
+    if ((e = prep(score_kernel<true, 0, 0>)) != cudaSuccess) return e;
     c->score_attr_set = true;
   }
   {
@@ -146,10 +157,13 @@ inline cudaError_t fast_match_batch(fm_ctx* c, const FastBatchArgs& a) {
   }
   {
     Span sp(&c->ev_match, c->stream, kPhScore);
-    // FM_PROBE=1|2 selects a timing-attribution variant of the kernel (wrong results, see fm_score.cuh)
-    static const int probe = getenv("FM_PROBE") ? atoi(getenv("FM_PROBE")) : 0;
-    static const uint32_t pre_tiles = getenv("FM_PRE") ? (uint32_t)atoi(getenv("FM_PRE")) : kPreTiles;
-    auto kern = probe == 1 ? score_kernel<false, 1> : probe == 2 ? score_kernel<false, 2> : score_kernel<false, 0>;
+    // fm_debug_set_option("probe" | "variant" | "pre_tiles") selects experiment builds of the kernel (frogmatch_debug.h);
+    // the defaults are the production kernel
+    const int probe = g_debug.probe, var = g_debug.variant;
+    const uint32_t pre_tiles = g_debug.pre_tiles >= 0 ? (uint32_t)g_debug.pre_tiles : kPreTiles;
+    auto kern = probe == 1 ? score_kernel<false, 1, 0> : probe == 2 ? score_kernel<false, 2, 0>
+              : var == 1 ? score_kernel<false, 0, 1> : var == 2 ? score_kernel<false, 0, 2>
+              : var == 3 ? score_kernel<false, 0, 3> : score_kernel<false, 0, 0>;
     kern<<<a.units, kScoreThreads, kScoreSmemBytes, c->stream>>>(
         a.images, a.tasks, a.unit_off, a.n_tasks, a.segs, c->d_bands.as<uint2>(), c->d_cands.as<Cand>(),
         &a.counters->scored_cols, nullptr, 0, 0, pre_tiles);

@@ -58,7 +58,7 @@ rescore_kernel(const ImageDev* __restrict__ images, const Task* __restrict__ tas
                const uint32_t* __restrict__ task_blk_off, uint32_t n_tasks, uint32_t segs,
                const Cand* __restrict__ cands, float thr, float ratio, uint32_t* __restrict__ rowres,
                uint2* __restrict__ redo_list, RescoreCounters* __restrict__ counters, float* __restrict__ rowdist) {
-  const uint32_t t = find_segment(task_blk_off, n_tasks, blockIdx.x);
+  const uint32_t t = find_segment_near(task_blk_off, n_tasks, blockIdx.x, gridDim.x);
   const Task task = tasks[t];
   if (task.flags & kTaskExact) return;
   const ImageDev A = images[task.col_img];

@@ -67,7 +67,7 @@ constexpr size_t kScoreSmemBytes = sizeof(ScoreSmem) + 1024;
 __global__ void __launch_bounds__(128)
 bands_kernel(const ImageDev* __restrict__ images, const Task* __restrict__ tasks,
              const uint32_t* __restrict__ task_blk_off, uint32_t n_tasks, uint2* __restrict__ bands) {
-  const uint32_t t = find_segment(task_blk_off, n_tasks, blockIdx.x);
+  const uint32_t t = find_segment_near(task_blk_off, n_tasks, blockIdx.x, gridDim.x);
   const Task task = tasks[t];
   if (task.flags & kTaskExact) return;
   const ImageDev A = images[task.col_img];
@@ -251,7 +251,7 @@ __device__ __forceinline__ void fold_second(const ChunkMax& c, float f15, float&
 // that only tracks the two largest chunk maxima (upd, !cap) and a capture visit against the threshold the
 // look-ahead established (!upd, cap: the chunk maxima must not be folded in a second time, g2 has to stay the
 // score of a column distinct from g1's).  Every other tile is visited once with both set.
-template <bool kMasked, int kProbe>
+template <bool kMasked, int kProbe, int kVar>
 __device__ __forceinline__ void score_pair(const uint32_t (&ra)[16], const uint32_t (&rb)[16], uint32_t col0, uint32_t lo,
                                            uint32_t width, RowScan& st, float two_eps, bool upd, bool cap) {
   constexpr uint32_t kAll = 0xffffffffu;
@@ -265,12 +265,15 @@ __device__ __forceinline__ void score_pair(const uint32_t (&ra)[16], const uint3
   const float hi = fmaxf(a.m, b.m), lw = fminf(a.m, b.m);
   // top two of {g1, g2, hi, lw} (g1 >= g2, hi >= lw)
   const float hi_u = upd ? hi : -INFINITY, lw_u = upd ? lw : -INFINITY;
+  // kVar & 2: test against the threshold of the PREVIOUS step (a lower threshold only captures more), so the
+  // compare -> vote -> branch chain does not wait for the g1/g2/thr update of this step
+  const float th_stale = st.thr;
   const float g2n = max3(st.g2, lw_u, fminf(st.g1, hi_u));
   st.g1 = fmaxf(st.g1, hi_u);
   st.g2 = g2n;
   if (kProbe != 1) st.thr = st.g2 - two_eps;
   float th = st.thr;
-  const bool hit = cap && hi > th;
+  const bool hit = cap && hi > ((kVar & 2) ? th_stale : th);
   if (__any_sync(kAll, hit)) {
     // Two rare situations share one vote: a row without a threshold yet, a row whose list is nearly full.
     if (__any_sync(kAll, hit && (st.g2 == -INFINITY || st.capw - st.cap > kFullAt))) {
@@ -331,7 +334,7 @@ __device__ __forceinline__ void score_pair(const uint32_t (&ra)[16], const uint3
 }
 
 // One 64-column accumulator tile of one row: two pairs of TMEM loads.
-template <bool kMasked, bool kDump, int kProbe>
+template <bool kMasked, bool kDump, int kProbe, int kVar>
 __device__ __forceinline__ void score_tile(uint32_t taddr, uint32_t cb, uint32_t lo, uint32_t width, RowScan& st,
                                            float two_eps, uint32_t bar_release, float* dump_row, bool upd, bool cap) {
   uint32_t ra[16], rb[16];
@@ -355,7 +358,7 @@ __device__ __forceinline__ void score_tile(uint32_t taddr, uint32_t cb, uint32_t
         dump_row[cb + (c + 1) * 16 + e] = __uint_as_float(rb[e]);
       }
     }
-    score_pair<kMasked, kProbe>(ra, rb, cb + c * 16, lo, width, st, two_eps, upd, cap);
+    score_pair<kMasked, kProbe, kVar>(ra, rb, cb + c * 16, lo, width, st, two_eps, upd, cap);
   }
 }
 
@@ -368,7 +371,9 @@ __device__ __forceinline__ void score_tile(uint32_t taddr, uint32_t cb, uint32_t
 // dump (kDump only): [256][dump_ld] raw t of the unit.
 // kProbe (performance attribution only, results are garbage): 1 = capture threshold pinned at +inf,
 // i.e. the max-tree fast path alone; 2 = epilogue skips the TMEM loads too (TMA + MMA pipeline alone).
-template <bool kDump, int kProbe = 0>
+// kVar (experiments): bit 0 = the two single-thread warps back off with nanosleep between barrier polls,
+// bit 1 = capture test against the previous step's threshold.
+template <bool kDump, int kProbe = 0, int kVar = 0>
 __global__ void __launch_bounds__(kScoreThreads, 2)
 score_kernel(const ImageDev* __restrict__ images, const Task* __restrict__ tasks,
              const uint32_t* __restrict__ unit_off, uint32_t n_tasks, uint32_t segs,
@@ -378,7 +383,7 @@ score_kernel(const ImageDev* __restrict__ images, const Task* __restrict__ tasks
   ScoreSmem& sm = *reinterpret_cast<ScoreSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
 
   const uint32_t unit = blockIdx.x + unit_base;  // unit_base != 0 only for single-unit debug launches
-  const uint32_t t = find_segment(unit_off, n_tasks, unit);
+  const uint32_t t = find_segment_near(unit_off, n_tasks, unit, kDump ? unit_off[n_tasks] : gridDim.x);
   const Task task = tasks[t];
   if (task.flags & kTaskExact) return;
   const ImageDev A = images[task.col_img];
@@ -461,7 +466,7 @@ score_kernel(const ImageDev* __restrict__ images, const Task* __restrict__ tasks
         for (uint32_t i = 0; i < n_sched; i++) {
           const uint32_t stg = i % kStages, use = i / kStages;
           const uint32_t tile = tile0 + (i < n_pre ? i : i - n_pre);
-          if (use > 0) ptx::mbar_wait(&sm.bar_bempty[stg], (use - 1) & 1);
+          if (use > 0) { if (kVar & 1) ptx::mbar_wait_sleep<400>(&sm.bar_bempty[stg], (use - 1) & 1); else ptx::mbar_wait(&sm.bar_bempty[stg], (use - 1) & 1); }
           ptx::mbar_expect_tx(&sm.bar_bfull[stg], kTileBytes);
           ptx::bulk_g2s(sm.b[stg], colop + (size_t)tile * kTileBytes, kTileBytes, &sm.bar_bfull[stg]);
         }
@@ -475,8 +480,13 @@ score_kernel(const ImageDev* __restrict__ images, const Task* __restrict__ tasks
         ptx::mbar_wait(&sm.bar_a, 0);
         for (uint32_t i = 0; i < n_sched; i++) {
           const uint32_t stg = i % kStages, acc = i & 1, use = i >> 1;
-          if (use > 0) ptx::mbar_wait(&sm.bar_accempty[acc][0], (use - 1) & 1);
-          ptx::mbar_wait(&sm.bar_bfull[stg], (i / kStages) & 1);
+          if (kVar & 1) {
+            if (use > 0) ptx::mbar_wait_sleep<100>(&sm.bar_accempty[acc][0], (use - 1) & 1);
+            ptx::mbar_wait_sleep<100>(&sm.bar_bfull[stg], (i / kStages) & 1);
+          } else {
+            if (use > 0) ptx::mbar_wait(&sm.bar_accempty[acc][0], (use - 1) & 1);
+            ptx::mbar_wait(&sm.bar_bfull[stg], (i / kStages) & 1);
+          }
           ptx::tc_fence_after();
           const uint64_t bdesc = ptx::umma_desc_sw128(ptx::smem_u32(sm.b[stg]));
 #pragma unroll
@@ -484,7 +494,8 @@ score_kernel(const ImageDev* __restrict__ images, const Task* __restrict__ tasks
             ptx::mma_f16_ss(tmem + acc * (2 * kTileCols), adesc0 + 2 * k, bdesc + 2 * k, idesc, k > 0);
           ptx::mma_commit(&sm.bar_accfull[acc][0]);
           if (use > 0) {
-            ptx::mbar_wait(&sm.bar_accempty[acc][1], (use - 1) & 1);
+            if (kVar & 1) ptx::mbar_wait_sleep<100>(&sm.bar_accempty[acc][1], (use - 1) & 1);
+            else ptx::mbar_wait(&sm.bar_accempty[acc][1], (use - 1) & 1);
             ptx::tc_fence_after();
           }
 #pragma unroll
@@ -522,10 +533,10 @@ score_kernel(const ImageDev* __restrict__ images, const Task* __restrict__ tasks
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive_u32(bar_full + 32 + acc * 16);
         } else if (!kDump && cb >= w_imin && cb + kTileCols <= w_imax) {
-          score_tile<false, kDump, kProbe>(taddr, cb, lo, width, st, two_eps, bar_full + 32 + acc * 16, dump_row, upd, cap);
+          score_tile<false, kDump, kProbe, kVar>(taddr, cb, lo, width, st, two_eps, bar_full + 32 + acc * 16, dump_row, upd, cap);
           scored += kTileCols;
         } else {
-          score_tile<true, kDump, kProbe>(taddr, cb, lo, width, st, two_eps, bar_full + 32 + acc * 16, dump_row, upd, cap);
+          score_tile<true, kDump, kProbe, kVar>(taddr, cb, lo, width, st, two_eps, bar_full + 32 + acc * 16, dump_row, upd, cap);
           scored += kTileCols;
         }
       }

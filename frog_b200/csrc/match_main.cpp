@@ -2,16 +2,36 @@
 //
 //   match <listfile-or-directory> [-o out] [-d dist] [-d2 ratio] [-n N] [-sp thr] [-np n] [-nt threads]
 //         [-zmin z] [-zmax z] [-sym] [-targ k] [-all x]   (reference keys, same meaning)
-//         [-gpus G] [-exact 1] [-stats file.json] [-gather nccl|host] [-plan 1]   (new keys; unknown to the reference)
+//         [-gpus G] [-exact 1] [-stats file.json] [-gather nccl|host] [-plan 1] [-mp 0|1] [-dists file]
+//                                                          (new keys; unknown to the reference)
 //
 // Same argv quirks (every key consumes two tokens except -sym, match.cpp:365-431), same keypoint
 // readers, same stdout protocol, byte-identical pairs.bin.  The pairing phase (match.cpp:638-652)
 // runs on B200s through the C ABI of libfrogmatch.so; there is no CPU fallback.
+//
+// Process model.  CUDA start-up is per process AND per visible device (cuInit: 0.6 s with one
+// device visible, 5 s with eight), so a one-shot executable that wants G GPUs runs ONE PROCESS PER
+// GPU: before the first CUDA call and before any thread exists, the parent forks G - 1 workers,
+// each of which sees exactly one device.  Parent and workers share one anonymous MAP_SHARED arena
+// created before the fork (inherited at the same address, released by the kernel when the
+// processes exit: nothing to clean up, nothing to leak):
+//   * the parent parses the keypoint files (OpenMP, as match.cpp:508-570 does) and drops every
+//     finished image's descriptors into the arena; every worker -- worker 0 is a thread of the
+//     parent -- uploads an image to its GPU as soon as it is marked ready, so host-to-device copies
+//     and CUDA start-up both hide under the parsing;
+//   * when all images are in, the parent shards the image pairs (longest processing time first)
+//     and publishes each worker's share; workers match, copy their compacted lists into the arena
+//     and leave with _exit; the parent writes pairs.bin in the reference's block order.
+// `-gather nccl` sends the lists GPU-to-GPU over NVLink to worker 0 instead (one communicator rank
+// per worker) -- identical bytes, but communicator start-up costs more than it saves a one-shot run.
 #include <omp.h>
+#include <sys/mman.h>
+#include <sys/wait.h>
 #include <unistd.h>
 
 #include <algorithm>
 #include <array>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -42,148 +62,249 @@ using std::string;
 
 namespace {
 
-struct GpuJob {
-  int device = 0;
-  std::vector<size_t> pair_ids;  // indices into the global pair list
-  fm_ctx* ctx = nullptr;
-  fm_result* res = nullptr;
-  fm_stats stats{};
-  string error;
-  double create_s = 0, upload_s = 0, match_s = 0;  // host wall-clock of the three phases of this job
-};
+constexpr int kMaxWorkers = 64;
 
 double now_s() {
   return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
-// CUDA start-up (driver initialisation + context + module load) takes of the order of a second per
-// process; it is started on background threads while the keypoint files are still being parsed.
-void create_context(GpuJob& job) {
-  const double t0 = now_s();
-  if (fm_create(job.device, &job.ctx) != FM_OK) job.error = fm_last_error(nullptr);
-  job.create_s = now_s() - t0;
+// ---- the shared arena ---------------------------------------------------------------------------------
+
+enum WorkerState : uint32_t { kStarting = 0, kContextUp = 1, kCountsOut = 2, kDone = 3, kFailed = 4 };
+
+struct WorkerSlot {
+  std::atomic<uint32_t> state;
+  char error[480];
+  char device[64];  // this worker's CUDA_VISIBLE_DEVICES entry (forked workers)
+  // plan, written by the parent before Control::plan_ready
+  uint64_t pairs_off;  // uint32 first[n_pairs] | uint32 second[n_pairs]
+  uint64_t n_pairs;
+  // result, written by the worker before state = kCountsOut (counts, total) / kDone (lists, distances)
+  uint64_t counts_off, lists_off, dists_off, total;
+  fm_stats stats;
+  double create_s, upload_s, match_s, gather_s, nccl_init_s;
+};
+
+struct ImageSlot {
+  std::atomic<uint32_t> ready;  // 1 once n, d and the three arrays are in place
+  uint32_t n, d;
+  uint64_t desc_off, scale_off, lap_off;
+};
+
+struct Control {
+  std::atomic<uint64_t> bump;  // next free byte of the arena
+  uint64_t arena_bytes;
+  std::atomic<uint32_t> abort;       // somebody failed: everybody leaves
+  std::atomic<uint32_t> plan_ready;  // pair shards published
+  std::atomic<uint32_t> nccl_id_ready;
+  uint32_t n_images, n_workers, dim;
+  float dist, ratio;
+  uint32_t flags;
+  uint32_t use_nccl;
+  unsigned char nccl_id[128];
+  WorkerSlot worker[kMaxWorkers];
+  // ImageSlot image[n_images] follows
+  ImageSlot* images() { return reinterpret_cast<ImageSlot*>(this + 1); }
+  char* base() { return reinterpret_cast<char*>(this); }
+  template <class T> T* at(uint64_t off) { return reinterpret_cast<T*>(base() + off); }
+  // 0 = the arena is exhausted
+  uint64_t alloc(uint64_t bytes) {
+    bytes = (bytes + 255) & ~(uint64_t)255;
+    const uint64_t off = bump.fetch_add(bytes);
+    return off + bytes <= arena_bytes ? off : 0;
+  }
+};
+
+Control* map_arena(size_t n_images, uint64_t estimate_bytes) {
+  const uint64_t head = sizeof(Control) + n_images * sizeof(ImageSlot);
+  // Virtual space is free (pages are committed when touched): reserve far more than any group needs; a kernel that
+  // refuses (strict overcommit) gets a request sized from the input files instead.
+  const uint64_t tries[2] = {(uint64_t)1 << 40, head + estimate_bytes + ((uint64_t)64 << 20)};
+  for (uint64_t bytes : tries) {
+    void* p = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_SHARED | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
+    if (p == MAP_FAILED) continue;
+    Control* c = new (p) Control();
+    c->arena_bytes = bytes;
+    c->bump.store((head + 4095) & ~(uint64_t)4095);
+    for (size_t i = 0; i < n_images; i++) new (c->images() + i) ImageSlot();
+    return c;
+  }
+  return nullptr;
 }
 
-void run_gpu_job(GpuJob& job, const std::vector<fmio::KeypointSet>& images, const std::vector<std::pair<int, int>>& indices,
-                 float dist, float ratio, uint32_t flags) {
-  if (!job.error.empty()) return;
-  if (!job.ctx) { create_context(job); if (!job.error.empty()) return; }
-  double t0 = now_s();
-  std::vector<char> needed(images.size(), 0);
-  for (size_t id : job.pair_ids) { needed[indices[id].first] = 1; needed[indices[id].second] = 1; }
-  std::vector<std::vector<float>> keep;  // scale / laplacian columns stay alive until the copies have finished
-  keep.reserve(2 * images.size());
-  for (size_t i = 0; i < images.size(); i++) {
-    if (!needed[i]) continue;
-    const fmio::KeypointSet& k = images[i];
-    keep.emplace_back(k.n);
-    keep.emplace_back(k.n);
-    std::vector<float>&scale = keep[keep.size() - 2], &lap = keep[keep.size() - 1];
-    for (uint32_t r = 0; r < k.n; r++) { scale[r] = k.row_head(r)[3]; lap[r] = k.row_head(r)[4]; }
-    const uint32_t d = k.d ? k.d : 48;
-    if (fm_upload_image(job.ctx, (uint32_t)i, k.desc.data(), scale.data(), lap.data(), k.n, d) != FM_OK) {
-      job.error = fm_last_error(job.ctx);
-      return;
-    }
+void worker_fail(Control* ctl, int g, const string& msg) {
+  WorkerSlot& w = ctl->worker[g];
+  snprintf(w.error, sizeof w.error, "%s", msg.c_str());
+  w.state.store(kFailed);
+  ctl->abort.store(1);
+}
+
+template <class Pred>
+bool wait_for(Control* ctl, Pred ready) {  // false = aborted
+  for (unsigned spins = 0; !ready(); spins++) {
+    if (ctl->abort.load()) return false;
+    if (spins < 64) std::this_thread::yield();
+    else usleep(100);
   }
-  if (fm_synchronize(job.ctx) != FM_OK) { job.error = fm_last_error(job.ctx); return; }
-  keep.clear();
-  job.upload_s = now_s() - t0;
-  t0 = now_s();
-  std::vector<uint32_t> pf(job.pair_ids.size()), ps(job.pair_ids.size());
-  for (size_t k = 0; k < job.pair_ids.size(); k++) {
-    pf[k] = (uint32_t)indices[job.pair_ids[k]].first;
-    ps[k] = (uint32_t)indices[job.pair_ids[k]].second;
-  }
-  if (fm_match(job.ctx, pf.data(), ps.data(), pf.size(), dist, ratio, flags, &job.res) != FM_OK) {
-    job.error = fm_last_error(job.ctx);
-    return;
-  }
-  fm_get_stats(job.ctx, &job.stats);
-  job.match_s = now_s() - t0;
+  return true;
 }
 
 #ifdef FM_WITH_NCCL
-// Multi-GPU result hand-off: every GPU leaves its compacted match lists in device
-// memory (FM_FLAG_DEVICE_ONLY); they travel GPU-to-GPU over NVLink to GPU 0 (one grouped
-// ncclSend/ncclRecv per peer) and reach the host in ONE device-to-host copy, mirroring the single
-// writer of match.cpp:660-745.  One process, one communicator per GPU (ncclCommInitAll), brought
-// up on a background thread while the keypoint files load.
-struct NcclGather {
-  std::vector<ncclComm_t> comms;
-  std::vector<cudaStream_t> streams;
-  std::vector<int> devices;
+struct NcclRank {
+  ncclComm_t comm = nullptr;
+  cudaStream_t stream = nullptr;
   string error;
-  uint32_t* d_stage = nullptr;  // on devices[0]: the peers' lists, concatenated
-  uint32_t* h_stage = nullptr;  // pinned
-  double init_s = 0, gather_s = 0;
-
-  void init(int n) {
+  double init_s = 0;
+  void init(Control* ctl, int g, int device) {
     const double t0 = now_s();
-    devices.resize(n);
-    std::iota(devices.begin(), devices.end(), 0);
-    comms.assign(n, nullptr);
-    ncclResult_t r = ncclCommInitAll(comms.data(), n, devices.data());
-    if (r != ncclSuccess) { error = string("ncclCommInitAll: ") + ncclGetErrorString(r); comms.clear(); return; }
-    streams.assign(n, nullptr);
-    for (int g = 0; g < n; g++) {
-      cudaError_t e = cudaSetDevice(g);
-      if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&streams[g], cudaStreamNonBlocking);
-      if (e != cudaSuccess) { error = string("NCCL gather stream: ") + cudaGetErrorString(e); return; }
+    ncclUniqueId id;
+    static_assert(sizeof(ncclUniqueId) <= sizeof(Control::nccl_id), "unique id does not fit");
+    if (g == 0) {
+      ncclResult_t r = ncclGetUniqueId(&id);
+      if (r != ncclSuccess) { error = string("ncclGetUniqueId: ") + ncclGetErrorString(r); return; }
+      memcpy(ctl->nccl_id, &id, sizeof id);
+      ctl->nccl_id_ready.store(1);
+    } else {
+      if (!wait_for(ctl, [&] { return ctl->nccl_id_ready.load() != 0; })) { error = "aborted"; return; }
+      memcpy(&id, ctl->nccl_id, sizeof id);
     }
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { error = string("NCCL gather stream: ") + cudaGetErrorString(e); return; }
+    ncclResult_t r = ncclCommInitRank(&comm, (int)ctl->n_workers, id, g);
+    if (r != ncclSuccess) { error = string("ncclCommInitRank: ") + ncclGetErrorString(r); comm = nullptr; return; }
     init_s = now_s() - t0;
-  }
-
-  // lists[g] / totals[g]: device pointer and match count of GPU g's result (g < n_used).  Returns, per
-  // peer g >= 1, the host pointer of its concatenated lists in `host_of` (host_of[0] stays null: GPU 0's
-  // own lists are fetched through the library).
-  bool gather(const std::vector<const uint32_t*>& lists, const std::vector<uint64_t>& totals, std::vector<const uint32_t*>& host_of) {
-    const double t0 = now_s();
-    const int n_used = (int)lists.size();
-    host_of.assign(n_used, nullptr);
-    uint64_t elems = 0;
-    std::vector<uint64_t> off(n_used, 0);
-    for (int g = 1; g < n_used; g++) { off[g] = elems; elems += 2 * totals[g]; }
-    if (elems == 0) return true;
-    auto cu = [&](cudaError_t e, const char* what) {
-      if (e != cudaSuccess) { error = string(what) + ": " + cudaGetErrorString(e); return false; }
-      return true;
-    };
-    auto nc = [&](ncclResult_t r, const char* what) {
-      if (r != ncclSuccess) { error = string(what) + ": " + ncclGetErrorString(r); return false; }
-      return true;
-    };
-    if (!cu(cudaSetDevice(devices[0]), "cudaSetDevice")) return false;
-    if (!cu(cudaMalloc(reinterpret_cast<void**>(&d_stage), elems * sizeof(uint32_t)), "cudaMalloc(gather stage)")) return false;
-    if (!cu(cudaMallocHost(reinterpret_cast<void**>(&h_stage), elems * sizeof(uint32_t)), "cudaMallocHost(gather stage)")) return false;
-    if (!nc(ncclGroupStart(), "ncclGroupStart")) return false;
-    for (int g = 1; g < n_used; g++) {
-      if (totals[g] == 0) continue;
-      if (!nc(ncclSend(lists[g], 2 * totals[g], ncclUint32, 0, comms[g], streams[g]), "ncclSend")) return false;
-      if (!nc(ncclRecv(d_stage + off[g], 2 * totals[g], ncclUint32, g, comms[0], streams[0]), "ncclRecv")) return false;
-    }
-    if (!nc(ncclGroupEnd(), "ncclGroupEnd")) return false;
-    if (!cu(cudaSetDevice(devices[0]), "cudaSetDevice")) return false;
-    if (!cu(cudaMemcpyAsync(h_stage, d_stage, elems * sizeof(uint32_t), cudaMemcpyDeviceToHost, streams[0]), "gather D2H")) return false;
-    for (int g = 0; g < n_used; g++) {
-      if (!cu(cudaSetDevice(devices[g]), "cudaSetDevice")) return false;
-      if (!cu(cudaStreamSynchronize(streams[g]), "gather synchronize")) return false;
-    }
-    for (int g = 1; g < n_used; g++) host_of[g] = h_stage + off[g];
-    gather_s = now_s() - t0;
-    return true;
-  }
-
-  ~NcclGather() {
-    if (d_stage) { cudaSetDevice(devices[0]); cudaFree(d_stage); }
-    if (h_stage) cudaFreeHost(h_stage);
-    for (size_t g = 0; g < streams.size(); g++)
-      if (streams[g]) { cudaSetDevice(devices[g]); cudaStreamDestroy(streams[g]); }
-    for (auto c : comms)
-      if (c) ncclCommDestroy(c);
   }
 };
 #endif
+
+// One worker = one GPU.  Runs as a thread of the parent (worker 0, and every worker with -mp 0) or as the main
+// thread of a forked process that sees a single device.
+void worker_run(Control* ctl, int g, int device) {
+  WorkerSlot& w = ctl->worker[g];
+  double t0 = now_s();
+  fm_ctx* ctx = nullptr;
+  if (fm_create(device, &ctx) != FM_OK) { worker_fail(ctl, g, fm_last_error(nullptr)); return; }
+  w.create_s = now_s() - t0;
+  w.state.store(kContextUp);
+#ifdef FM_WITH_NCCL
+  NcclRank nccl;
+  std::thread nccl_thread;
+  if (ctl->use_nccl) nccl_thread = std::thread([&] { nccl.init(ctl, g, device); });
+  struct Join { std::thread& t; ~Join() { if (t.joinable()) t.join(); } } join_nccl{nccl_thread};
+#endif
+
+  // ---- uploads, image by image as the parent finishes parsing them ----
+  double upload_busy = 0;
+  std::vector<uint32_t> empty;  // images without keypoints: uploaded last, with the group's descriptor length
+  for (uint32_t i = 0; i < ctl->n_images; i++) {
+    ImageSlot& im = ctl->images()[i];
+    if (!wait_for(ctl, [&] { return im.ready.load() != 0; })) return;
+    if (im.n == 0) { empty.push_back(i); continue; }
+    t0 = now_s();
+    if (fm_upload_image(ctx, i, ctl->at<float>(im.desc_off), ctl->at<float>(im.scale_off), ctl->at<float>(im.lap_off), im.n, im.d) != FM_OK) {
+      worker_fail(ctl, g, fm_last_error(ctx));
+      return;
+    }
+    upload_busy += now_s() - t0;
+  }
+  if (!wait_for(ctl, [&] { return ctl->plan_ready.load() != 0; })) return;
+  for (uint32_t i : empty) {
+    // match.cpp gives an image without keypoints zero matches whatever the others' descriptor length is
+    const float none = 0.f;
+    if (fm_upload_image(ctx, i, &none, &none, &none, 0, ctl->dim ? ctl->dim : 48u) != FM_OK) { worker_fail(ctl, g, fm_last_error(ctx)); return; }
+  }
+  t0 = now_s();
+  if (fm_synchronize(ctx) != FM_OK) { worker_fail(ctl, g, fm_last_error(ctx)); return; }
+  w.upload_s = upload_busy + (now_s() - t0);
+
+  // ---- this worker's image pairs ----
+  t0 = now_s();
+  const uint32_t* pf = ctl->at<uint32_t>(w.pairs_off);
+  const uint32_t* ps = pf + w.n_pairs;
+  bool via_nccl = false;
+#ifdef FM_WITH_NCCL
+  if (ctl->use_nccl) {
+    if (nccl_thread.joinable()) nccl_thread.join();
+    if (!nccl.error.empty()) { worker_fail(ctl, g, "NCCL gather unavailable: " + nccl.error); return; }
+    via_nccl = true;
+    w.nccl_init_s = nccl.init_s;
+  }
+#endif
+  fm_result* res = nullptr;
+  const uint32_t flags = ctl->flags | ((via_nccl && g > 0) ? FM_FLAG_DEVICE_ONLY : 0u);
+  if (fm_match(ctx, pf, ps, w.n_pairs, ctl->dist, ctl->ratio, flags, &res) != FM_OK) { worker_fail(ctl, g, fm_last_error(ctx)); return; }
+  fm_get_stats(ctx, &w.stats);
+  w.match_s = now_s() - t0;
+
+  // ---- hand the lists over ----
+  t0 = now_s();
+  w.total = fm_result_total(res);
+  w.counts_off = ctl->alloc(std::max<uint64_t>(w.n_pairs, 1) * sizeof(uint32_t));
+  const bool want_dist = ctl->flags & FM_FLAG_DISTANCES;
+  if (!via_nccl || g == 0) {
+    w.lists_off = ctl->alloc(std::max<uint64_t>(w.total, 1) * 2 * sizeof(uint32_t));
+    if (want_dist) w.dists_off = ctl->alloc(std::max<uint64_t>(w.total, 1) * sizeof(float));
+  }
+  if (!w.counts_off || ((!via_nccl || g == 0) && (!w.lists_off || (want_dist && !w.dists_off)))) {
+    worker_fail(ctl, g, "shared arena exhausted while publishing the match lists");
+    return;
+  }
+  uint32_t* counts = ctl->at<uint32_t>(w.counts_off);
+  for (uint64_t p = 0; p < w.n_pairs; p++) counts[p] = fm_result_count(res, p);
+  if ((!via_nccl || g == 0) && w.total) {
+    memcpy(ctl->at<uint32_t>(w.lists_off), fm_result_pairs(res, 0), w.total * 2 * sizeof(uint32_t));
+    if (want_dist) memcpy(ctl->at<float>(w.dists_off), fm_result_distances(res, 0), w.total * sizeof(float));
+  }
+  w.state.store(kCountsOut);
+#ifdef FM_WITH_NCCL
+  if (via_nccl) {
+    // Lists of workers 1.. travel GPU-to-GPU to worker 0 (ncclSend / ncclRecv over NVLink) and reach the host in ONE
+    // device-to-host copy there, mirroring the single writer of match.cpp:660-745.  (Distances stay a host-path
+    // feature: -dists with -gather nccl is refused in main.)
+    auto cu = [&](cudaError_t e, const char* what) {
+      if (e != cudaSuccess) { worker_fail(ctl, g, string(what) + ": " + cudaGetErrorString(e)); return false; }
+      return true;
+    };
+    auto nc = [&](ncclResult_t r, const char* what) {
+      if (r != ncclSuccess) { worker_fail(ctl, g, string(what) + ": " + ncclGetErrorString(r)); return false; }
+      return true;
+    };
+    if (g > 0) {
+      if (w.total) {
+        if (!nc(ncclSend(fm_result_device_pairs(res), 2 * w.total, ncclUint32, 0, nccl.comm, nccl.stream), "ncclSend")) return;
+        if (!cu(cudaStreamSynchronize(nccl.stream), "gather synchronize")) return;
+      }
+    } else {
+      uint64_t elems = 0;
+      std::vector<uint64_t> off(ctl->n_workers, 0);
+      for (uint32_t k = 1; k < ctl->n_workers; k++) {
+        if (!wait_for(ctl, [&] { return ctl->worker[k].state.load() >= kCountsOut; })) return;
+        off[k] = elems;
+        elems += 2 * ctl->worker[k].total;
+      }
+      if (elems) {
+        uint32_t* d_stage = nullptr;
+        const uint64_t stage_off = ctl->alloc(elems * sizeof(uint32_t));
+        if (!stage_off) { worker_fail(ctl, g, "shared arena exhausted (NCCL gather)"); return; }
+        if (!cu(cudaSetDevice(device), "cudaSetDevice")) return;
+        if (!cu(cudaMalloc(reinterpret_cast<void**>(&d_stage), elems * sizeof(uint32_t)), "cudaMalloc(gather stage)")) return;
+        if (!nc(ncclGroupStart(), "ncclGroupStart")) return;
+        for (uint32_t k = 1; k < ctl->n_workers; k++)
+          if (ctl->worker[k].total && !nc(ncclRecv(d_stage + off[k], 2 * ctl->worker[k].total, ncclUint32, (int)k, nccl.comm, nccl.stream), "ncclRecv")) return;
+        if (!nc(ncclGroupEnd(), "ncclGroupEnd")) return;
+        if (!cu(cudaMemcpyAsync(ctl->at<uint32_t>(stage_off), d_stage, elems * sizeof(uint32_t), cudaMemcpyDeviceToHost, nccl.stream), "gather D2H")) return;
+        if (!cu(cudaStreamSynchronize(nccl.stream), "gather synchronize")) return;
+        for (uint32_t k = 1; k < ctl->n_workers; k++) ctl->worker[k].lists_off = stage_off + off[k] * sizeof(uint32_t);
+      }
+    }
+  }
+#endif
+  w.gather_s = now_s() - t0;
+  w.state.store(kDone);
+  // The context, its device memory and (NCCL) communicator are not torn down: the process is about to leave, and
+  // destroying one CUDA context per GPU costs a one-shot run more than everything above.
+}
 
 }  // namespace
 
@@ -207,11 +328,12 @@ int main(int argc, char* argv[]) {
   int target = -1;
   int gpus = -1;
   const char* statsFile = nullptr;
-  bool planOnly = false;  // -plan 1: print the GPU plan (no CUDA call is made) and exit
+  const char* distsFile = nullptr;  // -dists f: squared distance of every emitted match (float32, block order of pairs.bin)
+  bool planOnly = false;            // -plan 1: print the GPU plan (no CUDA call is made) and exit
+  bool multiProcess = true;         // -mp 0: all GPUs from threads of this one process (pays cuInit for every visible device)
   // How the lists of GPUs 1.. reach the writer: "host" = every GPU copies its own lists over its own PCIe link,
-  // "nccl" = GPU-to-GPU over NVLink to GPU 0, then one device-to-host copy.  Bringing the communicators up
-  // (ncclCommInitAll, 1.5-2 s measured) costs a one-shot process more than matching a 50 x 50k group, so "host"
-  // is the default here; long-lived callers (bench.py under torchrun) gather over NCCL.
+  // "nccl" = GPU-to-GPU over NVLink to GPU 0, then one device-to-host copy.  Bringing the communicators up costs a
+  // one-shot process more than matching a 50 x 50k group, so "host" is the default here.
   const char* gatherMode = "host";
 
   // match.cpp:365-431: key = argv[k], value = argv[k+1]; advance by 2, by 1 for -sym.
@@ -234,8 +356,10 @@ int main(int argc, char* argv[]) {
       if (has("-gpus")) gpus = atoi(value);
       if (has("-exact")) forceExact = atoi(value) != 0;
       if (has("-stats")) statsFile = value;
+      if (has("-dists")) distsFile = value;
       if (has("-gather")) gatherMode = value;
       if (has("-plan")) planOnly = atoi(value) != 0;
+      if (has("-mp")) multiProcess = atoi(value) != 0;
     }
     if (has("-all")) matchAll = true;
     if (has("-p")) writePoints = true;
@@ -248,6 +372,11 @@ int main(int argc, char* argv[]) {
     return 1;
   }
   if (writePoints) cerr << "match: -p (debug CSV dump) is ignored by the B200 build" << endl;
+  const bool want_nccl = strcmp(gatherMode, "nccl") == 0;
+  if (distsFile && (matchAll || want_nccl)) {
+    cerr << "match: -dists is not available with -all or -gather nccl" << endl;
+    return 1;
+  }
 
   std::vector<std::array<double, 3>> rigids;
   std::vector<string> filenames;
@@ -285,17 +414,14 @@ int main(int argc, char* argv[]) {
     return 1;
   }
 
-  // ---- GPU bring-up, planned before the first CUDA call ---------------------------------------------
-  // CUDA start-up is per VISIBLE device (driver initialisation, then a context each): on an 8-GPU box it costs
-  // seconds, more than matching a 200 x 20k group on one GPU.  So the number of GPUs is chosen first -- -gpus G, or
-  // one GPU per ~4e12 descriptor pairs estimated from the keypoint file sizes -- the process restricts itself to
-  // those devices (a prefix of CUDA_VISIBLE_DEVICES when the caller set it; measured on an 8-GPU box: cuInit 5.2 s
-  // with 8 visible devices, 0.6 s with one), and everything CUDA happens on a background thread while the keypoint
-  // files load.  No CPU fallback: without a device the run fails below.
+  // ---- GPU plan, made before the first CUDA call ---------------------------------------------------------
+  // The number of GPUs follows the work: -gpus G, else one GPU per ~4e12 descriptor pairs estimated from the
+  // keypoint file sizes (a 200 x 20k group takes 0.6 s on one B200: a second GPU's start-up would cost more).
   const size_t n_load = std::min<size_t>(filenames.size(), (size_t)std::max(N, 0));
   const size_t planned_pairs = n_load < 2 ? 0 : (target >= 0 ? n_load - 1 : n_load * (n_load - 1) / 2);
+  double est_bytes = 0;  // upper estimate of the float data the arena will hold
   int G_want = gpus;
-  if (G_want <= 0) {
+  {
     double pts = 0, pts2 = 0;  // sum n_i, sum n_i^2 -> sum_{i<j} n_i n_j
     for (size_t i = 0; i < n_load; i++) {
       std::error_code ec;
@@ -305,108 +431,161 @@ int main(int argc, char* argv[]) {
       const bool gz = f.size() > 3 && f.compare(f.size() - 3, 3, ".gz") == 0;
       const bool bin = f.size() > 4 && f.compare(f.size() - 4, 4, ".bin") == 0;
       const double n_est = bytes / (bin ? 216.0 : gz ? 220.0 : 500.0);  // 54 floats; "%f" text; the same gzipped
+      est_bytes += bin ? bytes + 4096 : gz ? bytes * 24 : bytes * 2;    // text: >= 2 characters per value
       pts += n_est;
       pts2 += n_est * n_est;
     }
-    const double est_pairs = target >= 0 ? pts * pts / std::max<double>(n_load, 1) : (pts * pts - pts2) / 2;
-    G_want = (int)std::min(64.0, std::max(1.0, std::ceil(est_pairs / 4e12)));
+    if (G_want <= 0) {
+      const double est_pairs = target >= 0 ? pts * pts / std::max<double>(n_load, 1) : (pts * pts - pts2) / 2;
+      G_want = (int)std::min(64.0, std::max(1.0, std::ceil(est_pairs / 4e12)));
+    }
+    est_bytes += 16.0 * pts * std::max<double>(n_load, 1);  // match lists: <= 8 B per outer-loop row per image pair
   }
-  G_want = (int)std::max<size_t>(1, std::min<size_t>((size_t)G_want, std::max<size_t>(planned_pairs, 1)));
+  G_want = (int)std::max<size_t>(1, std::min<size_t>((size_t)std::min(G_want, kMaxWorkers), std::max<size_t>(planned_pairs, 1)));
   if (planOnly) {
     cout << "Planned GPUs : " << G_want << " (" << planned_pairs << " image pairs)" << endl;
     return 0;
   }
+  // device ids the workers may use: the caller's CUDA_VISIBLE_DEVICES list stays authoritative
+  std::vector<string> dev_ids;
   if (const char* vis_env = getenv("CUDA_VISIBLE_DEVICES")) {
-    // the caller's list stays authoritative: keep its first G_want entries
-    std::vector<string> ids;
     std::stringstream ss(vis_env);
     for (string tok; std::getline(ss, tok, ',');)
-      if (!tok.empty()) ids.push_back(tok);
-    if ((int)ids.size() > G_want) {
-      string vis;
-      for (int g = 0; g < G_want; g++) vis += (g ? "," : "") + ids[g];
-      setenv("CUDA_VISIBLE_DEVICES", vis.c_str(), 1);
-    }
+      if (!tok.empty()) dev_ids.push_back(tok);
   } else {
     int n_phys = 0;
-    for (std::error_code ec; n_phys < 64 && fs::exists("/dev/nvidia" + std::to_string(n_phys), ec);) n_phys++;
-    if (n_phys > G_want) {
-      string vis;
-      for (int g = 0; g < G_want; g++) vis += (g ? "," : "") + std::to_string(g);
-      setenv("CUDA_VISIBLE_DEVICES", vis.c_str(), 1);
+    for (std::error_code ec; n_phys < kMaxWorkers && fs::exists("/dev/nvidia" + std::to_string(n_phys), ec);) n_phys++;
+    for (int g = 0; g < n_phys; g++) dev_ids.push_back(std::to_string(g));
+  }
+  const bool have_ids = !dev_ids.empty();  // (no list and no device nodes: let CUDA report what it finds)
+  const int G = have_ids ? std::max(1, std::min<int>(G_want, (int)dev_ids.size())) : 1;
+  if (nt > 0) omp_set_num_threads(nt);
+  int nb = (int)n_load;
+  if (nb > 65535) { cerr << "match: more than 65535 images cannot be described by pairs.bin (u16 ids)" << endl; return 1; }
+
+  Control* ctl = map_arena((size_t)nb, (uint64_t)est_bytes);
+  if (!ctl) { cerr << "match: cannot map the shared arena" << endl; return 1; }
+  ctl->n_images = (uint32_t)nb;
+  ctl->n_workers = (uint32_t)G;
+  ctl->dist = dist;
+  ctl->ratio = dist2second;
+  ctl->flags = (symFlag ? FM_FLAG_SYM : 0u) | (forceExact ? FM_FLAG_FORCE_EXACT : 0u) |
+               (matchAll ? FM_FLAG_MATCH_ALL : 0u) |  // -all: match.cpp:295-300, bug-compatible (fm_all.cuh)
+               (distsFile ? FM_FLAG_DISTANCES : 0u);
+#ifdef FM_WITH_NCCL
+  ctl->use_nccl = (want_nccl && G > 1) ? 1u : 0u;
+#else
+  ctl->use_nccl = 0;
+  if (want_nccl) cerr << "match: built without NCCL; gathering the match lists through host memory" << endl;
+#endif
+
+  // ---- workers: forked BEFORE any thread or CUDA state exists in this process -------------------------------
+  cout << std::flush;
+  cerr << std::flush;
+  std::vector<pid_t> children;
+  const bool fork_workers = multiProcess && G > 1;
+  if (fork_workers) {
+    for (int g = 1; g < G; g++) {
+      snprintf(ctl->worker[g].device, sizeof ctl->worker[g].device, "%s", dev_ids[g].c_str());
+      pid_t pid = fork();
+      if (pid < 0) { cerr << "match: fork failed" << endl; ctl->abort.store(1); return 1; }
+      if (pid == 0) {
+        setenv("CUDA_VISIBLE_DEVICES", ctl->worker[g].device, 1);
+        worker_run(ctl, g, 0);
+        fflush(nullptr);
+        _exit(ctl->worker[g].state.load() == kDone ? 0 : 2);
+      }
+      children.push_back(pid);
     }
   }
-  int n_dev = 0, G_max = 0;
-  bool have_dev = false;
-  string dev_error;  // fm_last_error(NULL) is per thread: fetched on the thread that made the failing call
-  std::vector<GpuJob> jobs;
-#ifdef FM_WITH_NCCL
-  NcclGather gatherer;  // declared before the threads' joiners: destroyed after they have been joined
-#endif
-  std::thread nccl_thread;  // NCCL communicators: joined just before the gather (they come up under the matching too)
-  const bool want_nccl = strcmp(gatherMode, "nccl") == 0;
-  std::thread bringup([&]() {
-    have_dev = fm_device_count(&n_dev) == FM_OK && n_dev > 0;
-    if (!have_dev) dev_error = fm_last_error(nullptr);
-    G_max = have_dev ? std::max(1, std::min(G_want, n_dev)) : 0;
-    jobs.resize(G_max);
-    std::vector<std::thread> warmers;
-    for (int g = 0; g < G_max; g++) {
-      jobs[g].device = g;
-      warmers.emplace_back(create_context, std::ref(jobs[g]));
-    }
-#ifdef FM_WITH_NCCL
-    if (G_max > 1 && want_nccl) nccl_thread = std::thread([&gatherer, G_max]() { gatherer.init(G_max); });
-#endif
-    for (auto& t : warmers) t.join();
-  });
-  auto join_warmers = [&]() { if (bringup.joinable()) bringup.join(); };
-  struct Joiner {  // early `return`s below must not leave a joinable thread behind
-    std::thread &a, &b;
-    ~Joiner() { if (a.joinable()) a.join(); if (b.joinable()) b.join(); }
-  } joiner{bringup, nccl_thread};
-  (void)want_nccl;
+  if (have_ids) {
+    // this process: its own device only (forked workers), or the first G devices (threads)
+    string vis;
+    for (int g = 0; g < (fork_workers ? 1 : G); g++) vis += (g ? "," : "") + dev_ids[g];
+    setenv("CUDA_VISIBLE_DEVICES", vis.c_str(), 1);
+  }
+  std::vector<std::thread> local_workers;
+  for (int g = 0; g < (fork_workers ? 1 : G); g++) local_workers.emplace_back(worker_run, ctl, g, g);
+  // Every exit path below: tell the workers, reap them, and leave without tearing CUDA down.
+  auto leave = [&](int code) -> int {
+    if (code != 0) ctl->abort.store(1);
+    for (auto& t : local_workers)
+      if (t.joinable()) t.join();
+    for (pid_t pid : children) { int st = 0; waitpid(pid, &st, 0); }
+    cout << std::flush;
+    cerr << std::flush;
+    fflush(nullptr);
+    _exit(code);
+    return code;
+  };
+  auto report_failures = [&]() {
+    for (int g = 0; g < G; g++)
+      if (ctl->worker[g].state.load() == kFailed) cerr << "match: GPU " << g << ": " << ctl->worker[g].error << endl;
+  };
+
   cout << "Found " << filenames.size() << " files, loading : " << fmin(N, filenames.size()) << endl;
   start = std::chrono::system_clock::now();
   if (filenames.size() > (size_t)N) filenames.resize(N);
-  if (nt > 0) omp_set_num_threads(nt);
-  int nb = (int)filenames.size();
-  if (nb > 65535) { cerr << "match: more than 65535 images cannot be described by pairs.bin (u16 ids)" << endl; return 1; }
-  std::vector<fmio::KeypointSet> images(nb);
+  std::vector<fmio::KeypointSet> images(nb);  // header fields (pairs.bin records); descriptors move to the arena
   int load_failed = 0;
 
 #pragma omp parallel for schedule(dynamic)
-  for (int it = 0; it < nb; ++it) {  // match.cpp:508-570
+  for (int it = 0; it < nb; ++it) {  // match.cpp:508-570, with the per-image pruning of :579-609 done right away
     string err;
-    if (!fmio::read_keypoints(filenames[it], images[it], err)) {
+    fmio::KeypointSet& k = images[it];
+    if (ctl->abort.load()) continue;
+    if (!fmio::read_keypoints(filenames[it], k, err)) {
 #pragma omp critical
       { cerr << err << " (" << filenames[it] << ")" << endl; load_failed = 1; }
+      ctl->abort.store(1);
       continue;
     }
-    const uint32_t before = images[it].n;
     float zT = rigids.size() ? (float)rigids[it][2] : 0;
-    fmio::filter_z(images[it], zT, zmin, zmax);
+    fmio::filter_z(k, zT, zmin, zmax);
     std::array<double, 3> rg = rigids.size() ? rigids[it] : std::array<double, 3>{0, 0, 0};
 #pragma omp critical
-    cout << "image " << it << " rigid : " << rg[0] << ", " << rg[1] << ", " << rg[2] << " before : " << images[it].n
-         << " points, after : " << images[it].n << endl << std::flush;  // the reference prints the post-filter size twice
-    (void)before;
+    cout << "image " << it << " rigid : " << rg[0] << ", " << rg[1] << ", " << rg[2] << " before : " << k.n
+         << " points, after : " << k.n << endl << std::flush;  // the reference prints the post-filter size twice
+    fmio::prune(k, sp, np);  // an image's pruning depends on that image alone
+    ImageSlot& im = ctl->images()[it];
+    im.n = k.n;
+    im.d = k.d;
+    if (k.n) {
+      im.desc_off = ctl->alloc((uint64_t)k.n * k.d * sizeof(float));
+      im.scale_off = ctl->alloc((uint64_t)k.n * sizeof(float));
+      im.lap_off = ctl->alloc((uint64_t)k.n * sizeof(float));
+      if (!im.desc_off || !im.scale_off || !im.lap_off) {
+#pragma omp critical
+        { cerr << "match: shared arena exhausted while loading " << filenames[it] << endl; load_failed = 1; }
+        ctl->abort.store(1);
+        continue;
+      }
+      memcpy(ctl->at<float>(im.desc_off), k.desc.data(), (size_t)k.n * k.d * sizeof(float));
+      float* scale = ctl->at<float>(im.scale_off);
+      float* lap = ctl->at<float>(im.lap_off);
+      for (uint32_t r = 0; r < k.n; r++) { scale[r] = k.row_head(r)[3]; lap[r] = k.row_head(r)[4]; }
+      std::vector<float>().swap(k.desc);  // the writer needs the header fields only
+    }
+    im.ready.store(1);  // workers upload it from here on
   }
-  if (load_failed) return 1;
-  if (nb == 0) { cerr << "match: no keypoint files" << endl; return 1; }
+  if (load_failed) { report_failures(); return leave(1); }
+  if (ctl->abort.load()) {  // a worker gave up while the files were loading (typically: no CUDA device)
+    for (auto& t : local_workers)
+      if (t.joinable()) t.join();
+    report_failures();
+    bool no_device = false;
+    for (int g = 0; g < G; g++) no_device = no_device || strstr(ctl->worker[g].error, "no CUDA device");
+    if (no_device) cerr << "match: no CUDA device available; this build has no CPU path" << endl;
+    return leave(1);
+  }
+  if (nb == 0) { cerr << "match: no keypoint files" << endl; return leave(1); }
 
   end = std::chrono::system_clock::now();
   cout << " : " << std::chrono::duration<float>(end - start).count() << "s" << endl;
   start = end;
   cout << (images[0].n ? images[0].d : 0) << " values per descriptor" << endl;  // match.cpp:575
   cout << "Sorting and pruning..." << endl;
-
-#pragma omp parallel for schedule(dynamic)
-  for (int it = 0; it < nb; ++it) {  // match.cpp:579-609
-    fmio::prune(images[it], sp, np);
-#pragma omp critical
-    cout << ". (" << images[it].n << ")" << std::flush;
-  }
+  for (int it = 0; it < nb; ++it) cout << ". (" << images[it].n << ")" << std::flush;  // match.cpp:579-609 (done above)
   end = std::chrono::system_clock::now();
   cout << " : " << std::chrono::duration<float>(end - start).count() << "s" << endl;
   start = end;
@@ -415,8 +594,9 @@ int main(int argc, char* argv[]) {
   for (auto& k : images)
     if (k.n) {
       if (dim == 0) dim = k.d;
-      if (k.d != dim) { cerr << "match: images disagree on the descriptor length" << endl; return 1; }
+      if (k.d != dim) { cerr << "match: images disagree on the descriptor length" << endl; return leave(1); }
     }
+  ctl->dim = dim;
 
   // match.cpp:617-628
   std::vector<std::pair<int, int>> indices;
@@ -427,19 +607,10 @@ int main(int argc, char* argv[]) {
       for (int j = i + 1; j < nb; j++) indices.push_back(std::make_pair(i, j));
     }
   }
-  if (target >= nb) { cerr << "match: -targ " << target << " is not a valid image index" << endl; return 1; }
+  if (target >= nb) { cerr << "match: -targ " << target << " is not a valid image index" << endl; return leave(1); }
 
   cout << "Pairing... " << endl;
-  join_warmers();
-  if (!have_dev) {
-    cerr << "match: no CUDA device available (" << dev_error << "); this build has no CPU path" << endl;
-    return 1;
-  }
-  const int G = std::max(1, std::min<int>(G_max, std::max<size_t>(indices.size(), 1)));
-  for (int g = G; g < G_max; g++) {  // more GPUs than image pairs: release the surplus contexts
-    if (jobs[g].ctx) fm_destroy(jobs[g].ctx);
-  }
-  jobs.resize(G);
+  std::vector<std::vector<size_t>> shard(G);
   {
     // longest-processing-time-first sharding of image pairs (independent units, match.cpp:638-652)
     std::vector<size_t> order(indices.size());
@@ -449,59 +620,74 @@ int main(int argc, char* argv[]) {
     std::vector<double> load(G, 0.0);
     for (size_t id : order) {
       int g = (int)(std::min_element(load.begin(), load.end()) - load.begin());
-      jobs[g].pair_ids.push_back(id);
+      shard[g].push_back(id);
       load[g] += weight(id);
     }
     for (int g = 0; g < G; g++) {
-      jobs[g].device = g;
-      std::sort(jobs[g].pair_ids.begin(), jobs[g].pair_ids.end());  // consecutive pairs share the first image
+      std::sort(shard[g].begin(), shard[g].end());  // consecutive pairs share the first image
+      WorkerSlot& w = ctl->worker[g];
+      w.n_pairs = shard[g].size();
+      w.pairs_off = ctl->alloc(std::max<uint64_t>(w.n_pairs, 1) * 2 * sizeof(uint32_t));
+      if (!w.pairs_off) { cerr << "match: shared arena exhausted" << endl; return leave(1); }
+      uint32_t* pf = ctl->at<uint32_t>(w.pairs_off);
+      for (size_t k = 0; k < shard[g].size(); k++) {
+        pf[k] = (uint32_t)indices[shard[g][k]].first;
+        pf[w.n_pairs + k] = (uint32_t)indices[shard[g][k]].second;
+      }
     }
   }
-  // (a failed NCCL start-up is reported when the thread is joined; the lists of GPUs 1.. are then fetched per GPU)
-  const bool use_nccl = nccl_thread.joinable() && G > 1;
-  const uint32_t flags = (symFlag ? FM_FLAG_SYM : 0u) | (forceExact ? FM_FLAG_FORCE_EXACT : 0u) |
-                         (matchAll ? FM_FLAG_MATCH_ALL : 0u);  // -all: match.cpp:295-300, bug-compatible (fm_all.cuh)
-  {
-    std::vector<std::thread> threads;
-    for (int g = 1; g < G; g++)
-      threads.emplace_back(run_gpu_job, std::ref(jobs[g]), std::cref(images), std::cref(indices), dist, dist2second,
-                           flags | (use_nccl ? FM_FLAG_DEVICE_ONLY : 0u));
-    run_gpu_job(jobs[0], images, indices, dist, dist2second, flags);
-    for (auto& t : threads) t.join();
-  }
-  for (auto& j : jobs)
-    if (!j.error.empty()) { cerr << "match: GPU " << j.device << ": " << j.error << endl; return 1; }
+  ctl->plan_ready.store(1);
 
-  // gather: per pair, where its list lives
-  bool nccl_ok = true;
-  std::vector<const uint32_t*> host_of(G, nullptr);  // NCCL gather: host copy of GPU g's concatenated lists (g >= 1)
-#ifdef FM_WITH_NCCL
-  if (nccl_thread.joinable()) nccl_thread.join();
-  if (use_nccl && (!gatherer.error.empty() || (int)gatherer.comms.size() < G)) {
-    cerr << "match: NCCL gather unavailable (" << gatherer.error << "); fetching the match lists per GPU" << endl;
-    for (int g = 1; g < G; g++)
-      if (fm_result_fetch(jobs[g].res) != FM_OK) { cerr << "match: GPU " << g << ": " << fm_last_error(jobs[g].ctx) << endl; return 1; }
-    nccl_ok = false;
+  // ---- wait for the workers (a forked worker that dies without a word is noticed through waitpid) ----
+  {
+    std::vector<char> reaped(children.size(), 0);
+    for (;;) {
+      bool all = true;
+      for (int g = 0; g < G; g++) all = all && ctl->worker[g].state.load() == kDone;
+      if (all) break;
+      if (ctl->abort.load()) break;
+      for (size_t c = 0; c < children.size(); c++) {
+        if (reaped[c]) continue;
+        int st = 0;
+        if (waitpid(children[c], &st, WNOHANG) == children[c]) {
+          reaped[c] = 1;
+          const bool ok = WIFEXITED(st) && WEXITSTATUS(st) == 0;
+          if (!ok && ctl->worker[c + 1].state.load() != kFailed)
+            worker_fail(ctl, (int)c + 1, WIFSIGNALED(st) ? "worker process killed by signal " + std::to_string(WTERMSIG(st))
+                                                         : "worker process exited with status " + std::to_string(WEXITSTATUS(st)));
+        }
+      }
+      usleep(200);
+    }
+    if (ctl->abort.load()) {
+      for (auto& t : local_workers)
+        if (t.joinable()) t.join();
+      report_failures();
+      bool no_device = false;
+      for (int g = 0; g < G; g++) no_device = no_device || strstr(ctl->worker[g].error, "no CUDA device");
+      if (no_device) cerr << "match: no CUDA device available; this build has no CPU path" << endl;
+      return leave(1);
+    }
   }
-  if (use_nccl && nccl_ok) {
-    std::vector<const uint32_t*> lists(G);
-    std::vector<uint64_t> totals(G);
-    for (int g = 0; g < G; g++) { lists[g] = fm_result_device_pairs(jobs[g].res); totals[g] = fm_result_total(jobs[g].res); }
-    if (!gatherer.gather(lists, totals, host_of)) { cerr << "match: " << gatherer.error << endl; return 1; }
-  }
-#endif
+
+  // ---- per pair, where its list lives ----
   std::vector<fmio::PairBlock> by_pair(indices.size());
+  std::vector<const float*> dist_of(indices.size(), nullptr);
   long long sum = 0;
   for (int g = 0; g < G; g++) {
-    GpuJob& j = jobs[g];
+    WorkerSlot& w = ctl->worker[g];
+    const uint32_t* counts = ctl->at<uint32_t>(w.counts_off);
+    const uint32_t* lists = w.lists_off ? ctl->at<uint32_t>(w.lists_off) : nullptr;
+    const float* dists = w.dists_off ? ctl->at<float>(w.dists_off) : nullptr;
     uint64_t off = 0;
-    for (size_t k = 0; k < j.pair_ids.size(); k++) {
-      const size_t id = j.pair_ids[k];
+    for (size_t k = 0; k < shard[g].size(); k++) {
+      const size_t id = shard[g][k];
       fmio::PairBlock b;
       b.first = indices[id].first;
       b.second = indices[id].second;
-      b.count = fm_result_count(j.res, k);
-      b.pairs = (use_nccl && nccl_ok && g > 0) ? host_of[g] + 2 * off : fm_result_pairs(j.res, k);
+      b.count = counts[k];
+      b.pairs = lists ? lists + 2 * off : nullptr;
+      if (dists) dist_of[id] = dists + off;
       off += b.count;
       by_pair[id] = b;
       sum += b.count;
@@ -530,18 +716,30 @@ int main(int argc, char* argv[]) {
 
   if (!fmio::write_pairs_bin(outfilename.str(), filenames, rigids, images, blocks)) {
     cout << "write error : " << outfilename.str() << endl;  // match.cpp:677-682
-    exit(1);
+    return leave(1);
   }
   cout << "Output file : " << outfilename.str() << endl;
+  if (distsFile) {
+    // side output for the parity checks (pairs.bin has no distances): per block, in pairs.bin's block order, `count`
+    // float32 squared distances -- what the reference's norm() returns for each emitted pair (match.cpp:293)
+    FILE* f = fopen(distsFile, "wb");
+    if (!f) { cerr << "match: cannot write " << distsFile << endl; return leave(1); }
+    for (size_t id : order)
+      if (by_pair[id].count) fwrite(dist_of[id], sizeof(float), by_pair[id].count, f);
+    fclose(f);
+  }
 
   if (statsFile) {
     fm_stats tot{};
     float ms_max = 0;
-    double create_s = 0, upload_s = 0, match_s = 0;
-    for (auto& j : jobs) {
+    double create_s = 0, upload_s = 0, match_s = 0, gather_s = 0, nccl_init_s = 0;
+    for (int g = 0; g < G; g++) {
+      const WorkerSlot& j = ctl->worker[g];
       create_s = std::max(create_s, j.create_s);
       upload_s = std::max(upload_s, j.upload_s);
       match_s = std::max(match_s, j.match_s);
+      gather_s = std::max(gather_s, j.gather_s);
+      nccl_init_s = std::max(nccl_init_s, j.nccl_init_s);
       tot.descriptor_pairs += j.stats.descriptor_pairs;
       tot.scored_pairs += j.stats.scored_pairs;
       tot.rows += j.stats.rows;
@@ -551,21 +749,15 @@ int main(int argc, char* argv[]) {
       ms_max = std::max(ms_max, j.stats.ms_total);
     }
     std::ofstream sf(statsFile);
-    sf << "{\"gpus\": " << G << ", \"image_pairs\": " << indices.size() << ", \"descriptor_pairs\": " << tot.descriptor_pairs
-       << ", \"scored_pairs\": " << tot.scored_pairs << ", \"rows\": " << tot.rows << ", \"rows_exact\": " << tot.rows_exact
-       << ", \"candidates\": " << tot.candidates << ", \"kernel_launches\": " << tot.kernel_launches
+    sf << "{\"gpus\": " << G << ", \"processes\": " << (fork_workers ? G : 1) << ", \"image_pairs\": " << indices.size()
+       << ", \"descriptor_pairs\": " << tot.descriptor_pairs << ", \"scored_pairs\": " << tot.scored_pairs << ", \"rows\": " << tot.rows
+       << ", \"rows_exact\": " << tot.rows_exact << ", \"candidates\": " << tot.candidates << ", \"kernel_launches\": " << tot.kernel_launches
        << ", \"gpu_ms_max\": " << ms_max << ", \"pairing_s\": " << pairing_s << ", \"ctx_create_s\": " << create_s
-       << ", \"upload_s\": " << upload_s << ", \"match_call_s\": " << match_s << ", \"matches\": " << sum
-       << ", \"gather\": \"" << (use_nccl && nccl_ok ? "nccl" : (G > 1 ? "host" : "none")) << "\""
-#ifdef FM_WITH_NCCL
-       << ", \"nccl_init_s\": " << gatherer.init_s << ", \"nccl_gather_s\": " << gatherer.gather_s
-#endif
-       << "}" << endl;
+       << ", \"upload_s\": " << upload_s << ", \"match_call_s\": " << match_s << ", \"gather_s\": " << gather_s
+       << ", \"matches\": " << sum
+       << ", \"gather\": \"" << (ctl->use_nccl ? "nccl" : (G > 1 ? "host" : "none")) << "\""
+       << ", \"nccl_init_s\": " << nccl_init_s << "}" << endl;
   }
-  // pairs.bin and the stats file are closed.  Tearing down one CUDA context per GPU (and NCCL) costs a one-shot
-  // process up to seconds and frees nothing the operating system does not reclaim anyway: leave at once.
-  cout << std::flush;
-  cerr << std::flush;
-  fflush(nullptr);
-  _exit(0);
+  // pairs.bin and the side files are closed: leave at once (see worker_run on teardown).
+  return leave(0);
 }

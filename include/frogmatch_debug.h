@@ -34,6 +34,15 @@ int fm_debug_image(fm_ctx* ctx, uint32_t img, uint32_t* flags, uint32_t* n_class
 int fm_debug_score_unit(fm_ctx* ctx, uint32_t first_img, uint32_t second_img, uint32_t row_block, float* t_out,
                         uint32_t ld, uint32_t* bands_out, float* cand_t, uint32_t* cand_col);
 
+/*
+ * Experiment switches for kernel studies (process-wide; the defaults are the production configuration):
+ *   "probe"     1 | 2   timing-attribution builds of the scoring kernel -- results are GARBAGE
+ *   "variant"   n       experiment builds of the scoring kernel -- results stay exact
+ *   "pre_tiles" n       look-ahead depth of the scoring kernel (-1 = built-in default)
+ * Returns FM_ERR_INVALID for an unknown name.  Nothing reads environment variables.
+ */
+int fm_debug_set_option(const char* name, int value);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,4 +1,6 @@
 """GPU: libfrogmatch (through the C ABI) against the oracle on seeded inputs -- bit-exact."""
+import os
+
 import numpy as np
 import pytest
 
@@ -259,3 +261,35 @@ def test_match_all_generic_descriptor_length(env):
     for g, w in zip(res.all_pairs(), want):
         assert np.array_equal(g, w)
     res.free()
+
+
+@pytest.mark.parametrize("force_exact", [False, True])
+def test_distances_side_output(env, force_exact):
+    """FM_FLAG_DISTANCES: the squared distance kept for every emitted match is the value the reference's own norm()
+    (match.cpp:243-251) returns for that pair -- tolerance 0 ulp (the north star allows 2)."""
+    m, port = env
+    ref = O.RefLib() if os.path.exists(O.REF_LIB) else None
+    images = helpers.random_group("bank", 3, 1300)
+    pf, ps = [0, 0, 1], [1, 2, 2]
+    m.clear()
+    for i, (d, s, l) in enumerate(images):
+        m.upload(i, d, s, l)
+    for sym in (False, True):
+        res = m.match(pf, ps, 1.0, 0.95, sym=sym, force_exact=force_exact, distances=True)
+        want = port.match_pairs(images, pf, ps, 1.0, 0.95, sym)
+        for p in range(3):
+            got, dist = res.pairs(p), res.distances(p)
+            assert np.array_equal(got, want[p]) and dist.shape[0] == got.shape[0] > 0
+            a, b = images[pf[p]][0], images[ps[p]][0]
+            # forward part: (first_idx, second_idx); the -sym part appended after it is (second-image row.. swapped roles)
+            n_fwd = port.match_pairs(images, [pf[p]], [ps[p]], 1.0, 0.95, False)[0].shape[0]
+            fi, si = got[:n_fwd, 0], got[:n_fwd, 1]
+            exp = O.norm_matrix_numpy(b[si], a)[np.arange(n_fwd), fi] if n_fwd else np.zeros(0, np.float32)
+            assert np.array_equal(dist[:n_fwd].view(np.uint32), exp.view(np.uint32))
+            if ref is not None and n_fwd:
+                assert np.array_equal(ref.distances(a, b, fi, si).view(np.uint32), dist[:n_fwd].view(np.uint32))
+            if sym:  # reverse pass: rows of image `first` scan columns of image `second`; emitted as (row, match)
+                ri, ci = got[n_fwd:, 0], got[n_fwd:, 1]
+                exp = O.norm_matrix_numpy(a[ri], b)[np.arange(ri.shape[0]), ci]
+                assert np.array_equal(dist[n_fwd:].view(np.uint32), exp.view(np.uint32))
+        res.free()
