@@ -180,11 +180,17 @@ struct NcclRank {
 
 // One worker = one GPU.  Runs as a thread of the parent (worker 0, and every worker with -mp 0) or as the main
 // thread of a forked process that sees a single device.
-void worker_run(Control* ctl, int g, int device) {
+// `warm`: a context a resident server already holds for this device (see serve()); else one is created here.
+void worker_run(Control* ctl, int g, int device, fm_ctx* warm) {
   WorkerSlot& w = ctl->worker[g];
   double t0 = now_s();
-  fm_ctx* ctx = nullptr;
-  if (fm_create(device, &ctx) != FM_OK) { worker_fail(ctl, g, fm_last_error(nullptr)); return; }
+  fm_ctx* ctx = warm;
+  if (ctx) {
+    if (fm_clear_images(ctx) != FM_OK) { worker_fail(ctl, g, fm_last_error(ctx)); return; }
+  } else if (fm_create(device, &ctx) != FM_OK) {
+    worker_fail(ctl, g, fm_last_error(nullptr));
+    return;
+  }
   w.create_s = now_s() - t0;
   w.state.store(kContextUp);
 #ifdef FM_WITH_NCCL
@@ -301,14 +307,28 @@ void worker_run(Control* ctl, int g, int device) {
   }
 #endif
   w.gather_s = now_s() - t0;
+  if (warm) {  // a resident server keeps the context: hand the result's buffers back to it
+    fm_result_free(res);
+#ifdef FM_WITH_NCCL
+    if (nccl.comm) ncclCommDestroy(nccl.comm);
+    if (nccl.stream) cudaStreamDestroy(nccl.stream);
+#endif
+  }
   w.state.store(kDone);
-  // The context, its device memory and (NCCL) communicator are not torn down: the process is about to leave, and
-  // destroying one CUDA context per GPU costs a one-shot run more than everything above.
+  // One-shot runs do not tear the context, its device memory or the communicator down: the process is about to
+  // leave, and destroying one CUDA context per GPU costs more than everything above.
 }
+
+// Contexts a resident server (`match -serve-daemon`) keeps warm: one per visible device.
+struct WarmPool {
+  std::vector<fm_ctx*> ctx;
+};
 
 }  // namespace
 
-int main(int argc, char* argv[]) {
+// One `match` invocation.  `cout` / `cerr` are the caller's streams (a resident server relays them to its client);
+// with a WarmPool the GPUs' contexts already exist and no process is forked.
+int run_job(int argc, char* argv[], std::ostream& cout, std::ostream& cerr, WarmPool* warm) {
   std::chrono::time_point<std::chrono::system_clock> start, end;
   int N = 1000000;
   float sp = 0;
@@ -330,7 +350,8 @@ int main(int argc, char* argv[]) {
   const char* statsFile = nullptr;
   const char* distsFile = nullptr;  // -dists f: squared distance of every emitted match (float32, block order of pairs.bin)
   bool planOnly = false;            // -plan 1: print the GPU plan (no CUDA call is made) and exit
-  bool multiProcess = true;         // -mp 0: all GPUs from threads of this one process (pays cuInit for every visible device)
+  bool multiProcess = false;        // -mp 1: one forked worker process per GPU instead of one thread per GPU
+  bool serveMode = false;           // -serve 1: handled by main(): run inside the resident server (warm CUDA contexts)
   // How the lists of GPUs 1.. reach the writer: "host" = every GPU copies its own lists over its own PCIe link,
   // "nccl" = GPU-to-GPU over NVLink to GPU 0, then one device-to-host copy.  Bringing the communicators up costs a
   // one-shot process more than matching a 50 x 50k group, so "host" is the default here.
@@ -360,6 +381,7 @@ int main(int argc, char* argv[]) {
       if (has("-gather")) gatherMode = value;
       if (has("-plan")) planOnly = atoi(value) != 0;
       if (has("-mp")) multiProcess = atoi(value) != 0;
+      if (has("-serve")) serveMode = atoi(value) != 0;
     }
     if (has("-all")) matchAll = true;
     if (has("-p")) writePoints = true;
@@ -415,8 +437,12 @@ int main(int argc, char* argv[]) {
   }
 
   // ---- GPU plan, made before the first CUDA call ---------------------------------------------------------
-  // The number of GPUs follows the work: -gpus G, else one GPU per ~4e12 descriptor pairs estimated from the
-  // keypoint file sizes (a 200 x 20k group takes 0.6 s on one B200: a second GPU's start-up would cost more).
+  // The number of GPUs follows the work.  Bringing CUDA up costs a one-shot process ~0.55 s for the first GPU and
+  // ~0.65 s for EVERY further one -- serialised system-wide, whether the GPUs are driven from threads or from
+  // processes (profiles/r2_ctx_probe.txt) -- while one B200 matches ~1.3e13 descriptor pairs per second.  So without
+  // -gpus the plan is the G that minimises  start-up(G) + pairs / (G x rate), the pairs estimated from the keypoint
+  // file sizes: one GPU up to ~2e13 pairs (a 200 x 20k group is 8e12), two up to ~5e13, ...  A resident server
+  // (-serve 1) has its contexts up already and uses every GPU whenever the group has work for them.
   const size_t n_load = std::min<size_t>(filenames.size(), (size_t)std::max(N, 0));
   const size_t planned_pairs = n_load < 2 ? 0 : (target >= 0 ? n_load - 1 : n_load * (n_load - 1) / 2);
   double est_bytes = 0;  // upper estimate of the float data the arena will hold
@@ -437,7 +463,12 @@ int main(int argc, char* argv[]) {
     }
     if (G_want <= 0) {
       const double est_pairs = target >= 0 ? pts * pts / std::max<double>(n_load, 1) : (pts * pts - pts2) / 2;
-      G_want = (int)std::min(64.0, std::max(1.0, std::ceil(est_pairs / 4e12)));
+      const double rate = 1.3e13, first_gpu_s = warm ? 0.0 : 0.55, next_gpu_s = warm ? 0.01 : 0.65;
+      double best_t = 1e300;
+      for (int g = 1; g <= kMaxWorkers; g++) {
+        const double t = first_gpu_s + next_gpu_s * (g - 1) + est_pairs / (g * rate);
+        if (t < best_t) { best_t = t; G_want = g; }
+      }
     }
     est_bytes += 16.0 * pts * std::max<double>(n_load, 1);  // match lists: <= 8 B per outer-loop row per image pair
   }
@@ -446,6 +477,7 @@ int main(int argc, char* argv[]) {
     cout << "Planned GPUs : " << G_want << " (" << planned_pairs << " image pairs)" << endl;
     return 0;
   }
+  (void)serveMode;
   // device ids the workers may use: the caller's CUDA_VISIBLE_DEVICES list stays authoritative
   std::vector<string> dev_ids;
   if (const char* vis_env = getenv("CUDA_VISIBLE_DEVICES")) {
@@ -458,7 +490,8 @@ int main(int argc, char* argv[]) {
     for (int g = 0; g < n_phys; g++) dev_ids.push_back(std::to_string(g));
   }
   const bool have_ids = !dev_ids.empty();  // (no list and no device nodes: let CUDA report what it finds)
-  const int G = have_ids ? std::max(1, std::min<int>(G_want, (int)dev_ids.size())) : 1;
+  const int G = warm ? std::max(1, std::min<int>(G_want, (int)warm->ctx.size()))
+                     : have_ids ? std::max(1, std::min<int>(G_want, (int)dev_ids.size())) : 1;
   if (nt > 0) omp_set_num_threads(nt);
   int nb = (int)n_load;
   if (nb > 65535) { cerr << "match: more than 65535 images cannot be described by pairs.bin (u16 ids)" << endl; return 1; }
@@ -483,7 +516,7 @@ int main(int argc, char* argv[]) {
   cout << std::flush;
   cerr << std::flush;
   std::vector<pid_t> children;
-  const bool fork_workers = multiProcess && G > 1;
+  const bool fork_workers = multiProcess && G > 1 && !warm;
   if (fork_workers) {
     for (int g = 1; g < G; g++) {
       snprintf(ctl->worker[g].device, sizeof ctl->worker[g].device, "%s", dev_ids[g].c_str());
@@ -491,22 +524,24 @@ int main(int argc, char* argv[]) {
       if (pid < 0) { cerr << "match: fork failed" << endl; ctl->abort.store(1); return 1; }
       if (pid == 0) {
         setenv("CUDA_VISIBLE_DEVICES", ctl->worker[g].device, 1);
-        worker_run(ctl, g, 0);
+        worker_run(ctl, g, 0, nullptr);
         fflush(nullptr);
         _exit(ctl->worker[g].state.load() == kDone ? 0 : 2);
       }
       children.push_back(pid);
     }
   }
-  if (have_ids) {
+  if (have_ids && !warm) {
     // this process: its own device only (forked workers), or the first G devices (threads)
     string vis;
     for (int g = 0; g < (fork_workers ? 1 : G); g++) vis += (g ? "," : "") + dev_ids[g];
     setenv("CUDA_VISIBLE_DEVICES", vis.c_str(), 1);
   }
   std::vector<std::thread> local_workers;
-  for (int g = 0; g < (fork_workers ? 1 : G); g++) local_workers.emplace_back(worker_run, ctl, g, g);
-  // Every exit path below: tell the workers, reap them, and leave without tearing CUDA down.
+  for (int g = 0; g < (fork_workers ? 1 : G); g++) local_workers.emplace_back(worker_run, ctl, g, g, warm ? warm->ctx[g] : nullptr);
+  // Every exit path below: tell the workers, reap them, release the arena.  (A one-shot process then leaves through
+  // _exit in main, without tearing CUDA down.)
+  const uint64_t arena_bytes = ctl->arena_bytes;
   auto leave = [&](int code) -> int {
     if (code != 0) ctl->abort.store(1);
     for (auto& t : local_workers)
@@ -514,8 +549,7 @@ int main(int argc, char* argv[]) {
     for (pid_t pid : children) { int st = 0; waitpid(pid, &st, 0); }
     cout << std::flush;
     cerr << std::flush;
-    fflush(nullptr);
-    _exit(code);
+    munmap(ctl, arena_bytes);
     return code;
   };
   auto report_failures = [&]() {
@@ -758,6 +792,226 @@ int main(int argc, char* argv[]) {
        << ", \"gather\": \"" << (ctl->use_nccl ? "nccl" : (G > 1 ? "host" : "none")) << "\""
        << ", \"nccl_init_s\": " << nccl_init_s << "}" << endl;
   }
-  // pairs.bin and the side files are closed: leave at once (see worker_run on teardown).
   return leave(0);
+}
+
+// ---- resident server (`-serve 1`) -----------------------------------------------------------------------------
+// A one-shot process pays CUDA's start-up on every call (see the GPU plan above); callers that match many groups
+// (FROG.py over a study, the desk UI) can keep ONE server per user alive instead: `match <args> -serve 1` hands the
+// command line to the server over a unix socket -- starting it first if nobody listens -- and relays its stdout,
+// stderr and exit code, so the call looks exactly like a one-shot run to run.sh / FROG.py.  The server holds one
+// context per visible GPU, runs one job at a time through the very same run_job(), and leaves after `idle` seconds
+// without work (FROGMATCH_SERVE_IDLE, default 600).  Socket: $FROGMATCH_SOCKET or /tmp/frogmatch.<uid>.sock.
+
+#include <poll.h>
+#include <sys/socket.h>
+#include <sys/stat.h>
+#include <sys/un.h>
+
+namespace {
+
+string socket_path() {
+  if (const char* p = getenv("FROGMATCH_SOCKET")) return p;
+  return "/tmp/frogmatch." + std::to_string((unsigned)getuid()) + ".sock";
+}
+
+bool send_all(int fd, const void* p, size_t n) {
+  const char* c = static_cast<const char*>(p);
+  while (n) {
+    ssize_t k = send(fd, c, n, MSG_NOSIGNAL);
+    if (k <= 0) return false;
+    c += k;
+    n -= (size_t)k;
+  }
+  return true;
+}
+bool recv_all(int fd, void* p, size_t n) {
+  char* c = static_cast<char*>(p);
+  while (n) {
+    ssize_t k = recv(fd, c, n, 0);
+    if (k <= 0) return false;
+    c += k;
+    n -= (size_t)k;
+  }
+  return true;
+}
+// frame: u8 kind (1 stdout, 2 stderr, 3 exit code) | u32 length | payload
+bool send_frame(int fd, uint8_t kind, const void* p, uint32_t n) {
+  unsigned char head[5] = {kind, (unsigned char)n, (unsigned char)(n >> 8), (unsigned char)(n >> 16), (unsigned char)(n >> 24)};
+  return send_all(fd, head, 5) && (n == 0 || send_all(fd, p, n));
+}
+
+// std::ostream whose bytes travel to the client as frames of one kind
+class FrameBuf : public std::streambuf {
+  int fd_;
+  uint8_t kind_;
+  char buf_[4096];
+ public:
+  FrameBuf(int fd, uint8_t kind) : fd_(fd), kind_(kind) { setp(buf_, buf_ + sizeof buf_); }
+  int sync() override {
+    if (pptr() > pbase()) send_frame(fd_, kind_, pbase(), (uint32_t)(pptr() - pbase()));
+    setp(buf_, buf_ + sizeof buf_);
+    return 0;
+  }
+  int_type overflow(int_type ch) override {
+    sync();
+    if (ch != traits_type::eof()) { *pptr() = (char)ch; pbump(1); }
+    return ch;
+  }
+};
+
+int serve(const string& path, int idle_s) {
+  // contexts for every visible device, created side by side
+  int n_dev = 0;
+  if (fm_device_count(&n_dev) != FM_OK || n_dev <= 0) { fprintf(stderr, "match -serve: %s\n", fm_last_error(nullptr)); return 1; }
+  WarmPool pool;
+  pool.ctx.assign((size_t)std::min(n_dev, kMaxWorkers), nullptr);
+  {
+    std::vector<std::thread> th;
+    for (size_t g = 0; g < pool.ctx.size(); g++) th.emplace_back([&pool, g] { fm_create((int)g, &pool.ctx[g]); });
+    for (auto& t : th) t.join();
+  }
+  for (auto* c : pool.ctx)
+    if (!c) { fprintf(stderr, "match -serve: cannot create a context on every visible device\n"); return 1; }
+  int ls = socket(AF_UNIX, SOCK_STREAM, 0);
+  sockaddr_un addr{};
+  addr.sun_family = AF_UNIX;
+  snprintf(addr.sun_path, sizeof addr.sun_path, "%s", path.c_str());
+  unlink(path.c_str());
+  const mode_t old_mask = umask(0077);  // the socket belongs to this user alone
+  const bool bound = ls >= 0 && bind(ls, reinterpret_cast<sockaddr*>(&addr), sizeof addr) == 0 && listen(ls, 8) == 0;
+  umask(old_mask);
+  if (!bound) { perror("match -serve: bind"); return 1; }
+  for (;;) {
+    pollfd pfd{ls, POLLIN, 0};
+    const int pr = poll(&pfd, 1, idle_s * 1000);
+    if (pr == 0) break;  // idle: leave
+    if (pr < 0) continue;
+    const int fd = accept(ls, nullptr, nullptr);
+    if (fd < 0) continue;
+    // request: u32 length | cwd \0 arg0 \0 arg1 \0 ...
+    uint32_t len = 0;
+    std::vector<char> req;
+    if (recv_all(fd, &len, 4) && len > 0 && len < (1u << 24)) {
+      req.resize(len);
+      if (!recv_all(fd, req.data(), len)) req.clear();
+    }
+    if (!req.empty() && req.back() == 0) {
+      std::vector<char*> args;
+      for (size_t i = 0; i < req.size();) { args.push_back(req.data() + i); i += strlen(req.data() + i) + 1; }
+      if (args.size() >= 3 && strcmp(args[2], "-serve-stop") == 0) {
+        const uint32_t zero = 0;
+        send_frame(fd, 3, &zero, 4);
+        close(fd);
+        break;
+      }
+      int code = 1;
+      if (args.size() >= 2 && chdir(args[0]) == 0) {
+        FrameBuf ob(fd, 1), eb(fd, 2);
+        std::ostream os(&ob), es(&eb);
+        code = run_job((int)args.size() - 1, args.data() + 1, os, es, &pool);
+        os.flush();
+        es.flush();
+      }
+      const uint32_t c = (uint32_t)code;
+      send_frame(fd, 3, &c, 4);
+    }
+    close(fd);
+  }
+  close(ls);
+  unlink(path.c_str());
+  return 0;
+}
+
+int connect_to(const string& path) {
+  int fd = socket(AF_UNIX, SOCK_STREAM, 0);
+  if (fd < 0) return -1;
+  sockaddr_un addr{};
+  addr.sun_family = AF_UNIX;
+  snprintf(addr.sun_path, sizeof addr.sun_path, "%s", path.c_str());
+  if (connect(fd, reinterpret_cast<sockaddr*>(&addr), sizeof addr) != 0) { close(fd); return -1; }
+  return fd;
+}
+
+// Client side of `-serve 1`.  Returns the job's exit code, or -1 if no server could be reached or started (the caller
+// then runs the job itself).
+int run_served(int argc, char* argv[]) {
+  const string path = socket_path();
+  int fd = connect_to(path);
+  if (fd < 0) {
+    // nobody listens: start the server (detached, its own session), then wait for its socket
+    pid_t pid = fork();
+    if (pid == 0) {
+      setsid();
+      if (fork() != 0) _exit(0);  // the grandchild is adopted by init: no zombie, no controlling terminal
+      const string log = path + ".log";
+      FILE* lf = freopen(log.c_str(), "a", stderr);
+      (void)lf;
+      lf = freopen("/dev/null", "w", stdout);
+      lf = freopen("/dev/null", "r", stdin);
+      execl("/proc/self/exe", argv[0], "-serve-daemon", path.c_str(), (char*)nullptr);
+      _exit(127);
+    }
+    if (pid > 0) { int st = 0; waitpid(pid, &st, 0); }
+    for (int i = 0; i < 1200 && fd < 0; i++) {  // CUDA start-up for every visible GPU: up to a minute
+      usleep(50000);
+      fd = connect_to(path);
+    }
+    if (fd < 0) return -1;
+  }
+  std::vector<char> req;
+  char cwd[4096];
+  if (!getcwd(cwd, sizeof cwd)) { close(fd); return -1; }
+  req.insert(req.end(), cwd, cwd + strlen(cwd) + 1);
+  for (int i = 0; i < argc; i++) req.insert(req.end(), argv[i], argv[i] + strlen(argv[i]) + 1);
+  const uint32_t len = (uint32_t)req.size();
+  if (!send_all(fd, &len, 4) || !send_all(fd, req.data(), req.size())) { close(fd); return -1; }
+  std::vector<char> buf;
+  for (;;) {
+    unsigned char head[5];
+    if (!recv_all(fd, head, 5)) { fprintf(stderr, "match: the server closed the connection\n"); close(fd); return 1; }
+    const uint32_t n = head[1] | (head[2] << 8) | (head[3] << 16) | ((uint32_t)head[4] << 24);
+    buf.resize(n);
+    if (n && !recv_all(fd, buf.data(), n)) { close(fd); return 1; }
+    if (head[0] == 1) { fwrite(buf.data(), 1, n, stdout); fflush(stdout); }
+    else if (head[0] == 2) { fwrite(buf.data(), 1, n, stderr); }
+    else if (head[0] == 3) {
+      uint32_t code = 1;
+      if (n == 4) memcpy(&code, buf.data(), 4);
+      close(fd);
+      return (int)code;
+    }
+  }
+}
+
+}  // namespace
+
+int main(int argc, char* argv[]) {
+  if (argc >= 3 && strcmp(argv[1], "-serve-daemon") == 0) {
+    const char* idle = getenv("FROGMATCH_SERVE_IDLE");
+    const int rc = serve(argv[2], idle ? std::max(1, atoi(idle)) : 600);
+    fflush(nullptr);
+    _exit(rc);
+  }
+  bool served = false;
+  for (int k = 2; k + 1 < argc; k++)
+    if (strcmp(argv[k], "-serve") == 0 && atoi(argv[k + 1]) != 0) served = true;
+  if ((argc >= 2 && strcmp(argv[1], "-serve-stop") == 0)) {
+    const int fd = connect_to(socket_path());
+    if (fd < 0) return 0;  // nothing to stop
+    close(fd);
+    return run_served(argc, argv) == 0 ? 0 : 1;
+  }
+  if (served) {
+    const int rc = run_served(argc, argv);
+    if (rc >= 0) return rc;
+    cerr << "match: no resident server could be reached or started; running one-shot" << endl;
+  }
+  const int rc = run_job(argc, argv, cout, cerr, nullptr);
+  // pairs.bin and the side files are closed.  Tearing down one CUDA context per GPU (and NCCL) costs a one-shot
+  // process up to seconds and frees nothing the operating system does not reclaim anyway: leave at once.
+  cout << std::flush;
+  cerr << std::flush;
+  fflush(nullptr);
+  _exit(rc);
 }
