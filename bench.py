@@ -591,6 +591,7 @@ def bench_ours(args):
             "phases_ms": {k: s0[k] for k in ("ms_total", "ms_score", "ms_rescore", "ms_exact", "ms_compact", "ms_prep")},
             "rank0_host_ms_per_step": res_host_ms,
             "rows_exact_frac": s0["rows_exact"] / max(1, s0["rows"]), "candidates_per_row": s0["candidates"] / max(1, s0["rows"]),
+            "rows_rejected_early_frac": s0["rows_rejected_early"] / max(1, s0["rows"]),
             # differences from the reference whose distance / ratio sits within 4 ulp of -d / -d2, counted on the
             # cpu_baseline sample (N = 1 runs; null when that leg did not run)
             "threshold_eps_count": None,

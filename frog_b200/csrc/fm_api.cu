@@ -144,6 +144,7 @@ int finalize(fm_result* r) {
   for (size_t p = 0; p < r->n_pairs; p++) r->offsets[p + 1] = r->offsets[p] + r->counts[p];
   r->stats.scored_pairs = hc->scored_cols;
   r->stats.candidates = hc->rescore.candidates;
+  r->stats.rows_rejected_early = hc->rescore.rejected_early;
   r->stats.rows_exact += hc->redo_total;
   float acc[kNumPhases] = {0};
   for (auto& s : r->ev.spans) {
@@ -287,12 +288,12 @@ int fm_upload_image(fm_ctx* c, uint32_t img, const float* desc, const float* sca
   if (img >= c->images.size()) c->images.resize(img + 1);
   if (img >= c->h_images.size()) c->h_images.resize(img + 1, ImageDev{});
   Image& im = c->images[img];
-  // One slab per image: desc | scale | lap | perm | scale_sorted | rowop | colop (1 KB aligned pieces).
+  // One slab per image: desc | scale | lap | perm | scale_sorted | norm2_sorted | rowop | colop (1 KB aligned pieces).
   auto pad = [](size_t x) { return (x + 1023) & ~(size_t)1023; };
   const uint32_t n_pad = (n + 255u) & ~255u;  // rows are consumed 256 at a time, columns 64
   const size_t b_desc = pad((size_t)n * d * sizeof(float)), b_vec = pad((size_t)std::max(n, 1u) * sizeof(float));
   const size_t b_op = d == (uint32_t)kD ? pad((size_t)n_pad * kKPad * sizeof(__half)) : 0;
-  const size_t need = b_desc + 4 * b_vec + 2 * b_op + 1024;
+  const size_t need = b_desc + 5 * b_vec + 2 * b_op + 1024;
   if (!im.slab || im.slab_bytes < need) {  // a re-upload that fits reuses the image's slab
     void* p = nullptr;
     FM_CUDA(c, c->arena.alloc(need, &p));
@@ -321,8 +322,9 @@ int fm_upload_image(fm_ctx* c, uint32_t img, const float* desc, const float* sca
   v.n_pad = n_pad;
   v.perm = reinterpret_cast<uint32_t*>(base + b_desc + 2 * b_vec);
   v.scale_sorted = reinterpret_cast<float*>(base + b_desc + 3 * b_vec);
-  v.rowop = b_op ? reinterpret_cast<__half*>(base + b_desc + 4 * b_vec) : nullptr;
-  v.colop = b_op ? reinterpret_cast<__half*>(base + b_desc + 4 * b_vec + b_op) : nullptr;
+  v.norm2_sorted = reinterpret_cast<float*>(base + b_desc + 4 * b_vec);
+  v.rowop = b_op ? reinterpret_cast<__half*>(base + b_desc + 5 * b_vec) : nullptr;
+  v.colop = b_op ? reinterpret_cast<__half*>(base + b_desc + 5 * b_vec + b_op) : nullptr;
   {
     cudaError_t e = ensure_metas(c, (uint32_t)c->h_images.size());
     if (e != cudaSuccess) return cuda_fail(c, e, "fm_upload_image");

@@ -43,6 +43,7 @@ struct ImageDev {
   uint32_t pad_;
   const uint32_t* perm;        // (sorted) [n]   sorted position -> original index
   const float* scale_sorted;   // (sorted) [n]
+  const float* norm2_sorted;   // (sorted) [n]   |desc|^2 in FP32 (early rejection in the rescoring kernel)
   const __half* rowop;  // (sorted) [n_pad/128] tiles of 128 x 64 halves, SWIZZLE_128B K-major image,
                         //          columns 0..47 = fp16(desc), 48,49 = 1, rest 0 (this image as rows)
   const __half* colop;  // same tiling; columns 48,49 = hi/lo halves of -|desc|^2/2 (image as columns)

@@ -15,7 +15,7 @@ struct DeviceCounters {
   unsigned long long scored_cols;    // row x column scores evaluated by score_kernel
   RescoreCounters rescore;           // candidates, redo_rows (redo_rows is reset per batch)
   unsigned long long redo_total;     // redo rows accumulated over batches
-  unsigned long long pad[11];
+  unsigned long long pad[10];
 };
 static_assert(sizeof(DeviceCounters) == 128, "DeviceCounters layout");
 
@@ -100,7 +100,8 @@ inline cudaError_t fast_prepare_dirty(fm_ctx* c) {
                                         c->s_idx_sorted.as<uint32_t>(), (int)off, 0, end_bit, c->stream);
     if (e != cudaSuccess) return e;
   }
-  prep_finish_kernel<<<n_segs, 1024, 0, c->stream>>>(d_images, d_segs, d_metas, keys_sorted, c->s_idx_sorted.as<uint32_t>());
+  prep_finish_kernel<<<n_segs, 1024, 0, c->stream>>>(d_images, d_segs, d_metas, keys_sorted, c->s_idx_sorted.as<uint32_t>(),
+                                                     c->s_norm2.as<float>());
   if (blk_pack) prep_pack_kernel<<<blk_pack, 256, 0, c->stream>>>(d_images, d_segs, n_segs, c->s_norm2.as<float>());
   return cudaGetLastError();
 }

@@ -105,7 +105,8 @@ prep_keys_kernel(const ImageDev* __restrict__ images, const PrepSeg* __restrict_
 // build the laplacian class table.
 __global__ void __launch_bounds__(1024)
 prep_finish_kernel(const ImageDev* __restrict__ images, const PrepSeg* __restrict__ segs, ImageMeta* __restrict__ metas,
-                   const unsigned long long* __restrict__ keys_sorted, const uint32_t* __restrict__ idx_sorted) {
+                   const unsigned long long* __restrict__ keys_sorted, const uint32_t* __restrict__ idx_sorted,
+                   const float* __restrict__ norm2_all) {
   __shared__ uint32_t s_pos[kMaxClasses + 1];
   __shared__ uint32_t s_cnt, s_collide;
   const PrepSeg seg = segs[blockIdx.x];
@@ -113,6 +114,8 @@ prep_finish_kernel(const ImageDev* __restrict__ images, const PrepSeg* __restric
   ImageMeta* meta = metas + seg.img;
   uint32_t* perm = const_cast<uint32_t*>(im.perm);
   float* scale_sorted = const_cast<float*>(im.scale_sorted);
+  float* norm2_sorted = const_cast<float*>(im.norm2_sorted);
+  const float* norm2 = norm2_all + seg.off;
   const unsigned long long* ks = keys_sorted + seg.off;
   const uint32_t* is = idx_sorted + seg.off;
   const uint32_t n = seg.n;
@@ -123,6 +126,7 @@ prep_finish_kernel(const ImageDev* __restrict__ images, const PrepSeg* __restric
     const uint32_t o = is[s];
     perm[s] = o;
     scale_sorted[s] = __uint_as_float((uint32_t)k);
+    norm2_sorted[s] = norm2[o];
     if (s == 0 || (uint32_t)(ks[s - 1] >> 32) != (uint32_t)(k >> 32)) {
       uint32_t slot = atomicAdd(&s_cnt, 1u);
       if (slot <= kMaxClasses) s_pos[slot] = s;

@@ -18,8 +18,9 @@
 namespace fm {
 
 struct RescoreCounters {
-  unsigned long long candidates;  // exact distances evaluated
-  unsigned long long redo_rows;   // rows handed to exact_rows_kernel
+  unsigned long long candidates;      // exact distances evaluated
+  unsigned long long redo_rows;       // rows handed to exact_rows_kernel
+  unsigned long long rejected_early;  // rows proven unacceptable from their approximate scores alone
 };
 
 __device__ __forceinline__ float exact_norm48(const float (&r)[kD], const float* __restrict__ col) {
@@ -93,9 +94,29 @@ rescore_kernel(const ImageDev* __restrict__ images, const Task* __restrict__ tas
     }
   }
 
+  // Early rejection, certified.  With na = |a|^2 of the row, a column's squared distance is na - 2t, and the
+  // reference's FP32 value of it lies within `margin` of na - 2t~ (2 eps for the score, the rest for the FP32
+  // evaluation of na here and of the distance there).  The lists hold the row's two best approximate scores
+  // a1 >= a2, so   d1_ref >= d1_lo = na - 2 a1 - margin   and   d2_ref <= d2_hi = na - 2 a2 + margin.
+  //   * d1_lo > thr^2 (1 + 1e-5)            =>  sqrtf(d1) < thr is false                      (match.cpp:321)
+  //   * d1_lo > ratio^2 d2_hi (1 + 1e-4)    =>  sqrtf(d1 / d2) < ratio is false, and d2 != FLT_MAX because a
+  //                                              second gated-in column exists                 (match.cpp:320)
+  // Either way the row emits nothing and no exact distance has to be gathered: with -d2 0.8 on unrelated images
+  // that is almost every row.  (ratio >= 1 can never trigger the second test: a1 >= a2.)
+  bool rejected = false;
+  if (!overflow && a1 > -INFINITY) {
+    const float na = B.norm2_sorted[s];
+    const float margin = 2.f * eps + 1e-5f * (na + 4.f);
+    const float d1_lo = na - 2.f * a1 - margin;
+    const float d2_hi = na - 2.f * a2 + margin;
+    const float thr2 = thr * thr;
+    rejected = d1_lo > thr2 * 1.00001f;
+    if (a2 > -INFINITY && d2_hi > 0.f && ratio < 1.0e4f) rejected = rejected || d1_lo > ratio * ratio * d2_hi * 1.0001f;
+  }
+
   uint32_t match = kNone;
   uint32_t n_eval = 0;
-  if (!overflow && a1 > -INFINITY) {
+  if (!overflow && !rejected && a1 > -INFINITY) {
     float r[kD];
     const float4* src = reinterpret_cast<const float4*>(B.desc + (size_t)row * kD);
 #pragma unroll
@@ -126,9 +147,16 @@ rescore_kernel(const ImageDev* __restrict__ images, const Task* __restrict__ tas
     redo_list[slot] = make_uint2(t, s);
   }
   // statistics: one atomic per warp
+  uint32_t n_rej = rejected ? 1u : 0u;
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) n_eval += __shfl_xor_sync(0xffffffffu, n_eval, o);
-  if ((threadIdx.x & 31) == 0 && n_eval) atomicAdd(&counters->candidates, (unsigned long long)n_eval);
+  for (int o = 16; o > 0; o >>= 1) {
+    n_eval += __shfl_xor_sync(0xffffffffu, n_eval, o);
+    n_rej += __shfl_xor_sync(0xffffffffu, n_rej, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (n_eval) atomicAdd(&counters->candidates, (unsigned long long)n_eval);
+    if (n_rej) atomicAdd(&counters->rejected_early, (unsigned long long)n_rej);
+  }
 }
 
 // Exact redo of queued rows: one CTA per row (queued rows are rare -- a handful per million -- so

@@ -148,6 +148,7 @@ typedef struct fm_stats {
   float ms_exact;             /* ... exact brute-force kernel */
   float ms_compact;           /* ... stream compaction */
   float ms_prep;              /* CUDA-event time of all uploads' prep kernels since the last clear */
+  uint64_t rows_rejected_early; /* rows the rescoring kernel proved unacceptable from their approximate scores (no exact distance evaluated) */
 } fm_stats;
 
 /* Statistics of the most recent fm_match on this context (synchronises the stream). */

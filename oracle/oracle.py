@@ -21,6 +21,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 REF_BIN = os.path.join(HERE, "_ref", "match_ref")
 REF_LIB = os.path.join(HERE, "_ref", "libmatch_ref.so")
 PORT_LIB = os.path.join(HERE, "libmatch_oracle.so")
+FAST_LIB = os.path.join(HERE, "libfast_oracle.so")
 
 _f32p = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
 _u32p = np.ctypeslib.ndpointer(np.uint32, flags="C_CONTIGUOUS")
@@ -95,6 +96,28 @@ class RefLib(_CMLib):
         out = np.zeros(fi.shape[0], np.float32)
         self.lib.ref_distances(a, b, a.shape[1], fi, si, fi.shape[0], out)
         return out
+
+
+class FastLib:
+    """oracle/libfast_oracle.so: ComputeMatches vectorised across columns (fast_oracle.c) -- bit-identical to the port
+    and to the verbatim reference (tests/test_oracle.py), ~100x faster: the checker for 20k x 20k / 50k x 50k blocks."""
+
+    def __init__(self):
+        if not os.path.exists(FAST_LIB):
+            raise FileNotFoundError(f"{FAST_LIB} not built -- run `make -C oracle port`")
+        self.lib = C.CDLL(FAST_LIB)
+        self.lib.fo_compute_matches.argtypes = _CM_ARGS
+        self.lib.fo_compute_matches.restype = C.c_int64
+
+    def compute_matches(self, first, second, threshold: float, ratio: float, sym: bool = False) -> np.ndarray:
+        d1, s1, l1 = map(_f32, first)
+        d2, s2, l2 = map(_f32, second)
+        out = np.zeros((max(d2.shape[0], 1), 2), np.uint32)
+        n = self.lib.fo_compute_matches(d1, s1, l1, d1.shape[0], d2, s2, l2, d2.shape[0], d1.shape[1],
+                                        threshold, ratio, int(sym), out.reshape(-1))
+        if n < 0:
+            raise ValueError("fast oracle refused the input (threshold >= 1.8e19 or out of memory)")
+        return out[:n].copy()
 
 
 class PortLib(_CMLib):

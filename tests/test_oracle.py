@@ -138,3 +138,40 @@ def test_reference_binary_regenerates_golden(golden_dir, tmp_path, built):
     out = str(tmp_path / "o.bin")
     O.run_ref_binary([os.path.join(golden_dir, "list_bin.txt"), "-o", out, "-d", "1", "-d2", "0.8"])
     assert open(out, "rb").read() == open(os.path.join(golden_dir, "bin_ratio.pairs.bin"), "rb").read()
+
+
+def test_fast_oracle_is_pinned(libs):
+    """oracle/fast_oracle.c (vectorised across columns, k sequential) == the plain port == the verbatim reference, on
+    the flag sets of the callers, ragged sizes that are no multiple of its 512-column tile, exact ties (strict '<':
+    the lowest column wins), duplicated rows (d1 == d2 == 0: NaN ratio), scales sitting exactly on the 1.3f gate,
+    a third laplacian value and single-survivor rows (d2 == FLT_MAX)."""
+    port, ref = libs
+    fast = O.FastLib()
+    rng = np.random.default_rng(17)
+    cases = []
+    for kind, na, nb in (("bank", 1300, 777), ("iid", 513, 1025), ("bank", 1, 40), ("iid", 40, 1), ("iid", 0, 9), ("iid", 9, 0)):
+        a, b = synth.make(kind, max(na, 1), 0), synth.make(kind, max(nb, 1), 1)
+        cases.append(((a.desc[:na], a.scale[:na], a.lap[:na]), (b.desc[:nb], b.scale[:nb], b.lap[:nb])))
+    # adversarial set: ties, duplicates, gate boundaries
+    a, b = synth.make("bank", 600, 3), synth.make("bank", 700, 4)
+    da, sa, la = a.desc.copy(), a.scale.copy(), a.lap.copy()
+    db, sb, lb = b.desc.copy(), b.scale.copy(), b.lap.copy()
+    da[100:110] = da[50:60]            # duplicated columns: tie between two columns of image `first`
+    db[5] = da[7]; db[6] = da[7]       # rows identical to a column (d1 = 0) ...
+    da[8] = da[7]                      # ... and to a second one (d1 = d2 = 0 -> 0/0)
+    sb[20:40] = sa[20:40] * np.float32(1.3)   # scale ratio at / next to the float 1.3 boundary
+    sb[40:60] = np.nextafter(sa[40:60] * np.float32(1.3), np.float32(10), dtype=np.float32)
+    la[300:320] = 2.0; lb[300:330] = 2.0      # a third laplacian value
+    la[590:] = 7.0; lb[690] = 7.0             # few columns share the class: some rows have one survivor only
+    cases.append(((da, sa, la), (db, sb, lb)))
+    n_checked = 0
+    for first, second in cases:
+        for thr, rat, sym in PARAMS + [(1.0, 1.0, False)]:
+            f = fast.compute_matches(first, second, thr, rat, sym)
+            assert np.array_equal(f, port.compute_matches(first, second, thr, rat, sym))
+            if ref is not None:
+                assert np.array_equal(f, ref.compute_matches(first, second, thr, rat, sym))
+            n_checked += 1
+    assert n_checked == len(cases) * (len(PARAMS) + 1)
+    with pytest.raises(ValueError):  # thresholds at which the reference's carried `match` would show: refused
+        fast.compute_matches(cases[0][0], cases[0][1], 2e19, 1.0)
