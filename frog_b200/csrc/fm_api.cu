@@ -480,14 +480,6 @@ int fm_match(fm_ctx* c, const uint32_t* pair_first, const uint32_t* pair_second,
     FM_CUDA_R(c->d_chunk_status.ensure((size_t)max_chunks * sizeof(unsigned long long) * 2));
     FM_CUDA_R(cudaMemsetAsync(c->d_chunk_status.p, 0, c->d_chunk_status.cap, c->stream));
   }
-  if (!c->compact_grid) {
-    // persistent CTAs: never more than are resident at once (their look-back waits rely on it)
-    int per_sm = 0;
-    FM_CUDA_R(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, compact_kernel<false>, kCompactThreads, 0));
-    int per_sm_d = 0;
-    FM_CUDA_R(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_d, compact_kernel<true>, kCompactThreads, 0));
-    c->compact_grid = (uint32_t)std::max(1, std::min(per_sm, per_sm_d)) * (uint32_t)c->sm_count;
-  }
   FM_CUDA_R(c->d_totals.ensure(sizeof(DeviceCounters)));
   FM_CUDA_R(r->d_out.ensure(std::max<uint64_t>(total_rows, 1) * sizeof(uint2)));
   FM_CUDA_R(r->d_counts.ensure(std::max<size_t>(n_pairs, 1) * sizeof(uint32_t)));
@@ -616,7 +608,7 @@ int fm_match(fm_ctx* c, const uint32_t* pair_first, const uint32_t* pair_second,
         ca.running_total = &d_counters->running_total;
         ca.out_pairs = r->d_out.as<uint2>();
         ca.out_dist = want_dist ? r->d_dist.as<float>() : nullptr;
-        const uint32_t grid = std::min(b.chunks, c->compact_grid);
+        const uint32_t grid = b.chunks;
         if (want_dist) compact_kernel<true><<<grid, kCompactThreads, 0, c->stream>>>(ca);
         else compact_kernel<false><<<grid, kCompactThreads, 0, c->stream>>>(ca);
         c->stats.kernel_launches += 1;

@@ -129,7 +129,6 @@ struct fm_ctx {
   uint32_t dim = 0;
   // per-call scratch
   fm::DevBuf d_meta_blob, d_rowres, d_rowdist, d_chunk_status, d_totals;
-  uint32_t compact_grid = 0;   // persistent CTAs of the compaction kernel: what fits on the chip at once
   uint32_t compact_epoch = 0;  // tags the look-back status words of a compaction launch (fm_compact.cuh)
   fm::DevBuf d_bands, d_cands, d_redo, d_taskinfo;
   fm::DevBuf d_all, d_all_tasks;  // -all mode: per-row count / final / carry / offset, per-task totals and bases
