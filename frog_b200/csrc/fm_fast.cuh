@@ -146,9 +146,6 @@ inline cudaError_t fast_match_batch(fm_ctx* c, const FastBatchArgs& a) {
     if ((e = prep(score_kernel<false, 0, 0>)) != cudaSuccess) return e;
     if ((e = prep(score_kernel<false, 1, 0>)) != cudaSuccess) return e;
     if ((e = prep(score_kernel<false, 2, 0>)) != cudaSuccess) return e;
-    if ((e = prep(score_kernel<false, 0, 1>)) != cudaSuccess) return e;
-    if ((e = prep(score_kernel<false, 0, 2>)) != cudaSuccess) return e;
-    if ((e = prep(score_kernel<false, 0, 3>)) != cudaSuccess) return e;
     if ((e = prep(score_kernel<true, 0, 0>)) != cudaSuccess) return e;
     c->score_attr_set = true;
   }
@@ -162,9 +159,8 @@ inline cudaError_t fast_match_batch(fm_ctx* c, const FastBatchArgs& a) {
     // the defaults are the production kernel
     const int probe = g_debug.probe, var = g_debug.variant;
     const uint32_t pre_tiles = g_debug.pre_tiles >= 0 ? (uint32_t)g_debug.pre_tiles : kPreTiles;
-    auto kern = probe == 1 ? score_kernel<false, 1, 0> : probe == 2 ? score_kernel<false, 2, 0>
-              : var == 1 ? score_kernel<false, 0, 1> : var == 2 ? score_kernel<false, 0, 2>
-              : var == 3 ? score_kernel<false, 0, 3> : score_kernel<false, 0, 0>;
+    auto kern = probe == 1 ? score_kernel<false, 1, 0> : probe == 2 ? score_kernel<false, 2, 0> : score_kernel<false, 0, 0>;
+    (void)var;
     kern<<<a.units, kScoreThreads, kScoreSmemBytes, c->stream>>>(
         a.images, a.tasks, a.unit_off, a.n_tasks, a.segs, c->d_bands.as<uint2>(), c->d_cands.as<Cand>(),
         &a.counters->scored_cols, nullptr, 0, 0, pre_tiles);

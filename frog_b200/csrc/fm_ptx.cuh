@@ -43,25 +43,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
-// Poll with test_wait (no hardware suspend) and back off with a plain nanosleep in between: for single-thread
-// producer warps whose try_wait loops would otherwise wake on every barrier event of the CTA.
-template <uint32_t kSleepNs>
-__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
-  const uint32_t addr = smem_u32(bar);
-  for (;;) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(addr), "r"(parity)
-        : "memory");
-    if (ok) return;
-    __nanosleep(kSleepNs);
-  }
-}
-
 // Variants taking the barrier's shared-space address (keeps hot loops free of generic->shared conversions).
 __device__ __forceinline__ void mbar_arrive_u32(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");

@@ -265,15 +265,12 @@ __device__ __forceinline__ void score_pair(const uint32_t (&ra)[16], const uint3
   const float hi = fmaxf(a.m, b.m), lw = fminf(a.m, b.m);
   // top two of {g1, g2, hi, lw} (g1 >= g2, hi >= lw)
   const float hi_u = upd ? hi : -INFINITY, lw_u = upd ? lw : -INFINITY;
-  // kVar & 2: test against the threshold of the PREVIOUS step (a lower threshold only captures more), so the
-  // compare -> vote -> branch chain does not wait for the g1/g2/thr update of this step
-  const float th_stale = st.thr;
   const float g2n = max3(st.g2, lw_u, fminf(st.g1, hi_u));
   st.g1 = fmaxf(st.g1, hi_u);
   st.g2 = g2n;
   if (kProbe != 1) st.thr = st.g2 - two_eps;
   float th = st.thr;
-  const bool hit = cap && hi > ((kVar & 2) ? th_stale : th);
+  const bool hit = cap && hi > th;
   if (__any_sync(kAll, hit)) {
     // Two rare situations share one vote: a row without a threshold yet, a row whose list is nearly full.
     if (__any_sync(kAll, hit && (st.g2 == -INFINITY || st.capw - st.cap > kFullAt))) {
@@ -371,8 +368,11 @@ __device__ __forceinline__ void score_tile(uint32_t taddr, uint32_t cb, uint32_t
 // dump (kDump only): [256][dump_ld] raw t of the unit.
 // kProbe (performance attribution only, results are garbage): 1 = capture threshold pinned at +inf,
 // i.e. the max-tree fast path alone; 2 = epilogue skips the TMEM loads too (TMA + MMA pipeline alone).
-// kVar (experiments): bit 0 = the two single-thread warps back off with nanosleep between barrier polls,
-// bit 1 = capture test against the previous step's threshold.
+// kVar: slot for experiment builds (fm_debug_set_option("variant")); none is compiled in at present.  Tried and
+// dropped in round 2, all measured on C2 (profiles/r2_summary.md): nanosleep back-off in the two single-thread warps
+// (no change: their polling does not take issue slots the epilogue needs), testing against the previous step's
+// threshold to shorten the compare -> vote chain (-1 %), and loading the second half of a tile under the processing
+// of the first (needs ~130 registers per epilogue thread; 104 is the most setmaxnreg can hand out at two CTAs per SM).
 template <bool kDump, int kProbe = 0, int kVar = 0>
 __global__ void __launch_bounds__(kScoreThreads, 2)
 score_kernel(const ImageDev* __restrict__ images, const Task* __restrict__ tasks,
@@ -466,7 +466,7 @@ score_kernel(const ImageDev* __restrict__ images, const Task* __restrict__ tasks
         for (uint32_t i = 0; i < n_sched; i++) {
           const uint32_t stg = i % kStages, use = i / kStages;
           const uint32_t tile = tile0 + (i < n_pre ? i : i - n_pre);
-          if (use > 0) { if (kVar & 1) ptx::mbar_wait_sleep<400>(&sm.bar_bempty[stg], (use - 1) & 1); else ptx::mbar_wait(&sm.bar_bempty[stg], (use - 1) & 1); }
+          if (use > 0) ptx::mbar_wait(&sm.bar_bempty[stg], (use - 1) & 1);
           ptx::mbar_expect_tx(&sm.bar_bfull[stg], kTileBytes);
           ptx::bulk_g2s(sm.b[stg], colop + (size_t)tile * kTileBytes, kTileBytes, &sm.bar_bfull[stg]);
         }
@@ -480,13 +480,8 @@ score_kernel(const ImageDev* __restrict__ images, const Task* __restrict__ tasks
         ptx::mbar_wait(&sm.bar_a, 0);
         for (uint32_t i = 0; i < n_sched; i++) {
           const uint32_t stg = i % kStages, acc = i & 1, use = i >> 1;
-          if (kVar & 1) {
-            if (use > 0) ptx::mbar_wait_sleep<100>(&sm.bar_accempty[acc][0], (use - 1) & 1);
-            ptx::mbar_wait_sleep<100>(&sm.bar_bfull[stg], (i / kStages) & 1);
-          } else {
-            if (use > 0) ptx::mbar_wait(&sm.bar_accempty[acc][0], (use - 1) & 1);
-            ptx::mbar_wait(&sm.bar_bfull[stg], (i / kStages) & 1);
-          }
+          if (use > 0) ptx::mbar_wait(&sm.bar_accempty[acc][0], (use - 1) & 1);
+          ptx::mbar_wait(&sm.bar_bfull[stg], (i / kStages) & 1);
           ptx::tc_fence_after();
           const uint64_t bdesc = ptx::umma_desc_sw128(ptx::smem_u32(sm.b[stg]));
 #pragma unroll
@@ -494,8 +489,7 @@ score_kernel(const ImageDev* __restrict__ images, const Task* __restrict__ tasks
             ptx::mma_f16_ss(tmem + acc * (2 * kTileCols), adesc0 + 2 * k, bdesc + 2 * k, idesc, k > 0);
           ptx::mma_commit(&sm.bar_accfull[acc][0]);
           if (use > 0) {
-            if (kVar & 1) ptx::mbar_wait_sleep<100>(&sm.bar_accempty[acc][1], (use - 1) & 1);
-            else ptx::mbar_wait(&sm.bar_accempty[acc][1], (use - 1) & 1);
+            ptx::mbar_wait(&sm.bar_accempty[acc][1], (use - 1) & 1);
             ptx::tc_fence_after();
           }
 #pragma unroll
