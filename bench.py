@@ -579,7 +579,8 @@ def bench_ours(args):
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": achieved / peak_tf, "traffic": measured_traffic(args.workload), "peak_source": which + " (cuBLAS bf16 burst)",
-                         "kernel": "fm::score_kernel<false>", "kernel_ms": sc_ms, "launches_per_step": n_launch,
+                         "kernel": "fm::score_kernel<false>" + (" (reject pass + capture pass)" if s0.get("two_phase_batches") else ""),
+                         "kernel_ms": sc_ms, "launches_per_step": n_launch, "two_phase_batches_per_step": s0.get("two_phase_batches", 0),
                          "algorithmic_flop_per_launch": FLOP_PER_PAIR * pairs_per_launch,
                          "executed_tflops": executed, "executed_frac": executed / peak_tf,
                          "scored_fraction": scored_per_launch / max(1.0, pairs_per_launch), "rank": 0},

@@ -37,7 +37,7 @@ class Stats(C.Structure):
         ("rows_exact", C.c_uint64), ("candidates", C.c_uint64), ("kernel_launches", C.c_uint64),
         ("score_launches", C.c_uint64), ("ms_total", C.c_float), ("ms_score", C.c_float),
         ("ms_rescore", C.c_float), ("ms_exact", C.c_float), ("ms_compact", C.c_float), ("ms_prep", C.c_float),
-        ("rows_rejected_early", C.c_uint64),
+        ("rows_rejected_early", C.c_uint64), ("two_phase_batches", C.c_uint64),
     ]
 
     def as_dict(self) -> dict:

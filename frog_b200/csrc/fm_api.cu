@@ -20,6 +20,7 @@ struct fm_result {
   size_t n_pairs = 0;
   uint64_t total = 0;
   uint32_t flags = 0;
+  float ratio = 1.f;
   std::vector<uint32_t> counts;
   std::vector<uint64_t> offsets;
   DevBuf d_out, d_counts, d_dist;
@@ -145,6 +146,8 @@ int finalize(fm_result* r) {
   r->stats.scored_pairs = hc->scored_cols;
   r->stats.candidates = hc->rescore.candidates;
   r->stats.rows_rejected_early = hc->rescore.rejected_early;
+  if (r->ratio < 1.f && r->stats.rows > r->stats.rows_exact)
+    c->reject_hint = (double)hc->rescore.rejected_early / (double)(r->stats.rows - r->stats.rows_exact);
   r->stats.rows_exact += hc->redo_total;
   float acc[kNumPhases] = {0};
   for (auto& s : r->ev.spans) {
@@ -223,7 +226,7 @@ void fm_destroy(fm_ctx* c) {
   cudaStreamSynchronize(c->stream);
   c->arena.release();
   DevBuf* bufs[] = {&c->s_keys, &c->s_keys_sorted, &c->s_idx, &c->s_idx_sorted, &c->s_norm2, &c->s_sort, &c->s_segs, &c->d_images, &c->d_metas, &c->d_meta_blob, &c->d_rowres, &c->d_rowdist, &c->d_chunk_status,
-                    &c->d_totals, &c->d_bands, &c->d_cands, &c->d_redo, &c->d_taskinfo, &c->d_all, &c->d_all_tasks};
+                    &c->d_totals, &c->d_bands, &c->d_cands, &c->d_redo, &c->d_taskinfo, &c->d_rowstat, &c->d_need, &c->d_all, &c->d_all_tasks};
   for (auto* b : bufs) b->release();
   for (auto& b : c->out_free) b.release();
   for (auto& b : c->counts_free) b.release();
@@ -417,6 +420,7 @@ int fm_match(fm_ctx* c, const uint32_t* pair_first, const uint32_t* pair_second,
   r->ctx = c;
   r->n_pairs = n_pairs;
   r->flags = flags;
+  r->ratio = dist2second;
   r->d_out = take_buf(c->out_free, std::max<uint64_t>(total_rows, 1) * sizeof(uint2));
   r->d_counts = take_buf(c->counts_free, std::max<size_t>(n_pairs, 1) * sizeof(uint32_t));
   const bool want_dist = (flags & FM_FLAG_DISTANCES) && !match_all;
@@ -553,6 +557,18 @@ int fm_match(fm_ctx* c, const uint32_t* pair_first, const uint32_t* pair_second,
     FM_CUDA_R(cudaStreamSynchronize(c->stream));
   } else {
     Span total_span(&c->ev_match, c->stream, kPhTotal);
+    // Two-phase scoring (score_kernel kVar 1 / 2) pays only when nearly every row fails the reference's ratio test --
+    // images with little in common at -d2 < 1 -- and costs ~60 % extra otherwise.  So it is used when the previous
+    // call of this kind on this context rejected >= 99 % of its rows, or, inside a synchronous multi-batch call, once
+    // the first batch (single pass) has shown that much.
+    constexpr double kTwoPhaseMin = 0.99;
+    const bool two_phase_possible = dist2second < 1.f && segs == 1 && !force_exact;
+    bool two_phase = two_phase_possible && c->reject_hint >= kTwoPhaseMin;
+    bool probed = false;
+    if (g_debug.two_phase >= 0) {  // test hook: force the choice
+      two_phase = two_phase_possible && g_debug.two_phase != 0;
+      probed = true;
+    }
     for (size_t bi = 0; bi < batches.size(); bi++) {
       const Batch& b = batches[bi];
       const uint32_t nt = b.t1 - b.t0;
@@ -574,6 +590,7 @@ int fm_match(fm_ctx* c, const uint32_t* pair_first, const uint32_t* pair_second,
         fa.ratio = dist2second;
         fa.rowres = d_rowres;
         fa.rowdist = d_rowdist;
+        fa.two_phase = two_phase;
         fa.counters = d_counters;
         cudaError_t e = fast_match_batch(c, fa);
         if (e != cudaSuccess) {
@@ -612,6 +629,15 @@ int fm_match(fm_ctx* c, const uint32_t* pair_first, const uint32_t* pair_second,
         if (want_dist) compact_kernel<true><<<grid, kCompactThreads, 0, c->stream>>>(ca);
         else compact_kernel<false><<<grid, kCompactThreads, 0, c->stream>>>(ca);
         c->stats.kernel_launches += 1;
+      }
+      if (two_phase_possible && !two_phase && !probed && b.any_fast && !b.any_exact && bi + 1 < batches.size() &&
+          !(flags & FM_FLAG_ASYNC)) {
+        // a synchronous call with more batches to come: look at what the first one rejected
+        probed = true;
+        DeviceCounters* hc = reinterpret_cast<DeviceCounters*>(r->h_block);
+        FM_CUDA_R(cudaMemcpyAsync(hc, c->d_totals.p, sizeof(DeviceCounters), cudaMemcpyDeviceToHost, c->stream));
+        FM_CUDA_R(cudaStreamSynchronize(c->stream));
+        two_phase = (double)hc->rescore.rejected_early >= kTwoPhaseMin * (double)b.rows;
       }
     }
   }
@@ -743,6 +769,7 @@ int fm_debug_set_option(const char* name, int value) {
   if (!strcmp(name, "probe")) g_debug.probe = value;
   else if (!strcmp(name, "variant")) g_debug.variant = value;
   else if (!strcmp(name, "pre_tiles")) g_debug.pre_tiles = value;
+  else if (!strcmp(name, "two_phase")) g_debug.two_phase = value;
   else return FM_ERR_INVALID;
   return FM_OK;
 }
@@ -806,7 +833,7 @@ int fm_debug_score_unit(fm_ctx* c, uint32_t first_img, uint32_t second_img, uint
                                               c->d_bands.as<uint2>());
   score_kernel<true, 0, 0><<<1, kScoreThreads, kScoreSmemBytes, c->stream>>>(
       c->d_images.as<ImageDev>(), d_task.as<Task>(), d_meta.as<uint32_t>() + 2, 1, 1, c->d_bands.as<uint2>(),
-      c->d_cands.as<Cand>(), nullptr, d_dump.as<float>(), ld, row_block, 0);
+      c->d_cands.as<Cand>(), nullptr, d_dump.as<float>(), ld, row_block, 0, 0.f, 0.f, nullptr, nullptr);
   FM_CUDA(c, cudaGetLastError());
   FM_CUDA(c, cudaStreamSynchronize(c->stream));
   const uint32_t r0 = row_block * kUnitRows, nr = std::min<uint32_t>(kUnitRows, nB - r0);

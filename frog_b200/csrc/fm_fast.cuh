@@ -112,6 +112,7 @@ struct DebugOptions {
   int probe = 0;       // 1 | 2: timing-attribution builds of score_kernel (results are garbage)
   int variant = 0;     // experiment builds of score_kernel (results are exact)
   int pre_tiles = -1;  // look-ahead depth override; -1 = kPreTiles
+  int two_phase = -1;  // two-phase scoring: -1 = the library decides (fm_api.cu), 0 = never, 1 = whenever it is applicable
 };
 inline DebugOptions g_debug;
 
@@ -128,6 +129,7 @@ struct FastBatchArgs {
   float thr, ratio;
   uint32_t* rowres;
   float* rowdist;  // null unless FM_FLAG_DISTANCES
+  bool two_phase;  // reject pass + capture pass instead of the single pass (see score_kernel)
   DeviceCounters* counters;
 };
 
@@ -136,6 +138,10 @@ inline cudaError_t fast_match_batch(fm_ctx* c, const FastBatchArgs& a) {
   if ((e = c->d_bands.ensure((size_t)a.rows * sizeof(uint2))) != cudaSuccess) return e;
   if ((e = c->d_cands.ensure((size_t)a.rows * a.segs * kTopK * sizeof(Cand))) != cudaSuccess) return e;
   if ((e = c->d_redo.ensure((size_t)a.rows * sizeof(uint2))) != cudaSuccess) return e;
+  if (a.two_phase) {
+    if ((e = c->d_rowstat.ensure((size_t)a.rows)) != cudaSuccess) return e;
+    if ((e = c->d_need.ensure((size_t)a.units * kEpiWarps)) != cudaSuccess) return e;
+  }
   if (!c->score_attr_set) {
     // two CTAs per SM: ask for the full shared-memory carveout
     auto prep = [](auto kern) -> cudaError_t {
@@ -144,11 +150,14 @@ inline cudaError_t fast_match_batch(fm_ctx* c, const FastBatchArgs& a) {
       return cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     };
     if ((e = prep(score_kernel<false, 0, 0>)) != cudaSuccess) return e;
+    if ((e = prep(score_kernel<false, 0, 1>)) != cudaSuccess) return e;
+    if ((e = prep(score_kernel<false, 0, 2>)) != cudaSuccess) return e;
     if ((e = prep(score_kernel<false, 1, 0>)) != cudaSuccess) return e;
     if ((e = prep(score_kernel<false, 2, 0>)) != cudaSuccess) return e;
     if ((e = prep(score_kernel<true, 0, 0>)) != cudaSuccess) return e;
     c->score_attr_set = true;
   }
+  bool two_phase_ran = false;
   {
     Span sp(&c->ev_match, c->stream, kPhBands);
     bands_kernel<<<a.blocks128, 128, 0, c->stream>>>(a.images, a.tasks, a.blk_off, a.n_tasks, c->d_bands.as<uint2>());
@@ -161,15 +170,31 @@ inline cudaError_t fast_match_batch(fm_ctx* c, const FastBatchArgs& a) {
     const uint32_t pre_tiles = g_debug.pre_tiles >= 0 ? (uint32_t)g_debug.pre_tiles : kPreTiles;
     auto kern = probe == 1 ? score_kernel<false, 1, 0> : probe == 2 ? score_kernel<false, 2, 0> : score_kernel<false, 0, 0>;
     (void)var;
-    kern<<<a.units, kScoreThreads, kScoreSmemBytes, c->stream>>>(
-        a.images, a.tasks, a.unit_off, a.n_tasks, a.segs, c->d_bands.as<uint2>(), c->d_cands.as<Cand>(),
-        &a.counters->scored_cols, nullptr, 0, 0, pre_tiles);
+    uint8_t* rowstat = a.two_phase ? c->d_rowstat.as<uint8_t>() : nullptr;
+    uint8_t* need = a.two_phase ? c->d_need.as<uint8_t>() : nullptr;
+    if (a.two_phase && probe == 0) {
+      score_kernel<false, 0, 1><<<a.units, kScoreThreads, kScoreSmemBytes, c->stream>>>(
+          a.images, a.tasks, a.unit_off, a.n_tasks, a.segs, c->d_bands.as<uint2>(), c->d_cands.as<Cand>(),
+          &a.counters->scored_cols, nullptr, 0, 0, 0, a.thr, a.ratio, rowstat, need);
+      score_kernel<false, 0, 2><<<a.units, kScoreThreads, kScoreSmemBytes, c->stream>>>(
+          a.images, a.tasks, a.unit_off, a.n_tasks, a.segs, c->d_bands.as<uint2>(), c->d_cands.as<Cand>(),
+          &a.counters->scored_cols, nullptr, 0, 0, pre_tiles, a.thr, a.ratio, rowstat, need);
+      c->stats.kernel_launches += 1;
+      c->stats.two_phase_batches += 1;
+    } else {
+      rowstat = nullptr;
+      kern<<<a.units, kScoreThreads, kScoreSmemBytes, c->stream>>>(
+          a.images, a.tasks, a.unit_off, a.n_tasks, a.segs, c->d_bands.as<uint2>(), c->d_cands.as<Cand>(),
+          &a.counters->scored_cols, nullptr, 0, 0, pre_tiles, a.thr, a.ratio, nullptr, nullptr);
+    }
+    two_phase_ran = rowstat != nullptr;
   }
   {
     Span sp(&c->ev_match, c->stream, kPhRescore);
     rescore_kernel<<<a.blocks128, 128, 0, c->stream>>>(a.images, a.tasks, a.blk_off, a.n_tasks, a.segs,
                                                        c->d_cands.as<Cand>(), a.thr, a.ratio, a.rowres,
-                                                       c->d_redo.as<uint2>(), &a.counters->rescore, a.rowdist);
+                                                       c->d_redo.as<uint2>(), &a.counters->rescore, a.rowdist,
+                                                       two_phase_ran ? c->d_rowstat.as<uint8_t>() : nullptr);
     exact_rows_kernel<<<c->sm_count, kRedoThreads, 0, c->stream>>>(a.images, a.tasks, c->d_bands.as<uint2>(), c->d_redo.as<uint2>(),
                                                              &a.counters->rescore, a.thr, a.ratio, a.rowres, a.rowdist);
     fold_redo_kernel<<<1, 1, 0, c->stream>>>(a.counters);

@@ -58,7 +58,8 @@ __global__ void __launch_bounds__(128, 6)
 rescore_kernel(const ImageDev* __restrict__ images, const Task* __restrict__ tasks,
                const uint32_t* __restrict__ task_blk_off, uint32_t n_tasks, uint32_t segs,
                const Cand* __restrict__ cands, float thr, float ratio, uint32_t* __restrict__ rowres,
-               uint2* __restrict__ redo_list, RescoreCounters* __restrict__ counters, float* __restrict__ rowdist) {
+               uint2* __restrict__ redo_list, RescoreCounters* __restrict__ counters, float* __restrict__ rowdist,
+               const uint8_t* __restrict__ rowstat) {
   const uint32_t t = find_segment_near(task_blk_off, n_tasks, blockIdx.x, gridDim.x);
   const Task task = tasks[t];
   if (task.flags & kTaskExact) return;
@@ -69,6 +70,10 @@ rescore_kernel(const ImageDev* __restrict__ images, const Task* __restrict__ tas
   const uint32_t row = B.perm[s];
   const float eps = task_eps(A.meta, B.meta);
 
+  // Two-phase path: the reject pass of the scoring kernel has already proven most rows unacceptable (rowstat = 1);
+  // their candidate lists were never written.
+  const bool pre_rejected = rowstat != nullptr && rowstat[task.row_off + s] != 0;
+
   // Candidate lists (one per column segment) hold every column whose score exceeded the list's
   // final capture threshold g2 - 2 eps <= (row's 2nd best) - 2 eps, unsorted; a +inf marker in
   // any list means that list overflowed.
@@ -76,16 +81,18 @@ rescore_kernel(const ImageDev* __restrict__ images, const Task* __restrict__ tas
   const Cand* c = cands + (size_t)(task.row_off + s) * L;
   float a1 = -INFINITY, a2 = -INFINITY;
   bool overflow = false;
-  for (uint32_t e = 0; e < L; e++) {
-    const float v = c[e].t;
-    if (v == INFINITY) overflow = true;
-    else if (v > a1) { a2 = a1; a1 = v; }
-    else if (v > a2) { a2 = v; }
+  if (!pre_rejected) {
+    for (uint32_t e = 0; e < L; e++) {
+      const float v = c[e].t;
+      if (v == INFINITY) overflow = true;
+      else if (v > a1) { a2 = a1; a1 = v; }
+      else if (v > a2) { a2 = v; }
+    }
   }
   const float band = a2 - 2.f * eps;  // -inf when the row has fewer than two candidates
   // A truncated list dropped columns scoring <= its smallest kept entry: still complete iff that
   // entry is below the band.
-  for (uint32_t g = 0; g < segs && !overflow; g++) {
+  for (uint32_t g = 0; g < segs && !overflow && !pre_rejected; g++) {
     const Cand* l = c + g * kTopK;
     if (l[0].t > -INFINITY && (l[0].col & kCandTruncated)) {
       float lowest = l[0].t;
@@ -94,25 +101,11 @@ rescore_kernel(const ImageDev* __restrict__ images, const Task* __restrict__ tas
     }
   }
 
-  // Early rejection, certified.  With na = |a|^2 of the row, a column's squared distance is na - 2t, and the
-  // reference's FP32 value of it lies within `margin` of na - 2t~ (2 eps for the score, the rest for the FP32
-  // evaluation of na here and of the distance there).  The lists hold the row's two best approximate scores
-  // a1 >= a2, so   d1_ref >= d1_lo = na - 2 a1 - margin   and   d2_ref <= d2_hi = na - 2 a2 + margin.
-  //   * d1_lo > thr^2 (1 + 1e-5)            =>  sqrtf(d1) < thr is false                      (match.cpp:321)
-  //   * d1_lo > ratio^2 d2_hi (1 + 1e-4)    =>  sqrtf(d1 / d2) < ratio is false, and d2 != FLT_MAX because a
-  //                                              second gated-in column exists                 (match.cpp:320)
-  // Either way the row emits nothing and no exact distance has to be gathered: with -d2 0.8 on unrelated images
-  // that is almost every row.  (ratio >= 1 can never trigger the second test: a1 >= a2.)
-  bool rejected = false;
-  if (!overflow && a1 > -INFINITY) {
-    const float na = B.norm2_sorted[s];
-    const float margin = 2.f * eps + 1e-5f * (na + 4.f);
-    const float d1_lo = na - 2.f * a1 - margin;
-    const float d2_hi = na - 2.f * a2 + margin;
-    const float thr2 = thr * thr;
-    rejected = d1_lo > thr2 * 1.00001f;
-    if (a2 > -INFINITY && d2_hi > 0.f && ratio < 1.0e4f) rejected = rejected || d1_lo > ratio * ratio * d2_hi * 1.0001f;
-  }
+  // Early rejection, certified (certified_reject, fm_score.cuh): the lists hold the row's two best approximate scores
+  // a1 >= a2, and when the reference's ratio or threshold test must fail for them the row emits nothing and no exact
+  // distance has to be gathered: with -d2 0.8 on unrelated images that is almost every row.
+  bool rejected = pre_rejected;
+  if (!pre_rejected && !overflow && a1 > -INFINITY) rejected = certified_reject(B.norm2_sorted[s], a1, a2, eps, thr, ratio);
 
   uint32_t match = kNone;
   uint32_t n_eval = 0;

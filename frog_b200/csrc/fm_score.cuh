@@ -123,6 +123,23 @@ __device__ __forceinline__ float task_eps(const ImageMeta* ma, const ImageMeta* 
   return 1.01f * (na * db + da * nb + da * db) + 3e-5f * fmaxf(1.f, fmaxf(ma->max_norm2, mb->max_norm2));
 }
 
+// Certified early rejection (used by the reject pass here and by rescore_kernel).  With na = |a|^2 of the row, a
+// column's squared distance is na - 2t, and the reference's FP32 value of it lies within `margin` of na - 2t~ (2 eps
+// for the score, the rest for the FP32 evaluation of na and of the distance).  For a1 = the row's best approximate
+// score and a2 <= its second best:   d1_ref >= d1_lo = na - 2 a1 - margin,   d2_ref <= d2_hi = na - 2 a2 + margin.
+//   * d1_lo > thr^2 (1 + 1e-5)            =>  sqrtf(d1) < thr is false                               (match.cpp:321)
+//   * d1_lo > ratio^2 d2_hi (1 + 1e-4)    =>  sqrtf(d1 / d2) < ratio is false, and d2 != FLT_MAX because a second
+//                                              gated-in column exists (a2 > -inf)                     (match.cpp:320)
+// Either way the row emits nothing.  (ratio >= 1 can never trigger the second test: a1 >= a2.)
+__device__ __forceinline__ bool certified_reject(float na, float a1, float a2, float eps, float thr, float ratio) {
+  const float margin = 2.f * eps + 1e-5f * (na + 4.f);
+  const float d1_lo = na - 2.f * a1 - margin;
+  const float d2_hi = na - 2.f * a2 + margin;
+  bool rejected = d1_lo > thr * thr * 1.00001f;
+  if (a2 > -INFINITY && d2_hi > 0.f && ratio < 1.0e4f) rejected = rejected || d1_lo > ratio * ratio * d2_hi * 1.0001f;
+  return rejected;
+}
+
 // Per-row scan state (registers of the row's epilogue thread).
 //   g1 >= g2 : the two largest 16-column chunk maxima seen so far.  They belong to two distinct
 //              columns, so g2 <= (row's second-best score) at any time, and
@@ -330,6 +347,18 @@ __device__ __forceinline__ void score_pair(const uint32_t (&ra)[16], const uint3
   }
 }
 
+// Reject pass (kMode 1): the two largest 16-column chunk maxima only -- no threshold, no capture, no vote.
+template <bool kMasked>
+__device__ __forceinline__ void max_pair(const uint32_t (&ra)[16], const uint32_t (&rb)[16], uint32_t col0, uint32_t lo,
+                                         uint32_t width, RowScan& st) {
+  float fa[16], fb[16];
+  const ChunkMax a = chunk_max<kMasked>(ra, col0, lo, width, fa);
+  const ChunkMax b = chunk_max<kMasked>(rb, col0 + 16, lo, width, fb);
+  const float hi = fmaxf(a.m, b.m), lw = fminf(a.m, b.m);
+  st.g2 = max3(st.g2, lw, fminf(st.g1, hi));
+  st.g1 = fmaxf(st.g1, hi);
+}
+
 // One 64-column accumulator tile of one row: two pairs of TMEM loads.
 template <bool kMasked, bool kDump, int kProbe, int kVar>
 __device__ __forceinline__ void score_tile(uint32_t taddr, uint32_t cb, uint32_t lo, uint32_t width, RowScan& st,
@@ -355,7 +384,8 @@ __device__ __forceinline__ void score_tile(uint32_t taddr, uint32_t cb, uint32_t
         dump_row[cb + (c + 1) * 16 + e] = __uint_as_float(rb[e]);
       }
     }
-    score_pair<kMasked, kProbe, kVar>(ra, rb, cb + c * 16, lo, width, st, two_eps, upd, cap);
+    if (kVar == 1) max_pair<kMasked>(ra, rb, cb + c * 16, lo, width, st);
+    else score_pair<kMasked, kProbe, kVar>(ra, rb, cb + c * 16, lo, width, st, two_eps, upd, cap);
   }
 }
 
@@ -368,7 +398,18 @@ __device__ __forceinline__ void score_tile(uint32_t taddr, uint32_t cb, uint32_t
 // dump (kDump only): [256][dump_ld] raw t of the unit.
 // kProbe (performance attribution only, results are garbage): 1 = capture threshold pinned at +inf,
 // i.e. the max-tree fast path alone; 2 = epilogue skips the TMEM loads too (TMA + MMA pipeline alone).
-// kVar: slot for experiment builds (fm_debug_set_option("variant")); none is compiled in at present.  Tried and
+// kVar = mode of the TWO-PHASE path (fm_fast.cuh decides when to use it; 0 = the ordinary single pass):
+//   1  reject pass: every tile is scored but the epilogue only keeps each row's two largest chunk maxima g1 >= g2
+//      (a third of the single pass's instructions).  g1 is the row's best approximate score a1 and g2 <= a2, so the
+//      certified rejection test of the rescoring kernel (fm_rescore.cuh: the reference's ratio / threshold test must
+//      fail) can be made from them alone.  Writes rowstat[row] = 1 for rejected rows and, per epilogue warp of the
+//      unit, whether any of its rows survived (`need`).
+//   2  capture pass: the ordinary pass, run only by the warps whose `need` flag is set -- a unit none of whose
+//      warps needs it leaves at once, a warp that does not need it only hands its accumulators back, and the
+//      CTA's column range shrinks to the bands of the warps that do.
+// With -d2 < 1 on images that have little in common nearly every row is rejected (random descriptors at -d2 0.8:
+// 99.9 %), and the capture pass all but disappears.
+// Experiments tried and
 // dropped in round 2, all measured on C2 (profiles/r2_summary.md): nanosleep back-off in the two single-thread warps
 // (no change: their polling does not take issue slots the epilogue needs), testing against the previous step's
 // threshold to shorten the compare -> vote chain (-1 %), and loading the second half of a tile under the processing
@@ -378,7 +419,8 @@ __global__ void __launch_bounds__(kScoreThreads, 2)
 score_kernel(const ImageDev* __restrict__ images, const Task* __restrict__ tasks,
              const uint32_t* __restrict__ unit_off, uint32_t n_tasks, uint32_t segs,
              const uint2* __restrict__ bands, Cand* __restrict__ cands, unsigned long long* __restrict__ scored_cols,
-             float* __restrict__ dump, uint32_t dump_ld, uint32_t unit_base, uint32_t pre_tiles) {
+             float* __restrict__ dump, uint32_t dump_ld, uint32_t unit_base, uint32_t pre_tiles,
+             float thr, float ratio, uint8_t* __restrict__ rowstat, uint8_t* __restrict__ need) {
   extern __shared__ uint8_t smem_raw[];
   ScoreSmem& sm = *reinterpret_cast<ScoreSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
 
@@ -402,6 +444,13 @@ score_kernel(const ImageDev* __restrict__ images, const Task* __restrict__ tasks
     uint2 bd = bands[task.row_off + s];
     lo = bd.x;
     hi = bd.y;
+  }
+  // capture pass of the two-phase path: only the warps the reject pass left with surviving rows take part
+  bool need_w = true;
+  if (kVar == 2) {
+    need_w = is_epi && need[(size_t)unit * kEpiWarps + (warp - 2)] != 0;
+    if (!__syncthreads_or(need_w)) return;  // CTA-uniform: no row of this unit survived
+    if (!need_w) { lo = 0; hi = 0; }         // stays out of the column ranges below, skips every tile, writes nothing
   }
   // warp-level and CTA-level column ranges
   uint32_t w_cmin = (hi > lo) ? lo : 0xFFFFFFFFu, w_cmax = (hi > lo) ? hi : 0u;
@@ -430,7 +479,7 @@ score_kernel(const ImageDev* __restrict__ images, const Task* __restrict__ tasks
   // ONE row costs its whole warp the slow path.  Visiting the first tiles once without capturing establishes
   // the threshold of a 64 * n_pre column prefix before the first column is captured: a few tiles of extra
   // MMA work (the tensor pipe has slack) for about a third fewer slow-path entries and no list overflow handling.
-  const uint32_t n_pre = min(pre_tiles, n_tiles / 4);  // (the single-unit debug launch passes pre_tiles = 0)
+  const uint32_t n_pre = kVar == 1 ? 0u : min(pre_tiles, n_tiles / 4);  // (the single-unit debug launch passes pre_tiles = 0)
   const uint32_t n_sched = n_tiles + n_pre;
 
   RowScan st;
@@ -548,7 +597,22 @@ score_kernel(const ImageDev* __restrict__ images, const Task* __restrict__ tasks
     }
   }
 
-  if (is_epi && s < B.n) {
+  if (kVar == 1) {
+    // Reject pass: certified rejection from (g1, g2) -- the same test rescore_kernel applies to (a1, a2); g1 = a1 and
+    // g2 <= a2, so d2_hi only gets larger (harder to reject).  A row with no gated-in column has nothing to emit.
+    if (is_epi) {
+      bool rejected = true;
+      if (s < B.n && st.g1 > -INFINITY) {
+        const float eps = task_eps(A.meta, B.meta);
+        rejected = certified_reject(B.norm2_sorted[s], st.g1, st.g2, eps, thr, ratio);
+      }
+      if (s < B.n) rowstat[task.row_off + s] = rejected ? 1 : 0;
+      const bool all_rejected = __all_sync(0xffffffffu, rejected);
+      if (lane == 0) need[(size_t)unit * kEpiWarps + (warp - 2)] = all_rejected ? 0 : 1;
+    }
+    return;
+  }
+  if (is_epi && s < B.n && need_w) {
     // Final list: the entries above the final threshold.
     uint32_t cnt = st.ovf ? 0u : cap_compress(st.cap, min((st.capw - st.cap) / kCapStride, (uint32_t)kCapSlots), st.thr);
     uint32_t trunc = 0;

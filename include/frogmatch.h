@@ -148,7 +148,8 @@ typedef struct fm_stats {
   float ms_exact;             /* ... exact brute-force kernel */
   float ms_compact;           /* ... stream compaction */
   float ms_prep;              /* CUDA-event time of all uploads' prep kernels since the last clear */
-  uint64_t rows_rejected_early; /* rows the rescoring kernel proved unacceptable from their approximate scores (no exact distance evaluated) */
+  uint64_t rows_rejected_early; /* rows proven unacceptable from their approximate scores (no exact distance evaluated) */
+  uint64_t two_phase_batches;   /* batches scored in two phases (reject pass, then capture pass for the surviving rows' warps) */
 } fm_stats;
 
 /* Statistics of the most recent fm_match on this context (synchronises the stream). */

@@ -39,6 +39,8 @@ int fm_debug_score_unit(fm_ctx* ctx, uint32_t first_img, uint32_t second_img, ui
  *   "probe"     1 | 2   timing-attribution builds of the scoring kernel -- results are GARBAGE
  *   "variant"   n       experiment builds of the scoring kernel -- results stay exact
  *   "pre_tiles" n       look-ahead depth of the scoring kernel (-1 = built-in default)
+ *   "two_phase" -1|0|1  two-phase scoring (reject pass + capture pass): library's choice / never / whenever applicable
+ *                       -- results are exact either way
  * Returns FM_ERR_INVALID for an unknown name.  Nothing reads environment variables.
  */
 int fm_debug_set_option(const char* name, int value);

@@ -293,3 +293,71 @@ def test_distances_side_output(env, force_exact):
                 exp = O.norm_matrix_numpy(a[ri], b)[np.arange(ri.shape[0]), ci]
                 assert np.array_equal(dist[n_fwd:].view(np.uint32), exp.view(np.uint32))
         res.free()
+
+
+def _group(kind, n_images, n_points):
+    kps = [synth.make(kind, n_points, i) for i in range(n_images)]
+    return [(k.desc, k.scale, k.lap) for k in kps]
+
+
+def _fast_oracle_lists(images, pf, ps, thr, rat):
+    fast = O.FastLib()
+    return [fast.compute_matches(images[i], images[j], thr, rat) for i, j in zip(pf, ps)]
+
+
+@pytest.mark.parametrize("kind,thr,rat", [("iid", 1.0, 0.8), ("bank", 1.0, 0.8), ("bank", 0.22, 0.9), ("bank", 0.5, 0.998),
+                                          ("iid", 1.0, 0.5), ("bank", 1e10, 0.95)])
+def test_two_phase_scoring_forced(built, kind, thr, rat):
+    """Two-phase scoring (reject pass from the two best chunk maxima, capture pass for the warps with surviving rows)
+    forced on: lists bit-identical to the oracle whether nearly every row is rejected (iid) or most survive (bank)."""
+    images = _group(kind, 6, 12000)
+    images[3] = tuple(x[:7777] for x in images[3])  # ragged
+    pf = [i for i in range(6) for j in range(i + 1, 6)]
+    ps = [j for i in range(6) for j in range(i + 1, 6)]
+    want = _fast_oracle_lists(images, pf, ps, thr, rat)
+    m = capi.Matcher(0)
+    try:
+        capi.debug_set_option("two_phase", 1)
+        for i, (d, s, l) in enumerate(images):
+            m.upload(i, d, s, l)
+        res = m.match(pf, ps, thr, rat)
+        got, st = res.all_pairs(), m.stats()
+        res.free()
+    finally:
+        capi.debug_set_option("two_phase", -1)
+        m.close()
+    assert st["two_phase_batches"] >= 1 and st["rows_exact"] < 0.01 * st["rows"]
+    for p, (g, w) in enumerate(zip(got, want)):
+        assert np.array_equal(g, w), f"pair {p}: {g.shape[0]} vs {w.shape[0]}"
+    if kind == "iid":
+        assert st["rows_rejected_early"] > 0.98 * st["rows"]
+    else:
+        assert sum(w.shape[0] for w in want) > 1000
+
+
+def test_two_phase_scoring_is_chosen_from_what_the_data_shows(built):
+    """The library switches to two-phase scoring only after a call at -d2 < 1 rejected >= 99 % of its rows (random
+    descriptors), never for data with real correspondences, never at -d2 >= 1; results identical throughout."""
+    pf = [i for i in range(6) for j in range(i + 1, 6)]
+    ps = [j for i in range(6) for j in range(i + 1, 6)]
+    for kind, expect_switch in (("iid", True), ("bank", False)):
+        images = _group(kind, 6, 12000)
+        want = _fast_oracle_lists(images, pf, ps, 1.0, 0.8)
+        m = capi.Matcher(0)
+        try:
+            for i, (d, s, l) in enumerate(images):
+                m.upload(i, d, s, l)
+            used = []
+            for call in range(3):
+                res = m.match(pf, ps, 1.0, 0.8)
+                got, st = res.all_pairs(), m.stats()
+                res.free()
+                used.append(st["two_phase_batches"])
+                for g, w in zip(got, want):
+                    assert np.array_equal(g, w)
+            assert used[0] == 0 and (used[1] >= 1 and used[2] >= 1) == expect_switch, used
+            res = m.match(pf, ps, 1.0, 1.0)  # -d2 1: the ratio test cannot be decided from approximate scores
+            assert m.stats()["two_phase_batches"] == 0
+            res.free()
+        finally:
+            m.close()
