@@ -226,7 +226,7 @@ void fm_destroy(fm_ctx* c) {
   cudaStreamSynchronize(c->stream);
   c->arena.release();
   DevBuf* bufs[] = {&c->s_keys, &c->s_keys_sorted, &c->s_idx, &c->s_idx_sorted, &c->s_norm2, &c->s_sort, &c->s_segs, &c->d_images, &c->d_metas, &c->d_meta_blob, &c->d_rowres, &c->d_rowdist, &c->d_chunk_status,
-                    &c->d_totals, &c->d_bands, &c->d_cands, &c->d_redo, &c->d_taskinfo, &c->d_rowstat, &c->d_need, &c->d_all, &c->d_all_tasks};
+                    &c->d_totals, &c->d_bands, &c->d_cands, &c->d_redo, &c->d_taskinfo, &c->d_rowstat, &c->d_surv, &c->d_all, &c->d_all_tasks};
   for (auto* b : bufs) b->release();
   for (auto& b : c->out_free) b.release();
   for (auto& b : c->counts_free) b.release();
@@ -770,6 +770,7 @@ int fm_debug_set_option(const char* name, int value) {
   else if (!strcmp(name, "variant")) g_debug.variant = value;
   else if (!strcmp(name, "pre_tiles")) g_debug.pre_tiles = value;
   else if (!strcmp(name, "two_phase")) g_debug.two_phase = value;
+  else if (!strcmp(name, "surv_cap")) g_debug.surv_cap = value;
   else return FM_ERR_INVALID;
   return FM_OK;
 }
@@ -833,7 +834,7 @@ int fm_debug_score_unit(fm_ctx* c, uint32_t first_img, uint32_t second_img, uint
                                               c->d_bands.as<uint2>());
   score_kernel<true, 0, 0><<<1, kScoreThreads, kScoreSmemBytes, c->stream>>>(
       c->d_images.as<ImageDev>(), d_task.as<Task>(), d_meta.as<uint32_t>() + 2, 1, 1, c->d_bands.as<uint2>(),
-      c->d_cands.as<Cand>(), nullptr, d_dump.as<float>(), ld, row_block, 0, 0.f, 0.f, nullptr, nullptr);
+      c->d_cands.as<Cand>(), nullptr, d_dump.as<float>(), ld, row_block, 0, 0.f, 0.f, nullptr, nullptr, nullptr);
   FM_CUDA(c, cudaGetLastError());
   FM_CUDA(c, cudaStreamSynchronize(c->stream));
   const uint32_t r0 = row_block * kUnitRows, nr = std::min<uint32_t>(kUnitRows, nB - r0);

@@ -50,6 +50,12 @@ struct ImageDev {
   const ImageMeta* meta;
 };
 
+// Byte offset of (row r, 16-byte chunk q) inside a 128 x 128 B SWIZZLE_128B K-major tile:
+// 8-row x 128 B atoms, chunk index XORed with (row mod 8)  [cute Swizzle<3,4,3>].
+__host__ __device__ __forceinline__ uint32_t sw128_offset(uint32_t r, uint32_t q) {
+  return r * 128u + ((q ^ (r & 7u)) << 4);
+}
+
 // One directed ComputeMatches call: rows of `row_img` scan columns of `col_img`.
 struct Task {
   uint32_t col_img;  // image `first`  (points2 in match.cpp:255) unless swap

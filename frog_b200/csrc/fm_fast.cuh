@@ -112,6 +112,7 @@ struct DebugOptions {
   int probe = 0;       // 1 | 2: timing-attribution builds of score_kernel (results are garbage)
   int variant = 0;     // experiment builds of score_kernel (results are exact)
   int pre_tiles = -1;  // look-ahead depth override; -1 = kPreTiles
+  int surv_cap = -1;   // two-phase scoring: survivor-unit capacity override (tests of the overflow route); -1 = built-in
   int two_phase = -1;  // two-phase scoring: -1 = the library decides (fm_api.cu), 0 = never, 1 = whenever it is applicable
 };
 inline DebugOptions g_debug;
@@ -138,9 +139,13 @@ inline cudaError_t fast_match_batch(fm_ctx* c, const FastBatchArgs& a) {
   if ((e = c->d_bands.ensure((size_t)a.rows * sizeof(uint2))) != cudaSuccess) return e;
   if ((e = c->d_cands.ensure((size_t)a.rows * a.segs * kTopK * sizeof(Cand))) != cudaSuccess) return e;
   if ((e = c->d_redo.ensure((size_t)a.rows * sizeof(uint2))) != cudaSuccess) return e;
+  // two-phase scoring: survivor units the capture pass is launched with (an upper bound; a hundred times what the
+  // >= 99 %-rejection regime needs, and never more than there could be)
+  const uint32_t cap_units = g_debug.surv_cap > 0 ? (uint32_t)g_debug.surv_cap
+                                                  : std::min<uint32_t>(a.units + a.n_tasks, std::max<uint32_t>(1024u, 4u * a.n_tasks));
   if (a.two_phase) {
     if ((e = c->d_rowstat.ensure((size_t)a.rows)) != cudaSuccess) return e;
-    if ((e = c->d_need.ensure((size_t)a.units * kEpiWarps)) != cudaSuccess) return e;
+    if ((e = c->d_surv.ensure(((size_t)a.rows + 2 * (size_t)a.n_tasks + 2) * sizeof(uint32_t))) != cudaSuccess) return e;
   }
   if (!c->score_attr_set) {
     // two CTAs per SM: ask for the full shared-memory carveout
@@ -171,26 +176,34 @@ inline cudaError_t fast_match_batch(fm_ctx* c, const FastBatchArgs& a) {
     auto kern = probe == 1 ? score_kernel<false, 1, 0> : probe == 2 ? score_kernel<false, 2, 0> : score_kernel<false, 0, 0>;
     (void)var;
     uint8_t* rowstat = a.two_phase ? c->d_rowstat.as<uint8_t>() : nullptr;
-    uint8_t* need = a.two_phase ? c->d_need.as<uint8_t>() : nullptr;
     if (a.two_phase && probe == 0) {
+      // d_surv: survivor counts per task | survivor-unit prefix per task (+1) | survivor lists, laid out like the rows
+      uint32_t* surv_count = c->d_surv.as<uint32_t>();
+      uint32_t* surv_off = surv_count + a.n_tasks;
+      uint32_t* surv_rows = surv_off + a.n_tasks + 1;
+      if ((e = cudaMemsetAsync(surv_count, 0, (size_t)a.n_tasks * sizeof(uint32_t), c->stream)) != cudaSuccess) return e;
       score_kernel<false, 0, 1><<<a.units, kScoreThreads, kScoreSmemBytes, c->stream>>>(
           a.images, a.tasks, a.unit_off, a.n_tasks, a.segs, c->d_bands.as<uint2>(), c->d_cands.as<Cand>(),
-          &a.counters->scored_cols, nullptr, 0, 0, 0, a.thr, a.ratio, rowstat, need);
-      score_kernel<false, 0, 2><<<a.units, kScoreThreads, kScoreSmemBytes, c->stream>>>(
-          a.images, a.tasks, a.unit_off, a.n_tasks, a.segs, c->d_bands.as<uint2>(), c->d_cands.as<Cand>(),
-          &a.counters->scored_cols, nullptr, 0, 0, pre_tiles, a.thr, a.ratio, rowstat, need);
-      c->stats.kernel_launches += 1;
+          &a.counters->scored_cols, nullptr, 0, 0, 0, a.thr, a.ratio, rowstat, surv_count, surv_rows);
+      surv_plan_kernel<<<1, 1024, 0, c->stream>>>(surv_count, a.n_tasks, surv_off, cap_units, a.tasks, surv_rows, rowstat,
+                                                  c->d_redo.as<uint2>(), &a.counters->rescore.redo_rows);
+      score_kernel<false, 0, 2><<<cap_units, kScoreThreads, kScoreSmemBytes, c->stream>>>(
+          a.images, a.tasks, surv_off, a.n_tasks, 1u, c->d_bands.as<uint2>(), c->d_cands.as<Cand>(),
+          &a.counters->scored_cols, nullptr, 0, 0, pre_tiles, a.thr, a.ratio, rowstat, surv_count, surv_rows);
+      c->stats.kernel_launches += 2;
       c->stats.two_phase_batches += 1;
     } else {
       rowstat = nullptr;
       kern<<<a.units, kScoreThreads, kScoreSmemBytes, c->stream>>>(
           a.images, a.tasks, a.unit_off, a.n_tasks, a.segs, c->d_bands.as<uint2>(), c->d_cands.as<Cand>(),
-          &a.counters->scored_cols, nullptr, 0, 0, pre_tiles, a.thr, a.ratio, nullptr, nullptr);
+          &a.counters->scored_cols, nullptr, 0, 0, pre_tiles, a.thr, a.ratio, nullptr, nullptr, nullptr);
     }
     two_phase_ran = rowstat != nullptr;
   }
   {
     Span sp(&c->ev_match, c->stream, kPhRescore);
+    // two-phase: rows the reject pass threw out are not touched by the rescoring kernel at all
+    if (two_phase_ran && (e = cudaMemsetAsync(a.rowres, 0xFF, (size_t)a.rows * sizeof(uint32_t), c->stream)) != cudaSuccess) return e;
     rescore_kernel<<<a.blocks128, 128, 0, c->stream>>>(a.images, a.tasks, a.blk_off, a.n_tasks, a.segs,
                                                        c->d_cands.as<Cand>(), a.thr, a.ratio, a.rowres,
                                                        c->d_redo.as<uint2>(), &a.counters->rescore, a.rowdist,

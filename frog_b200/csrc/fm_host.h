@@ -131,7 +131,7 @@ struct fm_ctx {
   fm::DevBuf d_meta_blob, d_rowres, d_rowdist, d_chunk_status, d_totals;
   uint32_t compact_epoch = 0;  // tags the look-back status words of a compaction launch (fm_compact.cuh)
   fm::DevBuf d_bands, d_cands, d_redo, d_taskinfo;
-  fm::DevBuf d_rowstat, d_need;  // two-phase scoring: per-row rejection flags, per-(unit, warp) survivors
+  fm::DevBuf d_rowstat, d_surv;  // two-phase scoring: per-row rejection flags; survivor counts / unit prefix / lists
   // Fraction of tensor-path rows the certified rejection test threw out in the most recent finished call with
   // -d2 < 1 (-1: unknown).  At >= kTwoPhaseMin the next such call scores in two phases from its first batch on.
   double reject_hint = -1.0;

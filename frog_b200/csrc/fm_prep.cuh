@@ -162,12 +162,6 @@ prep_finish_kernel(const ImageDev* __restrict__ images, const PrepSeg* __restric
   }
 }
 
-// Byte offset of (row r, 16-byte chunk q) inside a 128 x 128 B SWIZZLE_128B K-major tile:
-// 8-row x 128 B atoms, chunk index XORed with (row mod 8)  [cute Swizzle<3,4,3>].
-__host__ __device__ __forceinline__ uint32_t sw128_offset(uint32_t r, uint32_t q) {
-  return r * 128u + ((q ^ (r & 7u)) << 4);
-}
-
 // One thread per (sorted keypoint, 16-byte chunk): FP16 operand tiles for both roles.
 __global__ void __launch_bounds__(256)
 prep_pack_kernel(const ImageDev* __restrict__ images, const PrepSeg* __restrict__ segs, uint32_t n_segs,

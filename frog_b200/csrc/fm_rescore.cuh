@@ -67,12 +67,12 @@ rescore_kernel(const ImageDev* __restrict__ images, const Task* __restrict__ tas
   const ImageDev B = images[task.row_img];
   const uint32_t s = (blockIdx.x - task_blk_off[t]) * 128 + threadIdx.x;
   if (s >= B.n) return;
-  const uint32_t row = B.perm[s];
-  const float eps = task_eps(A.meta, B.meta);
-
   // Two-phase path: the reject pass of the scoring kernel has already proven most rows unacceptable (rowstat = 1);
-  // their candidate lists were never written.
+  // their candidate lists were never written, and rowres was pre-filled with kNone for the whole batch, so such a
+  // row costs this kernel one byte.
   const bool pre_rejected = rowstat != nullptr && rowstat[task.row_off + s] != 0;
+  const uint32_t row = pre_rejected ? 0u : B.perm[s];
+  const float eps = task_eps(A.meta, B.meta);
 
   // Candidate lists (one per column segment) hold every column whose score exceeded the list's
   // final capture threshold g2 - 2 eps <= (row's 2nd best) - 2 eps, unsorted; a +inf marker in
@@ -134,7 +134,7 @@ rescore_kernel(const ImageDev* __restrict__ images, const Task* __restrict__ tas
     if (accept_rule(d1, d2, thr, ratio)) match = best;
     if (rowdist) rowdist[task.row_off + row] = d1;
   }
-  rowres[task.row_off + row] = match;
+  if (!pre_rejected) rowres[task.row_off + row] = match;
   if (overflow) {
     unsigned long long slot = atomicAdd(&counters->redo_rows, 1ull);
     redo_list[slot] = make_uint2(t, s);

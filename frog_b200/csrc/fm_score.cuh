@@ -53,6 +53,7 @@ struct alignas(1024) ScoreSmem {
   uint64_t bar_accempty[2][2];  // [stage][row half]: those warps -> MMA (each row half has its own accumulators)
   uint32_t tmem_base;
   uint32_t cmin, cmax;
+  uint32_t srow[kUnitRows];       // capture pass on survivors: sorted position of each unit row (0xFFFFFFFF: none)
   uint2 cap[kCapSlots][kUnitRows];  // [slot][row]: lanes of a warp hit distinct banks whatever their slot
 };
 constexpr size_t kScoreSmemBytes = sizeof(ScoreSmem) + 1024;
@@ -103,6 +104,48 @@ bands_kernel(const ImageDev* __restrict__ images, const Task* __restrict__ tasks
   }
   if (hi < lo) hi = lo;
   bands[task.row_off + s] = make_uint2(lo, hi);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Two-phase scoring, between the passes: cut every task's survivor list (written by the reject pass) into units of
+// 256 rows.  unit_off[t] = first survivor unit of task t (n_tasks + 1 entries), clamped to `cap_units` -- the grid the
+// capture pass is launched with.  Survivors that do not fit (only when far more rows survive than two-phase scoring is
+// meant for) are marked rejected for the rescoring kernel and queued for the exact row kernel instead.
+struct RescoreCounters;
+__global__ void __launch_bounds__(1024)
+surv_plan_kernel(const uint32_t* __restrict__ surv_count, uint32_t n_tasks, uint32_t* __restrict__ unit_off,
+                 uint32_t cap_units, const Task* __restrict__ tasks, const uint32_t* __restrict__ surv_rows,
+                 uint8_t* __restrict__ rowstat, uint2* __restrict__ redo_list, unsigned long long* __restrict__ redo_rows) {
+  __shared__ unsigned long long s_part[1024];
+  const uint32_t per = (n_tasks + 1023u) / 1024u;
+  const uint32_t t0 = min(n_tasks, threadIdx.x * per), t1 = min(n_tasks, t0 + per);
+  unsigned long long sum = 0;
+  for (uint32_t t = t0; t < t1; t++) sum += (surv_count[t] + kUnitRows - 1) / kUnitRows;
+  s_part[threadIdx.x] = sum;
+  __syncthreads();
+  for (int o = 1; o < 1024; o <<= 1) {  // inclusive scan of the 1024 partial sums
+    const unsigned long long v = threadIdx.x >= (uint32_t)o ? s_part[threadIdx.x - o] : 0ull;
+    __syncthreads();
+    s_part[threadIdx.x] += v;
+    __syncthreads();
+  }
+  unsigned long long run = s_part[threadIdx.x] - sum;
+  for (uint32_t t = t0; t < t1; t++) {
+    const uint32_t cnt = surv_count[t];
+    const unsigned long long units = (cnt + kUnitRows - 1) / kUnitRows;
+    unit_off[t] = (uint32_t)min(run, (unsigned long long)cap_units);
+    if (run + units > cap_units) {
+      const unsigned long long fit = run < cap_units ? (cap_units - run) * kUnitRows : 0ull;  // survivors that still get a unit
+      const Task task = tasks[t];
+      for (unsigned long long k = fit; k < cnt; k++) {
+        const uint32_t s = surv_rows[task.row_off + k];
+        rowstat[task.row_off + s] = 1;
+        redo_list[atomicAdd(redo_rows, 1ull)] = make_uint2(t, s);
+      }
+    }
+    run += units;
+  }
+  if (threadIdx.x == 1023) unit_off[n_tasks] = (uint32_t)min(s_part[1023], (unsigned long long)cap_units);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -400,15 +443,16 @@ __device__ __forceinline__ void score_tile(uint32_t taddr, uint32_t cb, uint32_t
 // i.e. the max-tree fast path alone; 2 = epilogue skips the TMEM loads too (TMA + MMA pipeline alone).
 // kVar = mode of the TWO-PHASE path (fm_fast.cuh decides when to use it; 0 = the ordinary single pass):
 //   1  reject pass: every tile is scored but the epilogue only keeps each row's two largest chunk maxima g1 >= g2
-//      (a third of the single pass's instructions).  g1 is the row's best approximate score a1 and g2 <= a2, so the
-//      certified rejection test of the rescoring kernel (fm_rescore.cuh: the reference's ratio / threshold test must
-//      fail) can be made from them alone.  Writes rowstat[row] = 1 for rejected rows and, per epilogue warp of the
-//      unit, whether any of its rows survived (`need`).
-//   2  capture pass: the ordinary pass, run only by the warps whose `need` flag is set -- a unit none of whose
-//      warps needs it leaves at once, a warp that does not need it only hands its accumulators back, and the
-//      CTA's column range shrinks to the bands of the warps that do.
+//      (a third of the single pass's instructions, no look-ahead revisit).  g1 is the row's best approximate score
+//      a1 and g2 <= a2, so the certified rejection test of the rescoring kernel (certified_reject below: the
+//      reference's ratio / threshold test must fail) can be made from them alone.  Writes rowstat[row] = 1 for
+//      rejected rows; the sorted position of every SURVIVING row is appended to its task's survivor list.
+//   2  capture pass on the survivors: surv_plan_kernel cuts every task's survivor list into units of 256 rows and
+//      `unit_off` is the prefix of THOSE units; a unit's row operand tiles are gathered row by row from the image's
+//      operand tiles (generic-proxy stores into the swizzled shared-memory image, then a proxy fence), everything
+//      else -- bands, MMAs, capture epilogue, candidate lists written at the rows' own positions -- is the ordinary pass.
 // With -d2 < 1 on images that have little in common nearly every row is rejected (random descriptors at -d2 0.8:
-// 99.9 %), and the capture pass all but disappears.
+// 99.9 %): the capture pass then works on ~20 rows per 20 000-row task.
 // Experiments tried and
 // dropped in round 2, all measured on C2 (profiles/r2_summary.md): nanosleep back-off in the two single-thread warps
 // (no change: their polling does not take issue slots the epilogue needs), testing against the previous step's
@@ -420,12 +464,14 @@ score_kernel(const ImageDev* __restrict__ images, const Task* __restrict__ tasks
              const uint32_t* __restrict__ unit_off, uint32_t n_tasks, uint32_t segs,
              const uint2* __restrict__ bands, Cand* __restrict__ cands, unsigned long long* __restrict__ scored_cols,
              float* __restrict__ dump, uint32_t dump_ld, uint32_t unit_base, uint32_t pre_tiles,
-             float thr, float ratio, uint8_t* __restrict__ rowstat, uint8_t* __restrict__ need) {
+             float thr, float ratio, uint8_t* __restrict__ rowstat, uint32_t* __restrict__ surv_count,
+             uint32_t* __restrict__ surv_rows) {
   extern __shared__ uint8_t smem_raw[];
   ScoreSmem& sm = *reinterpret_cast<ScoreSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
 
   const uint32_t unit = blockIdx.x + unit_base;  // unit_base != 0 only for single-unit debug launches
-  const uint32_t t = find_segment_near(unit_off, n_tasks, unit, kDump ? unit_off[n_tasks] : gridDim.x);
+  if (kVar == 2 && unit >= unit_off[n_tasks]) return;  // the grid is an upper bound on the survivor units
+  const uint32_t t = find_segment_near(unit_off, n_tasks, unit, (kDump || kVar == 2) ? unit_off[n_tasks] : gridDim.x);
   const Task task = tasks[t];
   if (task.flags & kTaskExact) return;
   const ImageDev A = images[task.col_img];
@@ -438,19 +484,18 @@ score_kernel(const ImageDev* __restrict__ images, const Task* __restrict__ tasks
   // epilogue thread -> row: TMEM sub-partition = warp % 4 (hardware rule), accumulator half = (warp - 2) / 4
   const uint32_t half = is_epi ? (warp - 2) >> 2 : 0;
   const uint32_t row_in_unit = half * 128 + (warp & 3) * 32 + lane;
-  const uint32_t s = rb * kUnitRows + row_in_unit;
+  uint32_t s = rb * kUnitRows + row_in_unit;
+  if (kVar == 2) {
+    // survivor unit: row k of the task's survivor list (any order), or no row at all
+    const uint32_t k = rb * kUnitRows + row_in_unit;
+    s = (is_epi && k < min(surv_count[t], B.n)) ? surv_rows[task.row_off + k] : 0xFFFFFFFFu;
+    if (is_epi) sm.srow[row_in_unit] = s;
+  }
   uint32_t lo = 0, hi = 0;
   if (is_epi && s < B.n) {
     uint2 bd = bands[task.row_off + s];
     lo = bd.x;
     hi = bd.y;
-  }
-  // capture pass of the two-phase path: only the warps the reject pass left with surviving rows take part
-  bool need_w = true;
-  if (kVar == 2) {
-    need_w = is_epi && need[(size_t)unit * kEpiWarps + (warp - 2)] != 0;
-    if (!__syncthreads_or(need_w)) return;  // CTA-uniform: no row of this unit survived
-    if (!need_w) { lo = 0; hi = 0; }         // stays out of the column ranges below, skips every tile, writes nothing
   }
   // warp-level and CTA-level column ranges
   uint32_t w_cmin = (hi > lo) ? lo : 0xFFFFFFFFu, w_cmax = (hi > lo) ? hi : 0u;
@@ -499,6 +544,20 @@ score_kernel(const ImageDev* __restrict__ images, const Task* __restrict__ tasks
       ptx::fence_mbar_init();
     }
     if (warp == 0) ptx::tmem_alloc<kAccCols>(&sm.tmem_base);
+    if (kVar == 2) {
+      // Gather the unit's two row-operand tiles: 16-byte chunk q of unit row r comes from chunk q of sorted row
+      // srow[r] in the image's pre-swizzled tiles and lands where SWIZZLE_128B wants it; rows without a survivor are
+      // zero.  (sm.srow was written before the two barriers of the column-range exchange above.)
+      const uint8_t* rowop_img = reinterpret_cast<const uint8_t*>(B.rowop);
+      for (uint32_t idx = threadIdx.x; idx < (uint32_t)kUnitRows * 8u; idx += kScoreThreads) {
+        const uint32_t r = idx >> 3, q = idx & 7u;
+        const uint32_t sr = sm.srow[r];
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (sr != 0xFFFFFFFFu) v = __ldg(reinterpret_cast<const uint4*>(rowop_img + (size_t)(sr >> 7) * kOpTileBytes + sw128_offset(sr & 127u, q)));
+        *reinterpret_cast<uint4*>(sm.a[r >> 7] + sw128_offset(r & 127u, q)) = v;
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to tcgen05.mma
+    }
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
@@ -507,10 +566,12 @@ score_kernel(const ImageDev* __restrict__ images, const Task* __restrict__ tasks
     if (warp == 0) {
       if (lane == 0) {
         // ---- TMA producer ------------------------------------------------------------------
-        const uint8_t* rowop = reinterpret_cast<const uint8_t*>(B.rowop) + (size_t)rb * 2 * kOpTileBytes;
-        ptx::mbar_expect_tx(&sm.bar_a, 2 * kOpTileBytes);
-        ptx::bulk_g2s(sm.a[0], rowop, kOpTileBytes, &sm.bar_a);
-        ptx::bulk_g2s(sm.a[1], rowop + kOpTileBytes, kOpTileBytes, &sm.bar_a);
+        if (kVar != 2) {
+          const uint8_t* rowop = reinterpret_cast<const uint8_t*>(B.rowop) + (size_t)rb * 2 * kOpTileBytes;
+          ptx::mbar_expect_tx(&sm.bar_a, 2 * kOpTileBytes);
+          ptx::bulk_g2s(sm.a[0], rowop, kOpTileBytes, &sm.bar_a);
+          ptx::bulk_g2s(sm.a[1], rowop + kOpTileBytes, kOpTileBytes, &sm.bar_a);
+        }
         const uint8_t* colop = reinterpret_cast<const uint8_t*>(A.colop);
         for (uint32_t i = 0; i < n_sched; i++) {
           const uint32_t stg = i % kStages, use = i / kStages;
@@ -526,7 +587,7 @@ score_kernel(const ImageDev* __restrict__ images, const Task* __restrict__ tasks
         constexpr uint32_t idesc = ptx::umma_idesc_f16_f32(128, kTileCols);
         const uint64_t adesc0 = ptx::umma_desc_sw128(ptx::smem_u32(sm.a[0]));
         const uint64_t adesc1 = ptx::umma_desc_sw128(ptx::smem_u32(sm.a[1]));
-        ptx::mbar_wait(&sm.bar_a, 0);
+        if (kVar != 2) ptx::mbar_wait(&sm.bar_a, 0);  // (survivor units: the gathered tiles are in place since the barrier above)
         for (uint32_t i = 0; i < n_sched; i++) {
           const uint32_t stg = i % kStages, acc = i & 1, use = i >> 1;
           if (use > 0) ptx::mbar_wait(&sm.bar_accempty[acc][0], (use - 1) & 1);
@@ -606,13 +667,14 @@ score_kernel(const ImageDev* __restrict__ images, const Task* __restrict__ tasks
         const float eps = task_eps(A.meta, B.meta);
         rejected = certified_reject(B.norm2_sorted[s], st.g1, st.g2, eps, thr, ratio);
       }
-      if (s < B.n) rowstat[task.row_off + s] = rejected ? 1 : 0;
-      const bool all_rejected = __all_sync(0xffffffffu, rejected);
-      if (lane == 0) need[(size_t)unit * kEpiWarps + (warp - 2)] = all_rejected ? 0 : 1;
+      if (s < B.n) {
+        rowstat[task.row_off + s] = rejected ? 1 : 0;
+        if (!rejected) surv_rows[task.row_off + atomicAdd(surv_count + t, 1u)] = s;  // at most B.n survivors: the list fits
+      }
     }
     return;
   }
-  if (is_epi && s < B.n && need_w) {
+  if (is_epi && s < B.n) {
     // Final list: the entries above the final threshold.
     uint32_t cnt = st.ovf ? 0u : cap_compress(st.cap, min((st.capw - st.cap) / kCapStride, (uint32_t)kCapSlots), st.thr);
     uint32_t trunc = 0;

@@ -41,6 +41,8 @@ int fm_debug_score_unit(fm_ctx* ctx, uint32_t first_img, uint32_t second_img, ui
  *   "pre_tiles" n       look-ahead depth of the scoring kernel (-1 = built-in default)
  *   "two_phase" -1|0|1  two-phase scoring (reject pass + capture pass): library's choice / never / whenever applicable
  *                       -- results are exact either way
+ *   "surv_cap"  n       survivor units the capture pass may use per batch (-1 = built-in); a small value forces the
+ *                       overflow route (surplus survivors go to the exact row kernel)
  * Returns FM_ERR_INVALID for an unknown name.  Nothing reads environment variables.
  */
 int fm_debug_set_option(const char* name, int value);

@@ -335,6 +335,29 @@ def test_two_phase_scoring_forced(built, kind, thr, rat):
         assert sum(w.shape[0] for w in want) > 1000
 
 
+def test_two_phase_scoring_survivor_overflow(built):
+    """More survivors than the capture pass has units for: the surplus rows are matched by the exact row kernel."""
+    images = _group("bank", 4, 13000)
+    pf, ps = [0, 0, 0, 1, 1, 2], [1, 2, 3, 2, 3, 3]
+    want = _fast_oracle_lists(images, pf, ps, 1.0, 0.9)
+    m = capi.Matcher(0)
+    try:
+        capi.debug_set_option("two_phase", 1)
+        capi.debug_set_option("surv_cap", 7)  # 7 units = 1792 rows of ~30 000 survivors
+        for i, (d, s, l) in enumerate(images):
+            m.upload(i, d, s, l)
+        res = m.match(pf, ps, 1.0, 0.9)
+        got, st = res.all_pairs(), m.stats()
+        res.free()
+    finally:
+        capi.debug_set_option("two_phase", -1)
+        capi.debug_set_option("surv_cap", -1)
+        m.close()
+    assert st["two_phase_batches"] >= 1 and st["rows_exact"] > 10000
+    for p, (g, w) in enumerate(zip(got, want)):
+        assert np.array_equal(g, w), f"pair {p}: {g.shape[0]} vs {w.shape[0]}"
+
+
 def test_two_phase_scoring_is_chosen_from_what_the_data_shows(built):
     """The library switches to two-phase scoring only after a call at -d2 < 1 rejected >= 99 % of its rows (random
     descriptors), never for data with real correspondences, never at -d2 >= 1; results identical throughout."""
