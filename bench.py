@@ -15,8 +15,9 @@ exact-size, to rank 0 over NCCL (NVLink).
 
 One JSON line on rank 0:
   value     descriptor pairs/s, keypoints resident in HBM when the timed region starts (lists end on rank 0's GPU)
-  e2e       the same through the C ABI from pinned HOST buffers: per step H2D upload of every image on every rank +
-            preparation + matching + gather + D2H of all lists to rank 0's host memory
+  e2e       the same through the C ABI from pinned HOST buffers: per step every image crosses PCIe once (rank r uploads
+            images r, r+N, ...) and reaches the other GPUs by an NCCL all-gather over NVLink, then preparation + matching +
+            list gather + D2H of all lists to rank 0's host memory
   roofline  tensor-core FLOP rate of the scoring kernel (96 FLOP per descriptor pair)
   wall      `bin/match` (the drop-in executable) process start -> exit on the same group at N GPUs, .bin and .csv.gz
   cpu_baseline  the verbatim reference match.cpp (oracle/_ref/match_ref) on this box's cores (N = 1 only)
@@ -372,6 +373,34 @@ def bench_ours(args):
             d, s, l = host[i]
             mm.upload_raw(i, d.data_ptr(), s.data_ptr(), l.data_ptr(), d.shape[0], d.shape[1])
 
+    # N > 1, end to end: every byte of the group crosses PCIe ONCE -- rank r copies images r, r + N, ... from its pinned
+    # host memory to its GPU -- and reaches the other GPUs over NVLink (NCCL all-gather), instead of every rank pulling
+    # the whole group over its own PCIe link.  fm_upload_image takes the gathered device pointers as they are.
+    uniform = len({k.n for k in kps}) == 1 and world > 1 and n_img % world == 0
+    mine_imgs = list(range(rank, n_img, world))
+    if uniform:
+        h_desc = torch.stack([host[i][0] for i in mine_imgs]).pin_memory()   # [n_local, n_pts, 48]
+        h_scale = torch.stack([host[i][1] for i in mine_imgs]).pin_memory()
+        h_lap = torch.stack([host[i][2] for i in mine_imgs]).pin_memory()
+        g_bufs = [None, None]  # per e2e context: the gathered group, alive until that context's next upload
+
+    def upload_sharded(mm, slot):
+        """H2D of this rank's images + all-gather over NVLink, on the current stream; returns this rank's H2D bytes."""
+        if not uniform:
+            upload_all(mm)
+            return h2d_bytes
+        n_local = len(mine_imgs)
+        loc = [h_desc.to(dev, non_blocking=True), h_scale.to(dev, non_blocking=True), h_lap.to(dev, non_blocking=True)]
+        full = [torch.empty((world * n_local,) + t.shape[1:], dtype=t.dtype, device=dev) for t in loc]
+        for f, t in zip(full, loc):
+            dist.all_gather_into_tensor(f, t)  # rank-major: row r * n_local + k = image k * world + r
+        g_bufs[slot] = (full, loc)
+        d_all, s_all, l_all = full
+        for i in needed:
+            row = (i % world) * n_local + i // world
+            mm.upload_raw(i, d_all[row].data_ptr(), s_all[row].data_ptr(), l_all[row].data_ptr(), d_all.shape[1], d_all.shape[2])
+        return sum(t.numel() * 4 for t in (h_desc, h_scale, h_lap))
+
     class PinnedLists:
         """Rank 0's host-side landing area for the match lists; grows on demand."""
 
@@ -497,11 +526,14 @@ def bench_ours(args):
         res.free()
         return d2h
 
+    h2d_step = [h2d_bytes]
+
     def timed_e2e(steps, warmup):
         d2h, total, prev = [], warmup + steps, None
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ctxs[0].clear()
-        upload_all(ctxs[0])
+        with torch.cuda.stream(streams[0]):
+            upload_sharded(ctxs[0], 0)
         for k in range(total):
             cur, st = ctxs[k % 2], streams[k % 2]
             if k == warmup:
@@ -512,7 +544,8 @@ def bench_ours(args):
                 host_ms.clear()
                 e0.record(st)
                 cur.clear()
-                upload_all(cur)  # pipeline fill: the first timed step's own upload is inside the region
+                with torch.cuda.stream(st):
+                    upload_sharded(cur, k % 2)  # pipeline fill: the first timed step's own upload is inside the region
             with phase("start_prep"):
                 res = e2e_start(cur, st)  # step k: prep + kernels queued
             if k + 1 < total and k + 1 != warmup:
@@ -521,8 +554,8 @@ def bench_ours(args):
                 nxt = ctxs[(k + 1) % 2]
                 with phase("clear"):
                     nxt.clear()
-                with phase("upload_enqueue"):
-                    upload_all(nxt)
+                with phase("upload_enqueue"), torch.cuda.stream(streams[(k + 1) % 2]):
+                    h2d_step[0] = upload_sharded(nxt, (k + 1) % 2)
             if prev is not None:
                 d2h.append(e2e_finish(prev))  # step k-1: lists to rank 0's pinned host memory, under step k's kernels
             prev = res
@@ -544,7 +577,7 @@ def bench_ours(args):
         mm.close()
 
     # whole-job aggregates
-    agg = torch.tensor([float(h2d_bytes), d2h_bytes, float(sum(s["kernel_launches"] for s in stats)), float(matches_rank)],
+    agg = torch.tensor([float(h2d_step[0]), d2h_bytes, float(sum(s["kernel_launches"] for s in stats)), float(matches_rank)],
                        dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(agg, op=dist.ReduceOp.SUM)
@@ -575,6 +608,7 @@ def bench_ours(args):
                        "image_pairs_per_rank": [len(s) for s in shards], "matches_per_step": matches_all},
             "e2e": {"value": total_pairs * args.steps / (ms_e2e * 1e-3), "unit": "descriptor pairs/s",
                     "h2d_bytes_per_step": h2d_all, "d2h_bytes_per_step": d2h_all, "ms_per_step": ms_e2e / args.steps,
+                    "nvlink_allgather_bytes_per_step": (float(h2d_all) * (world - 1) if (world > 1 and uniform) else 0.0),
                     "rank0_host_ms_per_step": e2e_host_ms},
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",

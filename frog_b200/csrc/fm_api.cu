@@ -308,9 +308,9 @@ int fm_upload_image(fm_ctx* c, uint32_t img, const float* desc, const float* sca
   float* d_scale = reinterpret_cast<float*>(base + b_desc);
   float* d_lap = reinterpret_cast<float*>(base + b_desc + b_vec);
   if (n) {
-    FM_CUDA(c, cudaMemcpyAsync(d_desc, desc, (size_t)n * d * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-    FM_CUDA(c, cudaMemcpyAsync(d_scale, scale, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-    FM_CUDA(c, cudaMemcpyAsync(d_lap, lap, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    FM_CUDA(c, cudaMemcpyAsync(d_desc, desc, (size_t)n * d * sizeof(float), cudaMemcpyDefault, c->stream));
+    FM_CUDA(c, cudaMemcpyAsync(d_scale, scale, (size_t)n * sizeof(float), cudaMemcpyDefault, c->stream));
+    FM_CUDA(c, cudaMemcpyAsync(d_lap, lap, (size_t)n * sizeof(float), cudaMemcpyDefault, c->stream));
   }
   im.valid = true;
   im.n = n;

@@ -79,9 +79,10 @@ int fm_synchronize(fm_ctx* ctx);
  * (match.cpp:39-48, 51-92, 137-208).
  *   desc  : n x d floats, row-major (Point::desc)
  *   scale : n floats (Point::scale)          lap : n floats (Point::laplacianSign)
- * Host memory, pageable or pinned; copies are queued on the context's stream, so PINNED buffers
- * must stay valid until the next fm_synchronize() / fm_match() on this context (pageable buffers
- * may be reused as soon as the call returns).  Re-uploading an index replaces the image.  All images of one
+ * Host memory (pageable or pinned) or DEVICE memory of the context's GPU -- e.g. keypoints that reached this GPU over
+ * NVLink from the rank that read them; the direction is inferred from the pointers.  Copies are queued on the
+ * context's stream, so pinned and device buffers must stay valid until the next fm_synchronize() / fm_match() on
+ * this context (pageable buffers may be reused as soon as the call returns).  Re-uploading an index replaces the image.  All images of one
  * context must share d (match.cpp:575 prints one descriptor size for the group).  d = 48 (SURF3D) runs on the
  * tensor-core path; any other d (surf3d -type 1/2: 24 r^3 or 8 r^3 values) on the exact FP32 kernels.
  */
