@@ -75,7 +75,6 @@ bands_kernel(const ImageDev* __restrict__ images, const Task* __restrict__ tasks
   const ImageDev B = images[task.row_img];
   const uint32_t s = (blockIdx.x - task_blk_off[t]) * 128 + threadIdx.x;
   if (s >= B.n) return;
-  const uint32_t act = __activemask();  // a warp cut by the end of the image continues with fewer lanes (see below)
   const ImageMeta* mb = B.meta;
   const ImageMeta* ma = A.meta;
   // class of this row in B, then the class with the same laplacian value in A
@@ -87,40 +86,28 @@ bands_kernel(const ImageDev* __restrict__ images, const Task* __restrict__ tasks
     if (ma->class_lap[ca] == lap) { beg = ma->class_begin[ca]; end = ma->class_begin[ca + 1]; break; }
   const float sr = B.scale_sorted[s];
   const float* __restrict__ sc = A.scale_sorted;
-  auto first_lo = [&](uint32_t l, uint32_t h) {  // first col in [l, h) with !(sr / sc > 1.3f), else h
-    while (l < h) {
-      const uint32_t m = (l + h) >> 1;
-      if (__fdiv_rn(sr, sc[m]) > 1.3f) l = m + 1; else h = m;
-    }
-    return l;
+  // The reference's predicate is fdiv_rn(x, y) > 1.3f (match.cpp:273-274).  The IEEE division is a dozen instructions,
+  // and 26 of them per row made this kernel instruction-bound; away from the boundary one multiplication decides:
+  // x > 1.3001f y  =>  x / y > 1.30009  =>  the rounded quotient exceeds 1.3f;  x < 1.2999f y  =>  it does not.  (Scales
+  // are finite and positive here: other images are flagged and take the exact kernel.)  Only quotients within 1e-4 of
+  // 1.3 pay for the division.
+  auto ratio_gt = [](float x, float y) {
+    if (x > 1.3001f * y) return true;
+    if (x < 1.2999f * y) return false;
+    return __fdiv_rn(x, y) > 1.3f;
   };
-  auto first_hi = [&](uint32_t l, uint32_t h) {  // first col in [l, h) with (sc / sr > 1.3f), else h
-    while (l < h) {
-      const uint32_t m = (l + h) >> 1;
-      if (__fdiv_rn(sc[m], sr) > 1.3f) h = m; else l = m + 1;
-    }
-    return l;
-  };
-  // Rows of one class are sorted by scale and float division is monotone, so lo and hi are non-decreasing along the
-  // warp: lanes 0 and 31 search the whole class, the lanes between them only between those two answers (a handful of
-  // steps instead of log2(class size)).  A warp that straddles a class boundary, or the end of the image, searches in full.
-  const uint32_t lane = threadIdx.x & 31u;
-  uint32_t lo = 0, hi = 0;
-  const bool edge = lane == 0 || lane == 31;
-  if (edge) { lo = first_lo(beg, end); hi = first_hi(lo, end); }
-  const bool whole = act == 0xffffffffu;
-  const uint32_t cb0 = __shfl_sync(act, cb, 0), cb31 = __shfl_sync(act, cb, whole ? 31 : 0);
-  const uint32_t lo0 = __shfl_sync(act, lo, 0), lo31 = __shfl_sync(act, lo, whole ? 31 : 0);
-  const uint32_t hi0 = __shfl_sync(act, hi, 0), hi31 = __shfl_sync(act, hi, whole ? 31 : 0);
-  if (!edge) {
-    if (whole && cb == cb0 && cb == cb31) {
-      lo = first_lo(lo0, lo31);
-      hi = first_hi(max(hi0, lo), max(hi31, lo));
-    } else {
-      lo = first_lo(beg, end);
-      hi = first_hi(lo, end);
-    }
+  uint32_t l = beg, h = end;
+  while (l < h) {  // first col with !(sr / sc > 1.3f)
+    const uint32_t m = (l + h) >> 1;
+    if (ratio_gt(sr, sc[m])) l = m + 1; else h = m;
   }
+  uint32_t lo = l, hi;
+  h = end;
+  while (l < h) {  // first col >= lo with (sc / sr > 1.3f)
+    const uint32_t m = (l + h) >> 1;
+    if (ratio_gt(sc[m], sr)) h = m; else l = m + 1;
+  }
+  hi = l;
   if (hi < lo) hi = lo;
   bands[task.row_off + s] = make_uint2(lo, hi);
 }
