@@ -27,6 +27,8 @@ PUBLIC_SYMBOLS = [
     "fm_clear_images", "fm_image_points", "fm_match", "fm_result_wait", "fm_result_num_pairs", "fm_result_total",
     "fm_result_count", "fm_result_pairs", "fm_result_distances", "fm_result_fetch", "fm_result_device_counts",
     "fm_result_device_pairs", "fm_result_free", "fm_get_stats", "fm_result_stats", "fm_version",
+    "fm_links_build", "fm_links_total", "fm_links_fetch", "fm_links_offsets", "fm_links_data", "fm_links_device_offsets",
+    "fm_links_device_data", "fm_links_build_ms", "fm_links_free",
 ]
 DEBUG_SYMBOLS = ["fm_debug_image", "fm_debug_score_unit", "fm_debug_set_option"]
 
@@ -96,6 +98,18 @@ def load():
     L.fm_debug_image.argtypes = [vp, C.c_uint32, u32p, u32p, f32p, u32p, f32p, vp, vp, vp, vp]
     L.fm_debug_score_unit.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32, vp, C.c_uint32, vp, vp, vp]
     L.fm_debug_set_option.argtypes = [C.c_char_p, C.c_int]
+    L.fm_links_build.argtypes = [vp, vp, vp, vp, C.POINTER(vp)]
+    L.fm_links_total.argtypes = [vp]
+    L.fm_links_total.restype = C.c_uint64
+    L.fm_links_fetch.argtypes = [vp]
+    L.fm_links_offsets.argtypes = [vp, C.c_uint32, u32p]
+    L.fm_links_offsets.restype = C.POINTER(C.c_uint64)
+    L.fm_links_data.argtypes = [vp]
+    L.fm_links_data.restype = u32p
+    L.fm_links_build_ms.argtypes = [vp]
+    L.fm_links_build_ms.restype = C.c_float
+    L.fm_links_free.argtypes = [vp]
+    L.fm_links_free.restype = None
     _lib = L
     return L
 
@@ -163,6 +177,31 @@ class Result:
         if not ptr:
             raise FrogMatchError("no distances: pass distances=True to match() (and fetch device-only results)")
         return np.ctypeslib.as_array(ptr, shape=(n,)).copy()
+
+    def links(self, pair_first, pair_second, block_order=None):
+        """The adjacency bin/frog builds from pairs.bin (ImageGroup::readPairs), built on the device from this result's
+        lists.  Returns (offsets, links, build_ms): offsets[img] = n_points + 1 uint64 offsets into `links`
+        ([total, 2] uint32: (image, point)), every point's links in the reference's push_back order."""
+        if self.counts is None:
+            self.wait()
+        L = self._m._L
+        pf = np.ascontiguousarray(pair_first, np.uint32)
+        ps = np.ascontiguousarray(pair_second, np.uint32)
+        bo = None if block_order is None else np.ascontiguousarray(block_order, np.uint32)
+        h = C.c_void_p()
+        self._m._check(L.fm_links_build(self._h, _ptr(pf), _ptr(ps), None if bo is None else _ptr(bo), C.byref(h)))
+        try:
+            self._m._check(L.fm_links_fetch(h))
+            total = L.fm_links_total(h)
+            data = np.ctypeslib.as_array(L.fm_links_data(h), shape=(max(total, 1), 2))[:total].copy()
+            offsets = {}
+            for img in sorted(set(pf.tolist()) | set(ps.tolist())):
+                n = C.c_uint32()
+                ptr = L.fm_links_offsets(h, img, C.byref(n))
+                offsets[img] = np.ctypeslib.as_array(ptr, shape=(n.value + 1,)).copy()
+            return offsets, data, float(L.fm_links_build_ms(h))
+        finally:
+            L.fm_links_free(h)
 
     def all_pairs(self):
         return [self.pairs(p) for p in range(self.n_pairs)]

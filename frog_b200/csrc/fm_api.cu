@@ -12,6 +12,7 @@
 #include "fm_fast.cuh"
 #include "fm_generic.cuh"
 #include "fm_host.h"
+#include "fm_links.cuh"
 
 using namespace fm;
 
@@ -35,6 +36,17 @@ struct fm_result {
   bool waited = false;
   EventPool ev;     // this call's phase brackets (and `done`)
   fm_stats stats{};  // launch-side counters; device counters and event times are filled in by finalize()
+};
+
+struct fm_links {
+  fm_ctx* ctx = nullptr;
+  uint64_t total = 0;        // half-links
+  uint32_t n_points = 0;     // points of all images of the context
+  std::vector<uint64_t> point_base;  // per image index: global id of its point 0 (n_images + 1 entries)
+  DevBuf d_off, d_links;
+  unsigned long long* h_off = nullptr;  // pinned, after fm_links_fetch
+  uint32_t* h_links = nullptr;
+  float ms_build = 0.f;
 };
 
 namespace {
@@ -760,6 +772,122 @@ int fm_result_stats(fm_result* r, fm_stats* out) {
   if (rc != FM_OK) return rc;
   *out = r->stats;
   return FM_OK;
+}
+
+// ---- consumer hand-off: link build (fm_links.cuh) -------------------------------------------------
+
+int fm_links_build(fm_result* r, const uint32_t* pair_first, const uint32_t* pair_second, const uint32_t* block_order,
+                   fm_links** out) {
+  if (!r || !out) return FM_ERR_INVALID;
+  *out = nullptr;
+  fm_ctx* c = r->ctx;
+  if (!r->waited) return fail(c, FM_ERR_INVALID, "fm_links_build: the result is not complete (fm_result_wait first)");
+  if (r->flags & FM_FLAG_MATCH_ALL) return fail(c, FM_ERR_UNSUPPORTED, "fm_links_build: -all results are not supported");
+  if (r->n_pairs && (!pair_first || !pair_second)) return fail(c, FM_ERR_INVALID, "fm_links_build: null pair arrays");
+  FM_CUDA(c, cudaSetDevice(c->device));
+  fm_links* l = new (std::nothrow) fm_links();
+  if (!l) return fail(c, FM_ERR_NOMEM, "fm_links_build: out of host memory");
+  l->ctx = c;
+  const size_t n_img = c->images.size();
+  l->point_base.assign(n_img + 1, 0);
+  for (size_t i = 0; i < n_img; i++) l->point_base[i + 1] = l->point_base[i] + (c->images[i].valid ? c->images[i].n : 0);
+  if (l->point_base[n_img] > 0xFFFFFFF0ull) { delete l; return fail(c, FM_ERR_UNSUPPORTED, "fm_links_build: more than 2^32 points"); }
+  l->n_points = (uint32_t)l->point_base[n_img];
+  // blocks in file order
+  std::vector<LinkBlock> blocks(r->n_pairs);
+  std::vector<unsigned long long> entry_off(r->n_pairs + 1, 0);
+  for (size_t k = 0; k < r->n_pairs; k++) {
+    const size_t p = block_order ? block_order[k] : k;
+    if (p >= r->n_pairs || pair_first[p] >= n_img || pair_second[p] >= n_img) { delete l; return fail(c, FM_ERR_INVALID, "fm_links_build: bad block order or pair"); }
+    LinkBlock& b = blocks[k];
+    b.src = r->offsets[p];
+    b.q0 = entry_off[k];
+    b.count = r->counts[p];
+    b.image1 = pair_first[p];
+    b.image2 = pair_second[p];
+    b.base1 = (uint32_t)l->point_base[b.image1];
+    b.base2 = (uint32_t)l->point_base[b.image2];
+    b.pad_ = 0;
+    entry_off[k + 1] = entry_off[k] + b.count;
+  }
+  const unsigned long long n_entries = entry_off[r->n_pairs];
+  l->total = 2ull * n_entries;
+  auto bail = [&](cudaError_t e, const char* what) { int code = cuda_fail(c, e, what); fm_links_free(l); return code; };
+  DevBuf d_blocks, d_eoff, d_deg, d_cursor, d_tmp;
+  struct Scratch { DevBuf* b[5]; ~Scratch() { for (auto* x : b) x->release(); } } scratch{{&d_blocks, &d_eoff, &d_deg, &d_cursor, &d_tmp}};
+  cudaError_t e;
+  const size_t np1 = (size_t)l->n_points + 1;
+  if ((e = d_blocks.ensure(std::max<size_t>(1, blocks.size()) * sizeof(LinkBlock))) != cudaSuccess) return bail(e, "fm_links_build");
+  if ((e = d_eoff.ensure(entry_off.size() * sizeof(unsigned long long))) != cudaSuccess) return bail(e, "fm_links_build");
+  if ((e = d_deg.ensure(np1 * sizeof(uint32_t))) != cudaSuccess) return bail(e, "fm_links_build");
+  if ((e = d_cursor.ensure(np1 * sizeof(uint32_t))) != cudaSuccess) return bail(e, "fm_links_build");
+  if ((e = d_tmp.ensure(std::max<uint64_t>(l->total, 1) * sizeof(HalfLink))) != cudaSuccess) return bail(e, "fm_links_build");
+  if ((e = l->d_off.ensure(np1 * sizeof(unsigned long long))) != cudaSuccess) return bail(e, "fm_links_build");
+  if ((e = l->d_links.ensure(std::max<uint64_t>(l->total, 1) * sizeof(uint2))) != cudaSuccess) return bail(e, "fm_links_build");
+  cudaEvent_t ev0, ev1;
+  cudaEventCreate(&ev0);
+  cudaEventCreate(&ev1);
+  if (!blocks.empty() && (e = cudaMemcpyAsync(d_blocks.p, blocks.data(), blocks.size() * sizeof(LinkBlock), cudaMemcpyHostToDevice, c->stream)) != cudaSuccess) return bail(e, "fm_links_build");
+  if ((e = cudaMemcpyAsync(d_eoff.p, entry_off.data(), entry_off.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice, c->stream)) != cudaSuccess) return bail(e, "fm_links_build");
+  cudaMemsetAsync(d_deg.p, 0, np1 * sizeof(uint32_t), c->stream);
+  cudaMemsetAsync(d_cursor.p, 0, np1 * sizeof(uint32_t), c->stream);
+  cudaEventRecord(ev0, c->stream);
+  const unsigned grid = (unsigned)((n_entries + 255) / 256);
+  const uint2* pairs = r->d_out.as<uint2>();
+  if (n_entries)
+    links_scatter_kernel<false><<<grid, 256, 0, c->stream>>>(d_blocks.as<LinkBlock>(), d_eoff.as<unsigned long long>(), (uint32_t)r->n_pairs, n_entries,
+                                                            pairs, d_deg.as<uint32_t>(), nullptr, nullptr, nullptr);
+  links_scan_kernel<<<1, 1024, 0, c->stream>>>(d_deg.as<uint32_t>(), l->n_points, l->d_off.as<unsigned long long>());
+  if (n_entries)
+    links_scatter_kernel<true><<<grid, 256, 0, c->stream>>>(d_blocks.as<LinkBlock>(), d_eoff.as<unsigned long long>(), (uint32_t)r->n_pairs, n_entries,
+                                                           pairs, nullptr, l->d_off.as<unsigned long long>(), d_cursor.as<uint32_t>(), d_tmp.as<HalfLink>());
+  if (l->n_points)
+    links_sort_kernel<<<(l->n_points + 127) / 128, 128, 0, c->stream>>>(l->d_off.as<unsigned long long>(), l->n_points, d_tmp.as<HalfLink>(),
+                                                                        l->d_links.as<uint2>());
+  cudaEventRecord(ev1, c->stream);
+  if ((e = cudaGetLastError()) != cudaSuccess) return bail(e, "fm_links_build: launch");
+  if ((e = cudaStreamSynchronize(c->stream)) != cudaSuccess) return bail(e, "fm_links_build");  // the scratch buffers and host tables die here
+  cudaEventElapsedTime(&l->ms_build, ev0, ev1);
+  cudaEventDestroy(ev0);
+  cudaEventDestroy(ev1);
+  *out = l;
+  return FM_OK;
+}
+
+uint64_t fm_links_total(const fm_links* l) { return l ? l->total : 0; }
+
+int fm_links_fetch(fm_links* l) {
+  if (!l) return FM_ERR_INVALID;
+  if (l->h_off) return FM_OK;
+  fm_ctx* c = l->ctx;
+  FM_CUDA(c, cudaSetDevice(c->device));
+  const size_t np1 = (size_t)l->n_points + 1;
+  FM_CUDA(c, cudaMallocHost(reinterpret_cast<void**>(&l->h_off), np1 * sizeof(unsigned long long)));
+  FM_CUDA(c, cudaMallocHost(reinterpret_cast<void**>(&l->h_links), std::max<uint64_t>(l->total, 1) * sizeof(uint2)));
+  FM_CUDA(c, cudaMemcpyAsync(l->h_off, l->d_off.p, np1 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+  if (l->total) FM_CUDA(c, cudaMemcpyAsync(l->h_links, l->d_links.p, l->total * sizeof(uint2), cudaMemcpyDeviceToHost, c->stream));
+  FM_CUDA(c, cudaStreamSynchronize(c->stream));
+  return FM_OK;
+}
+
+const uint64_t* fm_links_offsets(const fm_links* l, uint32_t img, uint32_t* n_points) {
+  if (!l || !l->h_off || (size_t)img + 1 >= l->point_base.size()) return nullptr;
+  if (n_points) *n_points = (uint32_t)(l->point_base[img + 1] - l->point_base[img]);
+  return reinterpret_cast<const uint64_t*>(l->h_off) + l->point_base[img];
+}
+const uint32_t* fm_links_data(const fm_links* l) { return (l && l->h_off) ? l->h_links : nullptr; }
+const uint64_t* fm_links_device_offsets(const fm_links* l) { return l ? reinterpret_cast<const uint64_t*>(l->d_off.p) : nullptr; }
+const uint32_t* fm_links_device_data(const fm_links* l) { return l ? l->d_links.as<uint32_t>() : nullptr; }
+float fm_links_build_ms(const fm_links* l) { return l ? l->ms_build : 0.f; }
+
+void fm_links_free(fm_links* l) {
+  if (!l) return;
+  cudaSetDevice(l->ctx->device);
+  l->d_off.release();
+  l->d_links.release();
+  if (l->h_off) cudaFreeHost(l->h_off);
+  if (l->h_links) cudaFreeHost(l->h_links);
+  delete l;
 }
 
 // ---- debug / test hooks (include/frogmatch_debug.h) ---------------------------------------------

@@ -133,6 +133,40 @@ const uint32_t* fm_result_device_counts(const fm_result* r);
 const uint32_t* fm_result_device_pairs(const fm_result* r);
 void fm_result_free(fm_result* r);
 
+/* ---- consumer hand-off ------------------------------------------------------------------------ */
+
+/*
+ * Build, on the device, the adjacency `bin/frog` builds when it reads pairs.bin -- ImageGroup::readPairs,
+ * registration/imageGroup.cxx:1386-1411: for every entry (p1, p2) of the block of images (image1, image2),
+ * {image2, p2} is appended to image1's point p1 and {image1, p1} to image2's point p2 (Point::links,
+ * registration/point.h:11-28) -- from the match lists of a finished fm_match, so that a consumer in the same
+ * process never reads the file back.  Every point's links come out in the reference's push_back order (blocks in
+ * file order, entries in list order), which its statistics depend on.
+ *   pair_first / pair_second : the arrays fm_match was called with (n_pairs = fm_result_num_pairs)
+ *   block_order              : the order in which the pair blocks appear in pairs.bin (match.cpp:727-742: row-major
+ *                              over (first, second)); NULL = submission order
+ * The result must be complete (fm_match without FM_FLAG_ASYNC, or fm_result_wait); FM_FLAG_MATCH_ALL results
+ * are not supported.  Points are numbered image after image in image-index order over the context's images.
+ */
+typedef struct fm_links fm_links;
+int fm_links_build(fm_result* r, const uint32_t* pair_first, const uint32_t* pair_second, const uint32_t* block_order,
+                   fm_links** out);
+/* Half-links in all = 2 x matches. */
+uint64_t fm_links_total(const fm_links* l);
+/* Copy offsets and links to pinned host memory (the device views are valid right after fm_links_build). */
+int fm_links_fetch(fm_links* l);
+/* Host, after fm_links_fetch: image `img`'s n_points + 1 offsets into fm_links_data (point p's links are entries
+ * [off[p], off[p+1])); NULL for an image the context does not hold. */
+const uint64_t* fm_links_offsets(const fm_links* l, uint32_t img, uint32_t* n_points);
+/* Host, after fm_links_fetch: 2 x total uint32, (image, point) per link. */
+const uint32_t* fm_links_data(const fm_links* l);
+/* Device views: total_points + 1 offsets (points numbered image after image), and the (image, point) pairs. */
+const uint64_t* fm_links_device_offsets(const fm_links* l);
+const uint32_t* fm_links_device_data(const fm_links* l);
+/* CUDA-event time of the build (count, scan, scatter, per-point ordering), milliseconds. */
+float fm_links_build_ms(const fm_links* l);
+void fm_links_free(fm_links* l);
+
 /* ---- instrumentation ------------------------------------------------------------------------- */
 
 typedef struct fm_stats {

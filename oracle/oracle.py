@@ -249,3 +249,51 @@ def run_ref_binary(args, cwd=None, threads=None) -> subprocess.CompletedProcess:
     if threads:
         cmd += ["-nt", str(threads)]
     return subprocess.run(cmd, cwd=cwd, capture_output=True, text=True, check=True)
+
+
+# ----------------------------------------------------------------------------------------------
+# consumer hand-off: the links bin/frog builds when it reads pairs.bin
+
+
+def read_pairs_links(blocks, n_points):
+    """ImageGroup::readPairs, registration/imageGroup.cxx:1386-1411, restated literally: blocks = [(image1, image2,
+    [m,2] uint32)] in FILE order; for every entry (p1, p2) push {image2, p2} onto image1's point p1 and {image1, p1}
+    onto image2's point p2.  Returns {image: list (per point) of lists of (image, point)}."""
+    links = {img: [[] for _ in range(n)] for img, n in n_points.items()}
+    for i, j, m in blocks:
+        for p1, p2 in m.tolist():
+            links[i][p1].append((j, p2))
+            links[j][p2].append((i, p1))
+    return links
+
+
+def read_pairs_links_csr(blocks, n_points):
+    """The same as CSR arrays (offsets per image, [total,2] links), through a STABLE sort of the push_back sequence by
+    point -- fast enough for BASELINE-size groups; pinned to read_pairs_links in tests/test_oracle.py."""
+    imgs = sorted(n_points)
+    base, run = {}, 0
+    for img in imgs:
+        base[img] = run
+        run += n_points[img]
+    gids, vals = [], []
+    for i, j, m in blocks:
+        if m.shape[0] == 0:
+            continue
+        m = m.astype(np.int64)
+        g = np.empty(2 * m.shape[0], np.int64)
+        v = np.empty((2 * m.shape[0], 2), np.uint32)
+        g[0::2] = base[i] + m[:, 0]
+        g[1::2] = base[j] + m[:, 1]
+        v[0::2, 0], v[0::2, 1] = j, m[:, 1]
+        v[1::2, 0], v[1::2, 1] = i, m[:, 0]
+        gids.append(g)
+        vals.append(v)
+    if gids:
+        g, v = np.concatenate(gids), np.concatenate(vals)
+        order = np.argsort(g, kind="stable")
+        v = v[order]
+        deg = np.bincount(g, minlength=run)
+    else:
+        v, deg = np.zeros((0, 2), np.uint32), np.zeros(run, np.int64)
+    off = np.concatenate([[0], np.cumsum(deg)]).astype(np.uint64)
+    return {img: off[base[img]: base[img] + n_points[img] + 1] for img in imgs}, v

@@ -384,3 +384,57 @@ def test_two_phase_scoring_is_chosen_from_what_the_data_shows(built):
             res.free()
         finally:
             m.close()
+
+
+@pytest.mark.parametrize("sym", [False, True])
+def test_links_build_matches_read_pairs(env, sym):
+    """Consumer hand-off: the adjacency built on the device from the match lists == ImageGroup::readPairs restated
+    (registration/imageGroup.cxx:1386-1411) on the same blocks in file order -- every point's links in push_back order."""
+    m, port = env
+    images = helpers.random_group("bank", 4, 1500)
+    images[1] = tuple(x[:611] for x in images[1])
+    # a submission order that is NOT the file order, with a -targ style pair (3, 0) whose block sorts between others
+    pairs = [(1, 2), (0, 1), (3, 0), (0, 3), (2, 3), (0, 2)]
+    pf, ps = [p[0] for p in pairs], [p[1] for p in pairs]
+    order = sorted(range(len(pairs)), key=lambda k: pairs[k])  # match.cpp:727-742: row-major over (first, second)
+    m.clear()
+    for i, (d, s, l) in enumerate(images):
+        m.upload(i, d, s, l)
+    res = m.match(pf, ps, 1.0, 0.95, sym=sym)
+    lists = res.all_pairs()
+    offsets, data, ms = res.links(pf, ps, block_order=order)
+    res.free()
+    n_points = {i: images[i][1].shape[0] for i in range(4)}
+    blocks = [(pairs[k][0], pairs[k][1], lists[k]) for k in order]
+    want_off, want = O.read_pairs_links_csr(blocks, n_points)
+    assert data.shape[0] == 2 * sum(l.shape[0] for l in lists) > 1000
+    assert np.array_equal(data, want)
+    for img in range(4):
+        assert np.array_equal(offsets[img].astype(np.uint64), want_off[img])
+    # and against the literal push_back loops on a few points
+    literal = O.read_pairs_links(blocks, n_points)
+    for img, p in ((0, 0), (0, 7), (1, 610), (2, 100), (3, 1499)):
+        got = [tuple(x) for x in data[int(offsets[img][p]): int(offsets[img][p + 1])].tolist()]
+        assert got == literal[img][p]
+
+
+def test_links_build_at_scale(built):
+    """C2-size group (0.9 M matches, 1.8 M half-links): device link build == the stable-sort restatement."""
+    kps = [synth.make("iid", 20000, i) for i in range(10)]
+    pf = [i for i in range(10) for j in range(i + 1, 10)]
+    ps = [j for i in range(10) for j in range(i + 1, 10)]
+    m = capi.Matcher(0)
+    try:
+        for i, k in enumerate(kps):
+            m.upload(i, k.desc, k.scale, k.lap)
+        res = m.match(pf, ps, 1.0, 1.0)
+        lists = res.all_pairs()
+        offsets, data, ms = res.links(pf, ps)
+        res.free()
+    finally:
+        m.close()
+    want_off, want = O.read_pairs_links_csr([(i, j, l) for i, j, l in zip(pf, ps, lists)], {i: 20000 for i in range(10)})
+    assert data.shape[0] > 1_500_000 and np.array_equal(data, want)
+    for img in range(10):
+        assert np.array_equal(offsets[img].astype(np.uint64), want_off[img])
+    assert 0 < ms < 50

@@ -175,3 +175,22 @@ def test_fast_oracle_is_pinned(libs):
     assert n_checked == len(cases) * (len(PARAMS) + 1)
     with pytest.raises(ValueError):  # thresholds at which the reference's carried `match` would show: refused
         fast.compute_matches(cases[0][0], cases[0][1], 2e19, 1.0)
+
+
+def test_links_restatements_agree(libs):
+    """readPairs restated literally (push_back loops) == the stable-sort CSR form used at scale."""
+    port, _ = libs
+    rng = np.random.default_rng(5)
+    n_points = {0: 40, 1: 35, 2: 50}
+    blocks = []
+    for i, j in ((0, 1), (0, 2), (1, 2), (2, 0)):  # the last one: a -targ style block order
+        m = np.stack([rng.integers(0, n_points[i], 60), rng.integers(0, n_points[j], 60)], axis=1).astype(np.uint32)
+        blocks.append((i, j, m))
+    blocks.append((1, 0, np.zeros((0, 2), np.uint32)))
+    lists = O.read_pairs_links(blocks, n_points)
+    off, data = O.read_pairs_links_csr(blocks, n_points)
+    for img, n in n_points.items():
+        for p in range(n):
+            got = [tuple(x) for x in data[int(off[img][p]): int(off[img][p + 1])].tolist()]
+            assert got == lists[img][p]
+    assert data.shape[0] == 2 * sum(b[2].shape[0] for b in blocks)
