@@ -237,7 +237,7 @@ void fm_destroy(fm_ctx* c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   c->arena.release();
-  DevBuf* bufs[] = {&c->s_keys, &c->s_keys_sorted, &c->s_idx, &c->s_idx_sorted, &c->s_norm2, &c->s_sort, &c->s_segs, &c->d_images, &c->d_metas, &c->d_meta_blob, &c->d_rowres, &c->d_rowdist, &c->d_chunk_status,
+  DevBuf* bufs[] = {&c->s_keys, &c->s_keys_sorted, &c->s_idx, &c->s_idx_sorted, &c->s_norm2, &c->s_sort, &c->s_segs, &c->d_images, &c->d_metas, &c->d_meta_blob, &c->d_rowres, &c->d_rowdist, &c->d_chunk_count, &c->d_chunk_out, &c->d_chunk_stage, &c->d_chunk_status,
                     &c->d_totals, &c->d_bands, &c->d_cands, &c->d_redo, &c->d_taskinfo, &c->d_rowstat, &c->d_surv, &c->d_all, &c->d_all_tasks};
   for (auto* b : bufs) b->release();
   for (auto& b : c->out_free) b.release();
@@ -491,9 +491,12 @@ int fm_match(fm_ctx* c, const uint32_t* pair_first, const uint32_t* pair_second,
     FM_CUDA_R(c->d_rowdist.ensure((size_t)max_rows * sizeof(float)));
     FM_CUDA_R(r->d_dist.ensure(std::max<uint64_t>(total_rows, 1) * sizeof(float)));
   }
-  if (c->d_chunk_status.cap < (size_t)max_chunks * sizeof(unsigned long long)) {
+  FM_CUDA_R(c->d_chunk_count.ensure((size_t)max_chunks * sizeof(uint32_t)));
+  FM_CUDA_R(c->d_chunk_out.ensure((size_t)max_chunks * sizeof(unsigned long long)));
+  FM_CUDA_R(c->d_chunk_stage.ensure((size_t)max_chunks * kStageCap * sizeof(uint2)));
+  if (!c->d_chunk_status.p) {
     // fresh memory may hold anything: clear it once, then the launch epoch tells stale words from current ones
-    FM_CUDA_R(c->d_chunk_status.ensure((size_t)max_chunks * sizeof(unsigned long long) * 2));
+    FM_CUDA_R(c->d_chunk_status.ensure((size_t)kOnePassChunks * sizeof(unsigned long long)));
     FM_CUDA_R(cudaMemsetAsync(c->d_chunk_status.p, 0, c->d_chunk_status.cap, c->stream));
   }
   FM_CUDA_R(c->d_totals.ensure(sizeof(DeviceCounters)));
@@ -630,17 +633,31 @@ int fm_match(fm_ctx* c, const uint32_t* pair_first, const uint32_t* pair_second,
         ca.n_chunks = b.chunks;
         ca.rowres = d_rowres;
         ca.rowdist = d_rowdist;
-        ca.status = c->d_chunk_status.as<unsigned long long>();
-        c->compact_epoch = (c->compact_epoch % 0x3FFFFFFEu) + 1u;  // 1 .. 2^30 - 2: never the cleared value 0
-        ca.epoch = c->compact_epoch;
+        ca.chunk_count = c->d_chunk_count.as<uint32_t>();
+        ca.chunk_out = c->d_chunk_out.as<unsigned long long>();
+        ca.stage = c->d_chunk_stage.as<uint2>();
         ca.pair_count = r->d_counts.as<uint32_t>();
         ca.running_total = &d_counters->running_total;
         ca.out_pairs = r->d_out.as<uint2>();
         ca.out_dist = want_dist ? r->d_dist.as<float>() : nullptr;
-        const uint32_t grid = b.chunks;
-        if (want_dist) compact_kernel<true><<<grid, kCompactThreads, 0, c->stream>>>(ca);
-        else compact_kernel<false><<<grid, kCompactThreads, 0, c->stream>>>(ca);
-        c->stats.kernel_launches += 1;
+        if (b.chunks <= kOnePassChunks) {
+          ca.status = c->d_chunk_status.as<unsigned long long>();
+          c->compact_epoch = (c->compact_epoch % 0x3FFFFFFEu) + 1u;  // 1 .. 2^30 - 2: never the cleared value 0
+          ca.epoch = c->compact_epoch;
+          if (want_dist) compact_onepass_kernel<true><<<b.chunks, kCompactThreads, 0, c->stream>>>(ca);
+          else compact_onepass_kernel<false><<<b.chunks, kCompactThreads, 0, c->stream>>>(ca);
+          c->stats.kernel_launches += 1;
+        } else if (want_dist) {
+          compact_count_kernel<true><<<b.chunks, kCompactThreads, 0, c->stream>>>(ca);
+          compact_scan_kernel<<<1, 1024, 0, c->stream>>>(ca);
+          compact_scatter_kernel<true><<<b.chunks, kCompactThreads, 0, c->stream>>>(ca);
+          c->stats.kernel_launches += 3;
+        } else {
+          compact_count_kernel<false><<<b.chunks, kCompactThreads, 0, c->stream>>>(ca);
+          compact_scan_kernel<<<1, 1024, 0, c->stream>>>(ca);
+          compact_scatter_kernel<false><<<b.chunks, kCompactThreads, 0, c->stream>>>(ca);
+          c->stats.kernel_launches += 3;
+        }
       }
       if (two_phase_possible && !two_phase && !probed && b.any_fast && !b.any_exact && bi + 1 < batches.size() &&
           !(flags & FM_FLAG_ASYNC)) {

@@ -5,23 +5,23 @@
 //         order ComputeMatches appends them in -- written at the running output offset so that
 //         consecutive tasks (and the two directions of a -sym pair) are contiguous.
 //
-// ONE pass, HBM-bound: 4 B read per row, 8 B written per match (+ 4 B per match with distances).
-// The rows of a batch are cut into chunks of <= 2048 rows of one task, described by a host-built
-// 16-byte record each (no per-chunk searches or dependent loads on the device).  One small CTA per
-// chunk (128 threads, 16 KB of shared memory: a dozen CTAs per SM, ~100 KB of loads in flight per
-// SM): fully coalesced 4-byte loads (sixteen per thread), warp ballots for the ranks, the exclusive
-// prefix of the chunk totals by decoupled look-back over one 64-bit status word per chunk (launch
-// epoch | state | value: no clearing between launches; 512 predecessors inspected per round, so
-// even the first wave of a launch -- where nobody has a finished neighbour yet -- needs three
-// rounds at most), staging in shared memory in output order, 16-byte stores.  CTAs of a 1-D grid
-// are dispatched in index order, so a chunk's predecessors are always running or done (the same
-// assumption every single-pass scan makes).
+// HBM-bound by nature: 4 B read per row, 8 B written per match (+ 4 B per match with distances).
+// The rows of a batch are cut into chunks of <= 4096 rows of one task, described by a host-built 16-byte record each
+// (no per-chunk searches or dependent loads on the device).  Three launches without any inter-CTA wait:
+//   count    one CTA per chunk: fully coalesced 4-byte loads (sixteen in flight per thread), warp ballots, the chunk's
+//            total -- and, when the chunk holds few matches (<= 64: the usual case when most rows are rejected), the
+//            compacted pairs themselves, parked in a small per-chunk staging slot;
+//   scan     one CTA: exclusive prefix of the chunk totals, per-pair counts, the running total;
+//   scatter  one CTA per chunk: a parked chunk only moves its few pairs to their final place (the rows are not read
+//            again); a dense chunk re-reads its rows (still L2-resident), ranks them, stages the pairs in shared
+//            memory in output order and writes them with 16-byte stores.
+// Batches of at most kOnePassChunks chunks take the single-launch kernel at the end of this file instead.
 #pragma once
 #include "fm_common.cuh"
 
 namespace fm {
 
-constexpr int kCompactThreads = 128;
+constexpr int kCompactThreads = 256;
 constexpr int kCompactPer = 16;                                 // rows per thread
 constexpr int kCompactChunk = kCompactThreads * kCompactPer;    // rows per chunk
 constexpr int kCompactSlices = kCompactPer * (kCompactThreads / 32);  // (iteration, warp) slices of 32 rows
@@ -41,24 +41,184 @@ __device__ __forceinline__ unsigned long long chunk_word(uint32_t epoch, unsigne
   return ((unsigned long long)epoch << 34) | (state << 32) | value;
 }
 
+constexpr uint32_t kOnePassChunks = 1536;  // batches up to this many chunks: one launch (compact_onepass_kernel)
+constexpr uint32_t kStageCap = 64;  // matches a chunk may park in its staging slot during the count pass
+
 struct CompactArgs {
   const ChunkDesc* chunks;
   uint32_t n_chunks;
   const uint32_t* rowres;
   const float* rowdist;           // kDist only: squared distance of the row's match
-  unsigned long long* status;     // n_chunks words (never cleared: epoch-tagged)
-  uint32_t epoch;                 // 30 bits, different from the previous launches that used `status`
+  uint32_t* chunk_count;          // n_chunks
+  unsigned long long* chunk_out;  // n_chunks: index of the chunk's first output pair
+  uint2* stage;                   // n_chunks x kStageCap parked pairs
   uint32_t* pair_count;           // per caller pair: += matches
-  unsigned long long* running_total;  // matches written before this batch; += this batch's on exit
+  unsigned long long* running_total;  // matches written before this batch; += this batch's
   uint2* out_pairs;
   float* out_dist;                // kDist only
+  unsigned long long* status;     // one-pass kernel: n_chunks look-back words (never cleared: epoch-tagged)
+  uint32_t epoch;                 // one-pass kernel: 30 bits, different from the previous launches that used `status`
 };
 
+// Loads, ranks and slice offsets of one chunk (shared by the count and the scatter pass).  Returns the chunk total;
+// afterwards s_slice holds the exclusive prefix of the (iteration, warp) slices and rank[i] the rank inside a slice.
+__device__ __forceinline__ uint32_t chunk_rank(const ChunkDesc& d, const uint32_t* __restrict__ rowres, uint32_t (&m)[kCompactPer],
+                                               uint32_t (&rank)[kCompactPer], uint32_t* s_slice, uint32_t* s_total) {
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t n = d.n_swap & 0x7FFFFFFFu;
+  const uint32_t* src = rowres + d.row_abs;
+#pragma unroll
+  for (int i = 0; i < kCompactPer; i++) {
+    const uint32_t r = i * kCompactThreads + tid;
+    m[i] = r < n ? __ldg(src + r) : kNone;
+  }
+#pragma unroll
+  for (int i = 0; i < kCompactPer; i++) {
+    const uint32_t b = __ballot_sync(0xffffffffu, m[i] != kNone);
+    rank[i] = __popc(b & ((1u << lane) - 1u));
+    if (lane == 0) s_slice[i * (kCompactThreads / 32) + warp] = __popc(b);
+  }
+  __syncthreads();
+  if (warp == 0) {  // exclusive scan of the slice totals (row order = slice order)
+    uint32_t carry = 0;
+#pragma unroll
+    for (int k = 0; k < kCompactSlices / 32; k++) {
+      const uint32_t v = s_slice[32 * k + lane];
+      uint32_t inc = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t nb = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= (uint32_t)o) inc += nb;
+      }
+      s_slice[32 * k + lane] = carry + inc - v;
+      carry += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    if (lane == 0) *s_total = carry;
+  }
+  __syncthreads();
+  return *s_total;
+}
+
+template <bool kDist>
+__global__ void __launch_bounds__(kCompactThreads)
+compact_count_kernel(const CompactArgs a) {
+  __shared__ uint32_t s_slice[kCompactSlices];
+  __shared__ uint32_t s_total;
+  const uint32_t chunk = blockIdx.x, tid = threadIdx.x, warp = tid >> 5;
+  const uint4 dv = __ldg(reinterpret_cast<const uint4*>(a.chunks) + chunk);
+  const ChunkDesc d{dv.x, dv.y, dv.z, dv.w};
+  uint32_t m[kCompactPer], rank[kCompactPer];
+  const uint32_t total = chunk_rank(d, a.rowres, m, rank, s_slice, &s_total);
+  if (tid == 0) a.chunk_count[chunk] = total;
+  if (kDist || total == 0 || total > kStageCap) return;  // CTA-uniform
+  const bool swap = d.n_swap >> 31;
+  uint2* st = a.stage + (size_t)chunk * kStageCap;
+#pragma unroll
+  for (int i = 0; i < kCompactPer; i++) {
+    if (m[i] != kNone) {
+      const uint32_t row = d.row_local + i * kCompactThreads + tid;
+      st[s_slice[i * (kCompactThreads / 32) + warp] + rank[i]] = swap ? make_uint2(row, m[i]) : make_uint2(m[i], row);
+    }
+  }
+}
+
+// One CTA: exclusive prefix of the chunk totals (offsets relative to *running_total), per-pair counts, new total.
+__global__ void __launch_bounds__(1024)
+compact_scan_kernel(const CompactArgs a) {
+  __shared__ unsigned long long s_part[1024];
+  const unsigned long long base0 = *a.running_total;
+  const uint32_t n = a.n_chunks;
+  const uint32_t per = (n + 1023u) / 1024u;
+  const uint32_t c0 = min(n, threadIdx.x * per), c1 = min(n, c0 + per);
+  unsigned long long sum = 0;
+  for (uint32_t c = c0; c < c1; c++) sum += a.chunk_count[c];
+  s_part[threadIdx.x] = sum;
+  __syncthreads();
+  for (int o = 1; o < 1024; o <<= 1) {
+    const unsigned long long v = threadIdx.x >= (uint32_t)o ? s_part[threadIdx.x - o] : 0ull;
+    __syncthreads();
+    s_part[threadIdx.x] += v;
+    __syncthreads();
+  }
+  unsigned long long run = base0 + s_part[threadIdx.x] - sum;
+  for (uint32_t c = c0; c < c1; c++) {
+    const uint32_t cnt = a.chunk_count[c];
+    a.chunk_out[c] = run;
+    run += cnt;
+    if (cnt) atomicAdd(a.pair_count + a.chunks[c].pair, cnt);
+  }
+  __syncthreads();
+  if (threadIdx.x == 1023) *a.running_total = base0 + s_part[1023];
+}
+
+template <bool kDist>
+__global__ void __launch_bounds__(kCompactThreads)
+compact_scatter_kernel(const CompactArgs a) {
+  __shared__ uint32_t s_slice[kCompactSlices];
+  __shared__ uint32_t s_total;
+  __shared__ __align__(16) uint2 s_stage[kCompactChunk + 2];
+  const uint32_t chunk = blockIdx.x, tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t total = a.chunk_count[chunk];
+  if (total == 0) return;  // CTA-uniform
+  const unsigned long long dst0 = a.chunk_out[chunk];  // index of this chunk's first output pair
+  if (!kDist && total <= kStageCap) {  // parked by the count pass: the rows are not read again
+    if (tid < total) a.out_pairs[dst0 + tid] = a.stage[(size_t)chunk * kStageCap + tid];
+    return;
+  }
+  const uint4 dv = __ldg(reinterpret_cast<const uint4*>(a.chunks) + chunk);
+  const ChunkDesc d{dv.x, dv.y, dv.z, dv.w};
+  uint32_t m[kCompactPer], rank[kCompactPer];
+  chunk_rank(d, a.rowres, m, rank, s_slice, &s_total);
+  // ---- stage in output order ----
+  const uint32_t shift = (uint32_t)(dst0 & 1ull);  // staged one slot late when the destination is not 16-byte aligned
+  const bool swap = d.n_swap >> 31;
+#pragma unroll
+  for (int i = 0; i < kCompactPer; i++) {
+    if (m[i] != kNone) {
+      const uint32_t row = d.row_local + i * kCompactThreads + tid;
+      const uint32_t pos = s_slice[i * (kCompactThreads / 32) + warp] + rank[i];
+      s_stage[pos + shift] = swap ? make_uint2(row, m[i]) : make_uint2(m[i], row);
+    }
+  }
+  __syncthreads();
+  // ---- 16-byte stores: [dst0 - shift, ...) is 16-byte aligned; the slot before the first and the one after the last
+  // pair are not this chunk's
+  uint2* dst = a.out_pairs + (dst0 - shift);
+  const uint32_t n_slots = total + shift;
+  const uint4* st4 = reinterpret_cast<const uint4*>(s_stage);
+  for (uint32_t q = tid; q < (n_slots + 1) / 2; q += kCompactThreads) {
+    const uint32_t s0 = 2 * q;
+    const bool lo_ok = s0 >= shift, hi_ok = s0 + 1 < n_slots;
+    if (lo_ok && hi_ok) __stcs(reinterpret_cast<uint4*>(dst) + q, st4[q]);
+    else if (lo_ok) dst[s0] = s_stage[s0];
+    else if (hi_ok) dst[s0 + 1] = s_stage[s0 + 1];
+  }
+  if (kDist) {  // the distances take the same route through the (now free) staging area
+    __syncthreads();
+    float* s_dist = reinterpret_cast<float*>(s_stage);
+#pragma unroll
+    for (int i = 0; i < kCompactPer; i++) {
+      if (m[i] != kNone)
+        s_dist[s_slice[i * (kCompactThreads / 32) + warp] + rank[i]] = a.rowdist[d.row_abs + i * kCompactThreads + tid];
+    }
+    __syncthreads();
+    float* dd = a.out_dist + dst0;
+    for (uint32_t q = tid; q < total; q += kCompactThreads) dd[q] = s_dist[q];
+  }
+}
+
+// ---- small batches: ONE launch -------------------------------------------------------------------------
+// Up to a wave or two of chunks the three launches above are launch latency and nothing else (C2: 19 us against 11).
+// Here a chunk obtains the exclusive prefix of the chunk totals by decoupled look-back over one 64-bit status word per
+// chunk (launch epoch | state | value: no clearing between launches; 1024 predecessors inspected per round).  CTAs of
+// a 1-D grid are dispatched in index order, so a chunk's predecessors are always running or done (the assumption every
+// single-pass scan makes).  For large batches the look-back chain is what bounds this design (95-140 us per 24 M rows
+// in every variant measured), hence the three-launch form there.
 constexpr int kCompactLook = 4;  // status words inspected per thread and look-back round
 
 template <bool kDist>
-__global__ void __launch_bounds__(kCompactThreads, 10)
-compact_kernel(const CompactArgs a) {
+__global__ void __launch_bounds__(kCompactThreads)
+compact_onepass_kernel(const CompactArgs a) {
   __shared__ uint32_t s_slice[kCompactSlices];  // slice totals, then their exclusive prefix
   __shared__ uint32_t s_total, s_first, s_unready, s_sum;
   __shared__ __align__(16) uint2 s_stage[kCompactChunk + 2];
@@ -199,5 +359,6 @@ compact_kernel(const CompactArgs a) {
     for (uint32_t q = tid; q < total; q += kCompactThreads) dd[q] = s_dist[q];
   }
 }
+
 
 }  // namespace fm

@@ -128,8 +128,8 @@ struct fm_ctx {
   bool images_dirty = true;
   uint32_t dim = 0;
   // per-call scratch
-  fm::DevBuf d_meta_blob, d_rowres, d_rowdist, d_chunk_status, d_totals;
-  uint32_t compact_epoch = 0;  // tags the look-back status words of a compaction launch (fm_compact.cuh)
+  fm::DevBuf d_meta_blob, d_rowres, d_rowdist, d_chunk_count, d_chunk_out, d_chunk_stage, d_chunk_status, d_totals;
+  uint32_t compact_epoch = 0;  // tags the look-back status words of a one-pass compaction launch (fm_compact.cuh)
   fm::DevBuf d_bands, d_cands, d_redo, d_taskinfo;
   fm::DevBuf d_rowstat, d_surv;  // two-phase scoring: per-row rejection flags; survivor counts / unit prefix / lists
   // Fraction of tensor-path rows the certified rejection test threw out in the most recent finished call with
