@@ -648,14 +648,16 @@ int fm_match(fm_ctx* c, const uint32_t* pair_first, const uint32_t* pair_second,
           else compact_onepass_kernel<false><<<b.chunks, kCompactThreads, 0, c->stream>>>(ca);
           c->stats.kernel_launches += 1;
         } else if (want_dist) {
-          compact_count_kernel<true><<<b.chunks, kCompactThreads, 0, c->stream>>>(ca);
+          const uint32_t grid = std::min<uint32_t>(b.chunks, (uint32_t)c->sm_count * 8u);  // grid-stride over the chunks
+          compact_count_kernel<true><<<grid, kCompactThreads, 0, c->stream>>>(ca);
           compact_scan_kernel<<<1, 1024, 0, c->stream>>>(ca);
-          compact_scatter_kernel<true><<<b.chunks, kCompactThreads, 0, c->stream>>>(ca);
+          compact_scatter_kernel<true><<<grid, kCompactThreads, 0, c->stream>>>(ca);
           c->stats.kernel_launches += 3;
         } else {
-          compact_count_kernel<false><<<b.chunks, kCompactThreads, 0, c->stream>>>(ca);
+          const uint32_t grid = std::min<uint32_t>(b.chunks, (uint32_t)c->sm_count * 8u);
+          compact_count_kernel<false><<<grid, kCompactThreads, 0, c->stream>>>(ca);
           compact_scan_kernel<<<1, 1024, 0, c->stream>>>(ca);
-          compact_scatter_kernel<false><<<b.chunks, kCompactThreads, 0, c->stream>>>(ca);
+          compact_scatter_kernel<false><<<grid, kCompactThreads, 0, c->stream>>>(ca);
           c->stats.kernel_launches += 3;
         }
       }

@@ -99,56 +99,72 @@ __device__ __forceinline__ uint32_t chunk_rank(const ChunkDesc& d, const uint32_
   return *s_total;
 }
 
+// (Count and scatter walk the chunks with a grid-stride loop: dispatching one 256-thread CTA per chunk costs ~0.4 us of
+// block scheduling each, which for the 6 000 chunks of a 24 M-row batch was most of the kernel's time.)
 template <bool kDist>
 __global__ void __launch_bounds__(kCompactThreads)
 compact_count_kernel(const CompactArgs a) {
   __shared__ uint32_t s_slice[kCompactSlices];
   __shared__ uint32_t s_total;
-  const uint32_t chunk = blockIdx.x, tid = threadIdx.x, warp = tid >> 5;
-  const uint4 dv = __ldg(reinterpret_cast<const uint4*>(a.chunks) + chunk);
-  const ChunkDesc d{dv.x, dv.y, dv.z, dv.w};
-  uint32_t m[kCompactPer], rank[kCompactPer];
-  const uint32_t total = chunk_rank(d, a.rowres, m, rank, s_slice, &s_total);
-  if (tid == 0) a.chunk_count[chunk] = total;
-  if (kDist || total == 0 || total > kStageCap) return;  // CTA-uniform
-  const bool swap = d.n_swap >> 31;
-  uint2* st = a.stage + (size_t)chunk * kStageCap;
+  const uint32_t tid = threadIdx.x, warp = tid >> 5;
+  for (uint32_t chunk = blockIdx.x; chunk < a.n_chunks; chunk += gridDim.x) {
+    const uint4 dv = __ldg(reinterpret_cast<const uint4*>(a.chunks) + chunk);
+    const ChunkDesc d{dv.x, dv.y, dv.z, dv.w};
+    uint32_t m[kCompactPer], rank[kCompactPer];
+    const uint32_t total = chunk_rank(d, a.rowres, m, rank, s_slice, &s_total);
+    if (tid == 0) a.chunk_count[chunk] = total;
+    if (!kDist && total != 0 && total <= kStageCap) {  // CTA-uniform
+      const bool swap = d.n_swap >> 31;
+      uint2* st = a.stage + (size_t)chunk * kStageCap;
 #pragma unroll
-  for (int i = 0; i < kCompactPer; i++) {
-    if (m[i] != kNone) {
-      const uint32_t row = d.row_local + i * kCompactThreads + tid;
-      st[s_slice[i * (kCompactThreads / 32) + warp] + rank[i]] = swap ? make_uint2(row, m[i]) : make_uint2(m[i], row);
+      for (int i = 0; i < kCompactPer; i++) {
+        if (m[i] != kNone) {
+          const uint32_t row = d.row_local + i * kCompactThreads + tid;
+          st[s_slice[i * (kCompactThreads / 32) + warp] + rank[i]] = swap ? make_uint2(row, m[i]) : make_uint2(m[i], row);
+        }
+      }
     }
+    __syncthreads();  // s_slice / s_total are rewritten by the next chunk
   }
 }
 
 // One CTA: exclusive prefix of the chunk totals (offsets relative to *running_total), per-pair counts, new total.
 __global__ void __launch_bounds__(1024)
 compact_scan_kernel(const CompactArgs a) {
-  __shared__ unsigned long long s_part[1024];
+  __shared__ unsigned long long s_warp[32];
   const unsigned long long base0 = *a.running_total;
-  const uint32_t n = a.n_chunks;
+  const uint32_t n = a.n_chunks, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t per = (n + 1023u) / 1024u;
   const uint32_t c0 = min(n, threadIdx.x * per), c1 = min(n, c0 + per);
   unsigned long long sum = 0;
   for (uint32_t c = c0; c < c1; c++) sum += a.chunk_count[c];
-  s_part[threadIdx.x] = sum;
-  __syncthreads();
-  for (int o = 1; o < 1024; o <<= 1) {
-    const unsigned long long v = threadIdx.x >= (uint32_t)o ? s_part[threadIdx.x - o] : 0ull;
-    __syncthreads();
-    s_part[threadIdx.x] += v;
-    __syncthreads();
+  unsigned long long inc = sum;  // inclusive scan inside the warp, then across the 32 warps
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned long long v = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= (uint32_t)o) inc += v;
   }
-  unsigned long long run = base0 + s_part[threadIdx.x] - sum;
+  if (lane == 31) s_warp[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    const unsigned long long w = s_warp[lane];
+    unsigned long long winc = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned long long v = __shfl_up_sync(0xffffffffu, winc, o);
+      if (lane >= (uint32_t)o) winc += v;
+    }
+    s_warp[lane] = winc - w;  // exclusive prefix of the warp totals
+    if (lane == 31) *a.running_total = base0 + winc;
+  }
+  __syncthreads();
+  unsigned long long run = base0 + s_warp[warp] + inc - sum;
   for (uint32_t c = c0; c < c1; c++) {
     const uint32_t cnt = a.chunk_count[c];
     a.chunk_out[c] = run;
     run += cnt;
     if (cnt) atomicAdd(a.pair_count + a.chunks[c].pair, cnt);
   }
-  __syncthreads();
-  if (threadIdx.x == 1023) *a.running_total = base0 + s_part[1023];
 }
 
 template <bool kDist>
@@ -157,53 +173,56 @@ compact_scatter_kernel(const CompactArgs a) {
   __shared__ uint32_t s_slice[kCompactSlices];
   __shared__ uint32_t s_total;
   __shared__ __align__(16) uint2 s_stage[kCompactChunk + 2];
-  const uint32_t chunk = blockIdx.x, tid = threadIdx.x, warp = tid >> 5;
-  const uint32_t total = a.chunk_count[chunk];
-  if (total == 0) return;  // CTA-uniform
-  const unsigned long long dst0 = a.chunk_out[chunk];  // index of this chunk's first output pair
-  if (!kDist && total <= kStageCap) {  // parked by the count pass: the rows are not read again
-    if (tid < total) a.out_pairs[dst0 + tid] = a.stage[(size_t)chunk * kStageCap + tid];
-    return;
-  }
-  const uint4 dv = __ldg(reinterpret_cast<const uint4*>(a.chunks) + chunk);
-  const ChunkDesc d{dv.x, dv.y, dv.z, dv.w};
-  uint32_t m[kCompactPer], rank[kCompactPer];
-  chunk_rank(d, a.rowres, m, rank, s_slice, &s_total);
-  // ---- stage in output order ----
-  const uint32_t shift = (uint32_t)(dst0 & 1ull);  // staged one slot late when the destination is not 16-byte aligned
-  const bool swap = d.n_swap >> 31;
-#pragma unroll
-  for (int i = 0; i < kCompactPer; i++) {
-    if (m[i] != kNone) {
-      const uint32_t row = d.row_local + i * kCompactThreads + tid;
-      const uint32_t pos = s_slice[i * (kCompactThreads / 32) + warp] + rank[i];
-      s_stage[pos + shift] = swap ? make_uint2(row, m[i]) : make_uint2(m[i], row);
+  const uint32_t tid = threadIdx.x, warp = tid >> 5;
+  for (uint32_t chunk = blockIdx.x; chunk < a.n_chunks; chunk += gridDim.x) {
+    const uint32_t total = a.chunk_count[chunk];
+    if (total == 0) continue;  // CTA-uniform
+    const unsigned long long dst0 = a.chunk_out[chunk];  // index of this chunk's first output pair
+    if (!kDist && total <= kStageCap) {  // parked by the count pass: the rows are not read again
+      if (tid < total) a.out_pairs[dst0 + tid] = a.stage[(size_t)chunk * kStageCap + tid];
+      continue;
     }
-  }
-  __syncthreads();
-  // ---- 16-byte stores: [dst0 - shift, ...) is 16-byte aligned; the slot before the first and the one after the last
-  // pair are not this chunk's
-  uint2* dst = a.out_pairs + (dst0 - shift);
-  const uint32_t n_slots = total + shift;
-  const uint4* st4 = reinterpret_cast<const uint4*>(s_stage);
-  for (uint32_t q = tid; q < (n_slots + 1) / 2; q += kCompactThreads) {
-    const uint32_t s0 = 2 * q;
-    const bool lo_ok = s0 >= shift, hi_ok = s0 + 1 < n_slots;
-    if (lo_ok && hi_ok) __stcs(reinterpret_cast<uint4*>(dst) + q, st4[q]);
-    else if (lo_ok) dst[s0] = s_stage[s0];
-    else if (hi_ok) dst[s0 + 1] = s_stage[s0 + 1];
-  }
-  if (kDist) {  // the distances take the same route through the (now free) staging area
-    __syncthreads();
-    float* s_dist = reinterpret_cast<float*>(s_stage);
+    const uint4 dv = __ldg(reinterpret_cast<const uint4*>(a.chunks) + chunk);
+    const ChunkDesc d{dv.x, dv.y, dv.z, dv.w};
+    uint32_t m[kCompactPer], rank[kCompactPer];
+    chunk_rank(d, a.rowres, m, rank, s_slice, &s_total);
+    // ---- stage in output order ----
+    const uint32_t shift = (uint32_t)(dst0 & 1ull);  // staged one slot late when the destination is not 16-byte aligned
+    const bool swap = d.n_swap >> 31;
 #pragma unroll
     for (int i = 0; i < kCompactPer; i++) {
-      if (m[i] != kNone)
-        s_dist[s_slice[i * (kCompactThreads / 32) + warp] + rank[i]] = a.rowdist[d.row_abs + i * kCompactThreads + tid];
+      if (m[i] != kNone) {
+        const uint32_t row = d.row_local + i * kCompactThreads + tid;
+        const uint32_t pos = s_slice[i * (kCompactThreads / 32) + warp] + rank[i];
+        s_stage[pos + shift] = swap ? make_uint2(row, m[i]) : make_uint2(m[i], row);
+      }
     }
     __syncthreads();
-    float* dd = a.out_dist + dst0;
-    for (uint32_t q = tid; q < total; q += kCompactThreads) dd[q] = s_dist[q];
+    // ---- 16-byte stores: [dst0 - shift, ...) is 16-byte aligned; the slot before the first and the one after the
+    // last pair are not this chunk's
+    uint2* dst = a.out_pairs + (dst0 - shift);
+    const uint32_t n_slots = total + shift;
+    const uint4* st4 = reinterpret_cast<const uint4*>(s_stage);
+    for (uint32_t q = tid; q < (n_slots + 1) / 2; q += kCompactThreads) {
+      const uint32_t s0 = 2 * q;
+      const bool lo_ok = s0 >= shift, hi_ok = s0 + 1 < n_slots;
+      if (lo_ok && hi_ok) __stcs(reinterpret_cast<uint4*>(dst) + q, st4[q]);
+      else if (lo_ok) dst[s0] = s_stage[s0];
+      else if (hi_ok) dst[s0 + 1] = s_stage[s0 + 1];
+    }
+    if (kDist) {  // the distances take the same route through the (now free) staging area
+      __syncthreads();
+      float* s_dist = reinterpret_cast<float*>(s_stage);
+#pragma unroll
+      for (int i = 0; i < kCompactPer; i++) {
+        if (m[i] != kNone)
+          s_dist[s_slice[i * (kCompactThreads / 32) + warp] + rank[i]] = a.rowdist[d.row_abs + i * kCompactThreads + tid];
+      }
+      __syncthreads();
+      float* dd = a.out_dist + dst0;
+      for (uint32_t q = tid; q < total; q += kCompactThreads) dd[q] = s_dist[q];
+    }
+    __syncthreads();  // the staging area and s_slice are rewritten by the next chunk
   }
 }
 
