@@ -649,13 +649,13 @@ int fm_match(fm_ctx* c, const uint32_t* pair_first, const uint32_t* pair_second,
           c->stats.kernel_launches += 1;
         } else if (want_dist) {
           const uint32_t grid = std::min<uint32_t>(b.chunks, (uint32_t)c->sm_count * 8u);  // grid-stride over the chunks
-          compact_count_kernel<true><<<grid, kCompactThreads, 0, c->stream>>>(ca);
+          compact_count_kernel<true><<<b.chunks, kCompactThreads, 0, c->stream>>>(ca);  // (one CTA per chunk measured faster here)
           compact_scan_kernel<<<1, 1024, 0, c->stream>>>(ca);
           compact_scatter_kernel<true><<<grid, kCompactThreads, 0, c->stream>>>(ca);
           c->stats.kernel_launches += 3;
         } else {
           const uint32_t grid = std::min<uint32_t>(b.chunks, (uint32_t)c->sm_count * 8u);
-          compact_count_kernel<false><<<grid, kCompactThreads, 0, c->stream>>>(ca);
+          compact_count_kernel<false><<<b.chunks, kCompactThreads, 0, c->stream>>>(ca);
           compact_scan_kernel<<<1, 1024, 0, c->stream>>>(ca);
           compact_scatter_kernel<false><<<grid, kCompactThreads, 0, c->stream>>>(ca);
           c->stats.kernel_launches += 3;
