@@ -2,6 +2,8 @@
 
     frog_b200/libfrogmatch.so   CUDA kernels + C ABI (include/frogmatch.h), sm_100a only
     bin/match                   the drop-in `match` executable (C++ host, links libfrogmatch.so)
+    frog_b200/libfrogsurf.so    SURF3D producer: CUDA kernels + C ABI (include/frogsurf.h)
+    bin/surf3d                  the `surf3d` executable over it (MetaImage volumes in, keypoint files out)
 
 `python -m frog_b200.build` builds both; nvcc cross-compiles sm_100a without a GPU.
 """
@@ -16,6 +18,8 @@ CSRC = os.path.join(ROOT, "frog_b200", "csrc")
 LIB = os.path.join(ROOT, "frog_b200", "libfrogmatch.so")
 BIN = os.path.join(ROOT, "bin", "match")
 FMIO = os.path.join(ROOT, "frog_b200", "libfmio.so")
+SURF_LIB = os.path.join(ROOT, "frog_b200", "libfrogsurf.so")
+SURF_BIN = os.path.join(ROOT, "bin", "surf3d")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -76,10 +80,35 @@ def build_fmio(force: bool = False) -> str:
     return FMIO
 
 
+def build_surf_lib(force: bool = False, verbose: bool = False) -> str:
+    srcs = [os.path.join(CSRC, f) for f in ("fs_api.cu", "fs_kernels.cuh")] + [
+        os.path.join(ROOT, "include", f) for f in ("frogsurf.h", "frogsurf_debug.h")]
+    if not force and _newer(SURF_LIB, srcs):
+        return SURF_LIB
+    cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [
+        "-shared", "-o", SURF_LIB, os.path.join(CSRC, "fs_api.cu")]
+    subprocess.run(cmd, check=True, cwd=ROOT)
+    return SURF_LIB
+
+
+def build_surf_cli(force: bool = False) -> str:
+    srcs = [os.path.join(CSRC, f) for f in ("surf_main.cpp", "surf_io.cpp", "surf_io.h")] + [os.path.join(ROOT, "include", "frogsurf.h")]
+    if not force and _newer(SURF_BIN, srcs + [SURF_LIB]):
+        return SURF_BIN
+    os.makedirs(os.path.dirname(SURF_BIN), exist_ok=True)
+    cmd = ["g++", "-O2", "-std=c++17", "-I", os.path.join(ROOT, "include"),
+           os.path.join(CSRC, "surf_main.cpp"), os.path.join(CSRC, "surf_io.cpp"),
+           "-o", SURF_BIN, "-L", os.path.dirname(SURF_LIB), "-lfrogsurf", "-lz", "-Wl,-rpath,$ORIGIN/../frog_b200"]
+    subprocess.run(cmd, check=True, cwd=ROOT)
+    return SURF_BIN
+
+
 def build_all(force: bool = False) -> None:
     build_lib(force)
     build_cli(force)
     build_fmio(force)
+    build_surf_lib(force)
+    build_surf_cli(force)
 
 
 if __name__ == "__main__":

@@ -1,0 +1,224 @@
+#include "surf_io.h"
+
+#include <zlib.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <map>
+#include <sstream>
+
+namespace fsio {
+
+namespace {
+
+size_t type_size(int t) { return t == FS_U8 ? 1 : (t == FS_I16 || t == FS_U16) ? 2 : 4; }
+
+std::string trim(const std::string& s) {
+  size_t a = s.find_first_not_of(" \t\r\n"), b = s.find_last_not_of(" \t\r\n");
+  return a == std::string::npos ? std::string() : s.substr(a, b - a + 1);
+}
+
+template <typename T>
+void flip_axis(std::vector<unsigned char>& data, const int dims[3], int axis) {
+  T* p = reinterpret_cast<T*>(data.data());
+  const size_t nx = dims[0], ny = dims[1], nz = dims[2];
+  const size_t n[3] = {nx, ny, nz};
+  for (size_t z = 0; z < nz; z++)
+    for (size_t y = 0; y < ny; y++)
+      for (size_t x = 0; x < nx; x++) {
+        size_t c[3] = {x, y, z};
+        if (c[axis] >= n[axis] / 2) continue;
+        size_t o[3] = {x, y, z};
+        o[axis] = n[axis] - 1 - c[axis];
+        std::swap(p[c[0] + nx * (c[1] + ny * c[2])], p[o[0] + nx * (o[1] + ny * o[2])]);
+      }
+}
+
+double sspacing(const double spacing[3]) { return std::pow(spacing[0] * spacing[1] * spacing[2], 1.0 / 3.0); }
+
+}  // namespace
+
+bool read_metaimage(const std::string& path, Volume& out, std::string& err) {
+  std::ifstream f(path, std::ios::binary);
+  if (!f) { err = "cannot open " + path; return false; }
+  std::map<std::string, std::string> kv;
+  std::string line, datafile;
+  while (std::getline(f, line)) {
+    const size_t eq = line.find('=');
+    if (eq == std::string::npos) continue;
+    const std::string k = trim(line.substr(0, eq)), v = trim(line.substr(eq + 1));
+    kv[k] = v;
+    if (k == "ElementDataFile") { datafile = v; break; }
+  }
+  auto ints = [&](const char* k, int* o, int n) { std::istringstream s(kv[k]); for (int i = 0; i < n; i++) if (!(s >> o[i])) return false; return true; };
+  auto dbls = [&](const char* k, double* o, int n) { std::istringstream s(kv[k]); for (int i = 0; i < n; i++) if (!(s >> o[i])) return false; return true; };
+  int ndims = 0;
+  if (!ints("NDims", &ndims, 1) || ndims != 3) { err = "MetaImage: NDims must be 3"; return false; }
+  if (!ints("DimSize", out.dims, 3)) { err = "MetaImage: DimSize"; return false; }
+  if (kv.count("ElementSpacing")) dbls("ElementSpacing", out.spacing, 3);
+  else if (kv.count("ElementSize")) dbls("ElementSize", out.spacing, 3);
+  if (kv.count("Offset")) dbls("Offset", out.origin, 3);
+  else if (kv.count("Position")) dbls("Position", out.origin, 3);
+  else if (kv.count("Origin")) dbls("Origin", out.origin, 3);
+  if (kv.count("ElementNumberOfChannels") && kv["ElementNumberOfChannels"] != "1") { err = "MetaImage: one channel only"; return false; }
+  if (kv.count("CompressedData") && (kv["CompressedData"] == "True" || kv["CompressedData"] == "true")) { err = "MetaImage: compressed data unsupported"; return false; }
+  if (kv.count("BinaryDataByteOrderMSB") && (kv["BinaryDataByteOrderMSB"] == "True" || kv["BinaryDataByteOrderMSB"] == "true")) { err = "MetaImage: big-endian data unsupported"; return false; }
+  const std::string et = kv["ElementType"];
+  if (et == "MET_UCHAR") out.voxel_type = FS_U8;
+  else if (et == "MET_SHORT") out.voxel_type = FS_I16;
+  else if (et == "MET_USHORT") out.voxel_type = FS_U16;
+  else if (et == "MET_INT") out.voxel_type = FS_I32;
+  else if (et == "MET_FLOAT") out.voxel_type = FS_F32;
+  else { err = "MetaImage: unsupported ElementType " + et; return false; }
+  const size_t bytes = (size_t)out.dims[0] * out.dims[1] * out.dims[2] * type_size(out.voxel_type);
+  out.data.resize(bytes);
+  if (datafile == "LOCAL") {
+    f.read(reinterpret_cast<char*>(out.data.data()), bytes);
+    if ((size_t)f.gcount() != bytes) { err = "MetaImage: short data"; return false; }
+  } else {
+    std::string dir;
+    const size_t slash = path.find_last_of('/');
+    if (slash != std::string::npos && datafile[0] != '/') dir = path.substr(0, slash + 1);
+    std::ifstream d(dir + datafile, std::ios::binary);
+    if (!d) { err = "cannot open " + dir + datafile; return false; }
+    d.read(reinterpret_cast<char*>(out.data.data()), bytes);
+    if ((size_t)d.gcount() != bytes) { err = "MetaImage: short data file"; return false; }
+  }
+  // vtkRobustImageReader.h:52-60, 97-113
+  for (const char* key : {"TransformMatrix", "Orientation", "Rotation"}) {
+    if (!kv.count(key)) continue;
+    double m[9];
+    if (!dbls(key, m, 9)) continue;
+    for (int i = 0; i < 3; i++) {
+      if (!(m[4 * i] < 0)) continue;
+      std::fprintf(stdout, "Warning : RobustReader flipping dimension %d\n", i);
+      switch (type_size(out.voxel_type)) {
+        case 1: flip_axis<uint8_t>(out.data, out.dims, i); break;
+        case 2: flip_axis<uint16_t>(out.data, out.dims, i); break;
+        default: flip_axis<uint32_t>(out.data, out.dims, i); break;
+      }
+      out.origin[i] = out.origin[i] - out.spacing[i] * (out.dims[i] - 1);
+    }
+  }
+  return true;
+}
+
+bool write_metaimage(const std::string& path, const Volume& v, std::string& err) {
+  static const char* names[] = {"MET_UCHAR", "MET_SHORT", "MET_USHORT", "MET_INT", "MET_FLOAT"};
+  std::ofstream f(path, std::ios::binary);
+  if (!f) { err = "cannot write " + path; return false; }
+  f << "ObjectType = Image\nNDims = 3\nBinaryData = True\nBinaryDataByteOrderMSB = False\nCompressedData = False\n";
+  f.precision(17);
+  f << "Offset = " << v.origin[0] << " " << v.origin[1] << " " << v.origin[2] << "\n";
+  f << "ElementSpacing = " << v.spacing[0] << " " << v.spacing[1] << " " << v.spacing[2] << "\n";
+  f << "DimSize = " << v.dims[0] << " " << v.dims[1] << " " << v.dims[2] << "\n";
+  f << "ElementType = " << names[v.voxel_type] << "\nElementDataFile = LOCAL\n";
+  f.write(reinterpret_cast<const char*>(v.data.data()), v.data.size());
+  return (bool)f;
+}
+
+bool write_points_csv(const std::string& path, const fs_point* pts, const float* desc, size_t n, size_t dsize,
+                      const double spacing[3], const double origin[3]) {
+  const double ss = sspacing(spacing);
+  std::ofstream f;
+  f.open(path, std::ofstream::out | std::ofstream::trunc);
+  if (!f) return false;
+  for (size_t i = 0; i != n; i++) {
+    const fs_point& p = pts[i];
+    f << p.x * spacing[0] + origin[0] << ",";
+    f << p.y * spacing[1] + origin[1] << ",";
+    f << p.z * spacing[2] + origin[2] << ",";
+    f << p.scale * ss << ",";
+    f << p.laplacian << ",";
+    f << p.response << ",";
+    for (size_t k = 0; k < dsize; k++) {
+      f << desc[i * dsize + k];
+      if (k < dsize - 1) f << ",";
+    }
+    f << std::endl;
+  }
+  f.close();
+  return true;
+}
+
+bool write_points_csvgz(const std::string& path, const char* gz_opts, int precision, const fs_point* pts, const float* desc,
+                        size_t n, size_t dsize, const double spacing[3], const double origin[3]) {
+  const double ss = sspacing(spacing);
+  std::string opts("w");
+  if (gz_opts) opts += gz_opts;
+  gzFile gz = gzopen(path.c_str(), opts.c_str());
+  if (!gz) return false;
+  std::string coeff("%f,"), coeff_end("%f");
+  if (precision >= 0) {
+    coeff_end = "%.";
+    coeff_end += std::to_string(precision);
+    coeff_end += "f";
+    coeff = coeff_end + ",";
+  }
+  // one formatted row per gzwrite instead of one gzprintf per cell: the deflate stream depends on the bytes only
+  std::vector<char> row(64 * (dsize + 8) + 512);
+  for (size_t i = 0; i != n; i++) {
+    const fs_point& p = pts[i];
+    size_t o = 0;
+    o += std::snprintf(row.data() + o, row.size() - o, "%f,", p.x * spacing[0] + origin[0]);
+    o += std::snprintf(row.data() + o, row.size() - o, "%f,", p.y * spacing[1] + origin[1]);
+    o += std::snprintf(row.data() + o, row.size() - o, "%f,", p.z * spacing[2] + origin[2]);
+    o += std::snprintf(row.data() + o, row.size() - o, "%f,", p.scale * ss);
+    o += std::snprintf(row.data() + o, row.size() - o, "%d,", p.laplacian);
+    o += std::snprintf(row.data() + o, row.size() - o, "%f,", p.response);
+    for (size_t k = 0; k < dsize; k++) {
+      if (row.size() - o < 400) row.resize(row.size() * 2);
+      o += std::snprintf(row.data() + o, row.size() - o, (k < dsize - 1 ? coeff : coeff_end).c_str(), desc[i * dsize + k]);
+    }
+    row[o++] = '\n';
+    if (gzwrite(gz, row.data(), (unsigned)o) != (int)o) { gzclose(gz); return false; }
+  }
+  return gzclose(gz) == Z_OK;
+}
+
+bool write_points_bin(const std::string& path, const fs_point* pts, const float* desc, size_t n, size_t dsize,
+                      const double spacing[3], const double origin[3]) {
+  const double ss = sspacing(spacing);
+  FILE* file = std::fopen(path.c_str(), "wb");
+  if (!file) return false;
+  std::vector<float> rec(6 + dsize);
+  for (size_t i = 0; i != n; i++) {
+    const fs_point& p = pts[i];
+    rec[0] = p.x * spacing[0] + origin[0];
+    rec[1] = p.y * spacing[1] + origin[1];
+    rec[2] = p.z * spacing[2] + origin[2];
+    rec[3] = p.scale * ss;
+    rec[4] = p.laplacian;
+    rec[5] = p.response;
+    if (dsize) std::memcpy(rec.data() + 6, desc + i * dsize, dsize * sizeof(float));
+    std::fwrite(rec.data(), sizeof(float), rec.size(), file);
+  }
+  std::fclose(file);
+  return true;
+}
+
+bool write_bounds_json(const std::string& path, const Volume& v) {
+  // picojson serialises a std::map (keys sorted) and numbers as "%.f" when integral below 2^53, else "%.17g"
+  auto num = [](double x) {
+    char buf[256];
+    double tmp;
+    std::snprintf(buf, sizeof buf, std::fabs(x) < (double)(1ULL << 53) && std::modf(x, &tmp) == 0 ? "%.f" : "%.17g", x);
+    return std::string(buf);
+  };
+  double b[6];
+  for (int i = 0; i < 3; i++) {
+    b[2 * i] = v.origin[i];
+    b[2 * i + 1] = v.origin[i] + (v.dims[i] - 1) * v.spacing[i];
+  }
+  std::ofstream f;
+  f.open(path, std::ofstream::out | std::ofstream::trunc);
+  if (!f) return false;
+  f << "{\"bounds\":{\"xmax\":" << num(b[1]) << ",\"xmin\":" << num(b[0]) << ",\"ymax\":" << num(b[3]) << ",\"ymin\":" << num(b[2])
+    << ",\"zmax\":" << num(b[5]) << ",\"zmin\":" << num(b[4]) << "}}";
+  f.close();
+  return true;
+}
+
+}  // namespace fsio

@@ -203,3 +203,32 @@ def write_group(dirpath: str, kind: str, n_images: int, n_points: int, fmt: str 
     with open(lst, "w") as f:
         f.write("\n".join(lines) + "\n")
     return lst
+
+
+def make_volume(shape, seed: int, blobs_per_mvox: float = 900.0, dtype=np.int16) -> np.ndarray:
+    """Synthetic CT-like volume [z, y, x] for the SURF3D producer: a smooth background, Gaussian
+    blobs of both signs over the detector's scale range (sigma 1.2 .. 14 voxels, small ones most frequent) and
+    a little noise, quantised to integers in roughly [-1000, 2500] like Hounsfield units."""
+    rng = np.random.default_rng(4000 + seed)
+    nz, ny, nx = shape
+    vol = np.zeros(shape, np.float32)
+    z, y, x = np.meshgrid(np.linspace(0, 1, nz, dtype=np.float32), np.linspace(0, 1, ny, dtype=np.float32),
+                          np.linspace(0, 1, nx, dtype=np.float32), indexing="ij")
+    vol += 200.0 * np.sin(3.1 * x + 0.3) * np.cos(2.3 * y) + 150.0 * z
+    n_blobs = max(8, int(blobs_per_mvox * nz * ny * nx / 1e6))
+    sig = 1.2 * (14.0 / 1.2) ** (rng.random(n_blobs) ** 2.2)
+    cz, cy, cx = rng.random(n_blobs) * nz, rng.random(n_blobs) * ny, rng.random(n_blobs) * nx
+    amp = rng.choice([-1.0, 1.0], n_blobs) * rng.uniform(300.0, 1500.0, n_blobs)
+    for s, a, pz, py, px in zip(sig, amp, cz, cy, cx):
+        r = int(np.ceil(3.5 * s))
+        z0, z1 = max(0, int(pz) - r), min(nz, int(pz) + r + 1)
+        y0, y1 = max(0, int(py) - r), min(ny, int(py) + r + 1)
+        x0, x1 = max(0, int(px) - r), min(nx, int(px) + r + 1)
+        if z0 >= z1 or y0 >= y1 or x0 >= x1:
+            continue
+        gz = np.exp(-0.5 * ((np.arange(z0, z1) - pz) / s) ** 2).astype(np.float32)
+        gy = np.exp(-0.5 * ((np.arange(y0, y1) - py) / s) ** 2).astype(np.float32)
+        gx = np.exp(-0.5 * ((np.arange(x0, x1) - px) / s) ** 2).astype(np.float32)
+        vol[z0:z1, y0:y1, x0:x1] += a * gz[:, None, None] * gy[None, :, None] * gx[None, None, :]
+    vol += rng.normal(0.0, 12.0, shape).astype(np.float32)
+    return np.clip(np.rint(vol), -1000, 2500).astype(dtype)

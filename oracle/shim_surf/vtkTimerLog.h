@@ -1,0 +1,2 @@
+// TEST INFRASTRUCTURE ONLY -- see vtkShimCore.h
+#include "vtkShimCore.h"
