@@ -20,6 +20,7 @@ BIN = os.path.join(ROOT, "bin", "match")
 FMIO = os.path.join(ROOT, "frog_b200", "libfmio.so")
 SURF_LIB = os.path.join(ROOT, "frog_b200", "libfrogsurf.so")
 SURF_BIN = os.path.join(ROOT, "bin", "surf3d")
+FSIO = os.path.join(ROOT, "frog_b200", "libfsio.so")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -85,7 +86,8 @@ def build_surf_lib(force: bool = False, verbose: bool = False) -> str:
         os.path.join(ROOT, "include", f) for f in ("frogsurf.h", "frogsurf_debug.h")]
     if not force and _newer(SURF_LIB, srcs):
         return SURF_LIB
-    cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [
+    # -fmad=false: the host and device statements of the interpolation solve must execute the same IEEE operations
+    cmd = ["nvcc"] + NVCC_FLAGS + ["-fmad=false"] + (["-Xptxas", "-v"] if verbose else []) + [
         "-shared", "-o", SURF_LIB, os.path.join(CSRC, "fs_api.cu")]
     subprocess.run(cmd, check=True, cwd=ROOT)
     return SURF_LIB
@@ -103,12 +105,24 @@ def build_surf_cli(force: bool = False) -> str:
     return SURF_BIN
 
 
+def build_fsio(force: bool = False) -> str:
+    """bin/surf3d's host I/O (MetaImage reader, keypoint writers) as a small C library (no CUDA)."""
+    srcs = [os.path.join(CSRC, f) for f in ("surf_io.cpp", "surf_io.h")] + [os.path.join(ROOT, "include", "frogsurf.h")]
+    if not force and _newer(FSIO, srcs):
+        return FSIO
+    cmd = ["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-I", os.path.join(ROOT, "include"),
+           os.path.join(CSRC, "surf_io.cpp"), "-o", FSIO, "-lz"]
+    subprocess.run(cmd, check=True, cwd=ROOT)
+    return FSIO
+
+
 def build_all(force: bool = False) -> None:
     build_lib(force)
     build_cli(force)
     build_fmio(force)
     build_surf_lib(force)
     build_surf_cli(force)
+    build_fsio(force)
 
 
 if __name__ == "__main__":

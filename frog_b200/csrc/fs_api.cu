@@ -15,6 +15,7 @@
 namespace {
 
 thread_local std::string g_create_error;
+int g_response_tile = 2;  // fs_debug_set_option("response_tile", v): 0 flat, 1 32x8x1, 2 32x4x2, 3 32x2x4, 4 32x1x8, 5 32x4x4
 
 struct Layer {
   fs::LayerDev dev{};
@@ -31,7 +32,8 @@ struct fs_ctx {
   int nx = 0, ny = 0, nz = 0;
   int32_t* d_cast = nullptr;
   fs::u64* d_integral = nullptr;
-  size_t vol_cap = 0;
+  fs::u64* d_split = nullptr;  // parity-split copy of the integral volume (fs_kernels.cuh, integral_z_kernel)
+  size_t vol_cap = 0, split_cap = 0, cast_cap = 0;
   void* d_in = nullptr;
   size_t in_cap = 0;
   double* d_blockmin = nullptr;
@@ -40,6 +42,9 @@ struct fs_ctx {
   uint8_t* d_layer_b = nullptr;
   size_t layer_f_cap = 0, layer_b_cap = 0;
   fs::Candidate* d_cand = nullptr;
+  fs::Interpolated* d_interp = nullptr;
+  size_t interp_cap = 0;
+  std::vector<fs::Interpolated> h_interp;
   unsigned* d_count = nullptr;  // [0] candidates, [1] clamped keypoints
   unsigned cand_cap = 0;
   std::vector<fs_point> points;
@@ -49,6 +54,7 @@ struct fs_ctx {
   size_t desc_cap = 0;
   uint32_t desc_size = 0;
   bool have_volume = false;
+  bool keep_cast = false;  // fs_debug_keep_cast_volume: also store vtk3DSURF::Cast (only the parity tests read it)
   fs_stats stats{};
 };
 
@@ -105,14 +111,27 @@ int run_integral(fs_ctx* c, const T* in, double* shift_out) {
   for (int i = 1; i < blocks; i++) mn = std::min(mn, mins[i]);
   const double shift = -mn;  // Shift->SetShift( -Range[ 0 ] ), vtk3DSURF.cxx:172
   *shift_out = shift;
-  const size_t smem = ((size_t)c->nx + 32) * sizeof(fs::u64);
+  // rows per tile: 16 (one per warp) while two CTAs still fit an SM's shared memory, fewer for very wide volumes
+  int rows = 16;
+  while (rows > 1 && ((size_t)c->nx * (rows + 1)) * sizeof(fs::u64) > 100 * 1024) rows >>= 1;
+  const size_t smem = ((size_t)c->nx * (rows + 1)) * sizeof(fs::u64);
   if (smem > 200 * 1024) return fail(c, FS_ERR_UNSUPPORTED, "nx = %d is too wide for the row scan", c->nx);
   FS_CUDA(c, cudaFuncSetAttribute(fs::integral_xy_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  fs::integral_xy_kernel<T><<<c->nz, 512, smem, c->stream>>>(in, c->d_cast, c->d_integral, c->nx, c->ny, shift);
+  fs::integral_xy_kernel<T><<<c->nz, 512, smem, c->stream>>>(in, c->keep_cast ? c->d_cast : nullptr, c->d_integral, c->nx, c->ny, rows, shift);
   const size_t slice = (size_t)c->nx * c->ny;
-  fs::integral_z_kernel<<<(unsigned)((slice + 255) / 256), 256, 0, c->stream>>>(c->d_integral, slice, c->nz);
+  fs::integral_z_kernel<<<(unsigned)((slice + 255) / 256), 256, 0, c->stream>>>(c->d_integral, c->d_split, c->nx, c->ny, c->nz);
   FS_CUDA(c, cudaGetLastError());
   return FS_OK;
+}
+
+fs::IntegralSplit split_view(const fs_ctx* c) {
+  fs::IntegralSplit I;
+  const long long hx = (c->nx + 1) / 2;
+  I.p0 = c->d_split;
+  I.p1 = c->d_split + (size_t)hx * c->ny * c->nz;
+  I.sy = hx;
+  I.sz = hx * c->ny;
+  return I;
 }
 
 fs::Integral integral_view(const fs_ctx* c) {
@@ -173,61 +192,6 @@ long long first_hit(int limit, int nr, int nc, int nd, PR pr, PC pc, PD pd) {
   return -1;
 }
 
-// ---- interpolation step (fasthessian.cxx:614-661): X = -pinv(H) dD, singular values below 0.001 of the
-// largest dropped.  H is symmetric, so its SVD is its eigen-decomposition up to signs: a cyclic Jacobi
-// eigen-solver in double gives pinv(H) = sum over kept eigenpairs of q q^T / lambda.  (The reference calls
-// cv::SVD from OpenCV, which is not part of the reference tree; results agree with any accurate SVD to
-// rounding, ~1e-13 relative, and are pinned by the tests to that tolerance, not bit for bit.)
-void solve_offsets(const double dD[4], const double Hs[10], double X[4]) {
-  double A[4][4] = {{Hs[0], Hs[4], Hs[5], Hs[6]}, {Hs[4], Hs[1], Hs[7], Hs[8]}, {Hs[5], Hs[7], Hs[2], Hs[9]}, {Hs[6], Hs[8], Hs[9], Hs[3]}};
-  double Q[4][4] = {{1, 0, 0, 0}, {0, 1, 0, 0}, {0, 0, 1, 0}, {0, 0, 0, 1}};
-  for (int sweep = 0; sweep < 64; sweep++) {
-    double off = 0, diag = 0;
-    for (int i = 0; i < 4; i++) {
-      diag += A[i][i] * A[i][i];
-      for (int j = i + 1; j < 4; j++) off += A[i][j] * A[i][j];
-    }
-    if (off <= 1e-32 * diag || off == 0) break;
-    for (int p = 0; p < 3; p++)
-      for (int q = p + 1; q < 4; q++) {
-        if (A[p][q] == 0) continue;
-        const double theta = (A[q][q] - A[p][p]) / (2 * A[p][q]);
-        const double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1));
-        const double cs = 1 / std::sqrt(t * t + 1), sn = t * cs;
-        for (int k = 0; k < 4; k++) {
-          const double akp = A[k][p], akq = A[k][q];
-          A[k][p] = cs * akp - sn * akq;
-          A[k][q] = sn * akp + cs * akq;
-        }
-        for (int k = 0; k < 4; k++) {
-          const double apk = A[p][k], aqk = A[q][k];
-          A[p][k] = cs * apk - sn * aqk;
-          A[q][k] = sn * apk + cs * aqk;
-        }
-        for (int k = 0; k < 4; k++) {
-          const double qkp = Q[k][p], qkq = Q[k][q];
-          Q[k][p] = cs * qkp - sn * qkq;
-          Q[k][q] = sn * qkp + cs * qkq;
-        }
-      }
-  }
-  double wmax = 0;
-  for (int i = 0; i < 4; i++) wmax = std::max(wmax, std::fabs(A[i][i]));
-  int largest = 0;
-  for (int i = 1; i < 4; i++) if (std::fabs(A[i][i]) > std::fabs(A[largest][largest])) largest = i;
-  for (int k = 0; k < 4; k++) X[k] = 0;
-  for (int i = 0; i < 4; i++) {
-    const double lam = A[i][i];
-    // W_inv(0,0) = 1 / W(0) unconditionally (a zero matrix gives inf -> NaN -> rejected, as in the reference);
-    // the others are dropped when W(i) / W(0) < 0.001
-    if (i != largest && !(std::fabs(lam) / wmax >= 0.001)) continue;
-    double proj = 0;
-    for (int k = 0; k < 4; k++) proj += Q[k][i] * dD[k];
-    const double coef = proj / lam;
-    for (int k = 0; k < 4; k++) X[k] -= Q[k][i] * coef;
-  }
-}
-
 bool by_response(const fs_point& i, const fs_point& j) { return i.response > j.response; }  // vtk3DSURF.cxx:32
 
 int upload_points(fs_ctx* c) {
@@ -284,8 +248,8 @@ void fs_destroy(fs_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
-  cudaFree(c->d_cast); cudaFree(c->d_integral); cudaFree(c->d_in); cudaFree(c->d_blockmin);
-  cudaFree(c->d_layer_f); cudaFree(c->d_layer_b); cudaFree(c->d_cand); cudaFree(c->d_count);
+  cudaFree(c->d_cast); cudaFree(c->d_integral); cudaFree(c->d_split); cudaFree(c->d_in); cudaFree(c->d_blockmin);
+  cudaFree(c->d_layer_f); cudaFree(c->d_layer_b); cudaFree(c->d_cand); cudaFree(c->d_interp); cudaFree(c->d_count);
   cudaFree(c->d_points); cudaFree(c->d_desc);
   if (c->ev[0]) cudaEventDestroy(c->ev[0]);
   if (c->ev[1]) cudaEventDestroy(c->ev[1]);
@@ -303,9 +267,10 @@ int fs_set_volume(fs_ctx* c, const void* voxels, int voxel_type, int nx, int ny,
   const size_t n = (size_t)nx * ny * nz;
   c->have_volume = false;
   c->nx = nx; c->ny = ny; c->nz = nz;
-  size_t cap2 = c->vol_cap;
-  if (int rc = ensure(c, c->d_cast, c->vol_cap, n)) return rc;
-  if (int rc = ensure(c, c->d_integral, cap2, n)) { c->vol_cap = 0; return rc; }
+  if (c->keep_cast)
+    if (int rc = ensure(c, c->d_cast, c->cast_cap, n)) return rc;
+  if (int rc = ensure(c, c->d_integral, c->vol_cap, n)) return rc;
+  if (int rc = ensure(c, c->d_split, c->split_cap, (size_t)2 * ((nx + 1) / 2) * ny * nz)) return rc;
   cudaPointerAttributes at{};
   const bool on_device = cudaPointerGetAttributes(&at, voxels) == cudaSuccess &&
                          (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged);
@@ -361,7 +326,7 @@ int fs_detect(fs_ctx* c, float threshold, uint32_t* n_points) {
   c->layers.clear();
   size_t off = 0;
   uint64_t computed = 0;
-  const fs::Integral I = integral_view(c);
+  const fs::IntegralSplit I = split_view(c);
   for (const LayerGeom& g : geom) {
     Layer L;
     L.voxels = (size_t)g.w * g.h * g.d;
@@ -377,7 +342,15 @@ int fs_detect(fs_ctx* c, float threshold, uint32_t* n_points) {
     if (iw > 0 && ih > 0 && id > 0) {
       const long long n = iw * ih * id;
       computed += (uint64_t)n;
-      fs::response_layer_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(I, L.dev);
+      auto grid = [&](int ty, int tz) { return dim3((unsigned)((iw + 31) / 32), (unsigned)((ih + ty - 1) / ty), (unsigned)((id + tz - 1) / tz)); };
+      switch (g_response_tile) {
+        case 0: fs::response_layer_flat_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(I, L.dev); break;
+        case 1: fs::response_layer_kernel<8, 1><<<grid(8, 1), 256, 0, c->stream>>>(I, L.dev); break;
+        case 3: fs::response_layer_kernel<2, 4><<<grid(2, 4), 256, 0, c->stream>>>(I, L.dev); break;
+        case 4: fs::response_layer_kernel<1, 8><<<grid(1, 8), 256, 0, c->stream>>>(I, L.dev); break;
+        case 5: fs::response_layer_kernel<4, 4><<<grid(4, 4), 512, 0, c->stream>>>(I, L.dev); break;
+        default: fs::response_layer_kernel<4, 2><<<grid(4, 2), 256, 0, c->stream>>>(I, L.dev); break;
+      }
     }
     c->layers.push_back(L);
   }
@@ -462,29 +435,29 @@ int fs_detect(fs_ctx* c, float threshold, uint32_t* n_points) {
     cap = found + 1024;  // rerun with room for all of them
   }
 
-  // ---- host: order as the reference's loops visit them, interpolate, keep the close ones ----
-  std::vector<fs::Candidate> cand(c->stats.n_candidates);
-  if (!cand.empty())
-    FS_CUDA(c, cudaMemcpy(cand.data(), c->d_cand, cand.size() * sizeof(fs::Candidate), cudaMemcpyDeviceToHost));
-  std::sort(cand.begin(), cand.end(), [](const fs::Candidate& a, const fs::Candidate& b) { return a.key < b.key; });
+  // ---- interpolation on the device, one thread per extremum; the host only restores the reference's push_back
+  // order (the loop position in `key`) among the accepted ones ----
+  const unsigned nc = c->stats.n_candidates;
   c->points.clear();
-  for (const fs::Candidate& k : cand) {
-    const PassHost& ph = passes[(size_t)(k.key >> 48)];
-    const fs::LayerDev &b = c->layers[ph.b].dev, &m = c->layers[ph.m].dev, &t = c->layers[ph.t].dev;
-    double X[4];
-    solve_offsets(k.dD, k.H, X);
-    const double xX = X[0], xY = X[1], xZ = X[2], xS = X[3];
-    if (std::fabs(xX) < 1.0f && std::fabs(xY) < 1.0f && std::fabs(xZ) < 1.0f && std::fabs(xS) < 1.0f) {
-      const int filterStep = m.filter - b.filter;
-      fs_point p;
-      p.x = static_cast<float>((k.c + xX) * t.step);
-      p.y = static_cast<float>((k.r + xY) * t.step);
-      p.z = static_cast<float>((k.d + xZ) * t.step);
-      p.scale = static_cast<float>((0.1333f) * (m.filter + xS * filterStep));
-      p.laplacian = k.laplacian;
-      p.response = k.response;
-      c->points.push_back(p);
-    }
+  if (nc) {
+    size_t icap = c->interp_cap;
+    if (int rc = ensure(c, c->d_interp, icap, (size_t)nc)) return rc;
+    c->interp_cap = icap;
+    fs::PassScales scales{};
+    for (size_t i = 0; i < passes.size() && i < 8; i++)
+      scales.p[i] = fs::PassScale{c->layers[passes[i].t].dev.step, c->layers[passes[i].m].dev.filter, c->layers[passes[i].b].dev.filter};
+    fs::interpolate_kernel<<<(nc + 127) / 128, 128, 0, c->stream>>>(c->d_cand, nc, scales, c->d_interp);
+    FS_CUDA(c, cudaGetLastError());
+    c->h_interp.resize(nc);
+    FS_CUDA(c, cudaMemcpyAsync(c->h_interp.data(), c->d_interp, (size_t)nc * sizeof(fs::Interpolated), cudaMemcpyDeviceToHost, c->stream));
+    FS_CUDA(c, cudaStreamSynchronize(c->stream));
+    std::vector<std::pair<uint64_t, uint32_t>> order;
+    order.reserve(nc);
+    for (unsigned i = 0; i < nc; i++)
+      if (c->h_interp[i].accepted) order.emplace_back(c->h_interp[i].key, i);
+    std::sort(order.begin(), order.end());
+    c->points.reserve(order.size());
+    for (const auto& o : order) c->points.push_back(c->h_interp[o.second].point);
   }
   c->desc_size = 0;
   c->stats.n_points = (uint32_t)c->points.size();
@@ -524,7 +497,7 @@ int fs_describe(fs_ctx* c, int type, int radius, int normalize) {
   if (!c) return FS_ERR_INVALID;
   if (!c->have_volume) return fail(c, FS_ERR_STATE, "fs_describe: no volume");
   if (type != 0 && type != 1) return fail(c, FS_ERR_UNSUPPORTED, "fs_describe: descriptor type %d needs vtkImageResize", type);
-  if (radius < 1 || (type == 0 && radius > 10) || radius > 64) return fail(c, FS_ERR_UNSUPPORTED, "fs_describe: radius %d", radius);
+  if (radius < 1 || (type == 0 && radius > 10) || radius > fs::kMaxRadius) return fail(c, FS_ERR_UNSUPPORTED, "fs_describe: radius %d", radius);
   FS_CUDA(c, cudaSetDevice(c->device));
   const size_t n = c->points.size();
   const size_t S = (size_t)8 * radius * radius * radius;
@@ -536,7 +509,7 @@ int fs_describe(fs_ctx* c, int type, int radius, int normalize) {
   FS_CUDA(c, cudaMemsetAsync(c->d_count + 1, 0, sizeof(unsigned), c->stream));
   FS_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
   if (n)
-    fs::describe_kernel<<<(unsigned)n, 256, smem, c->stream>>>(integral_view(c), c->d_points, (unsigned)n, radius, type, normalize,
+    fs::describe_kernel<<<(unsigned)n, 128, smem, c->stream>>>(integral_view(c), c->d_points, (unsigned)n, radius, type, normalize,
                                                                c->d_desc, c->d_count + 1);
   FS_CUDA(c, cudaGetLastError());
   FS_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
@@ -579,7 +552,7 @@ float fs_debug_expf(float x) { return fs::glibc_expf(x); }
 void fs_debug_expf_many(const float* x, float* y, size_t n) {
   for (size_t i = 0; i < n; i++) y[i] = fs::glibc_expf(x[i]);
 }
-void fs_debug_solve_offsets(const double* dD, const double* H10, double* X) { solve_offsets(dD, H10, X); }
+void fs_debug_solve_offsets(const double* dD, const double* H10, double* X) { fs::solve_offsets(dD, H10, X); }
 /* layer geometry and loop limits for an nx x ny x nz volume: per layer width, height, depth, step, filter, limit */
 int fs_debug_layers(int nx, int ny, int nz, int32_t* out6, int cap) {
   const std::vector<LayerGeom> g = layer_geometry(nx, ny, nz, octaves_for(nx, ny, nz));
@@ -605,9 +578,18 @@ uint32_t fs_debug_select(const float* response, uint32_t n, int number_of_points
   return (uint32_t)pts.size();
 }
 
+int fs_debug_set_option(const char* name, int value) {
+  if (name && std::strcmp(name, "response_tile") == 0) { g_response_tile = value; return FS_OK; }
+  return FS_ERR_INVALID;
+}
+
+void fs_debug_keep_cast_volume(fs_ctx* c, int on) { if (c) c->keep_cast = on != 0; }
+
 int fs_get_cast_volume(fs_ctx* c, int32_t* out) {
   if (!c || !out) return FS_ERR_INVALID;
   if (!c->have_volume) return fail(c, FS_ERR_STATE, "no volume");
+  if (!c->keep_cast || c->cast_cap < (size_t)c->nx * c->ny * c->nz)
+    return fail(c, FS_ERR_STATE, "the shifted volume is only kept after fs_debug_keep_cast_volume(ctx, 1)");
   FS_CUDA(c, cudaSetDevice(c->device));
   FS_CUDA(c, cudaMemcpy(out, c->d_cast, (size_t)c->nx * c->ny * c->nz * sizeof(int32_t), cudaMemcpyDeviceToHost));
   return FS_OK;

@@ -62,71 +62,89 @@ __global__ void volume_min_kernel(const T* __restrict__ in, size_t n, double* __
 // ---------------------------------------------------------------------------------------------
 // Integral volume (integral.cxx:11-121).  The reference runs three in-place passes (x, y, z); sums
 // of unsigned 64-bit integers are exact in any order, so this does x and y in one pass per z slice
-// (row scan + running column sums kept in shared memory) and z in a second, fully coalesced pass.
-// HBM traffic: voxel read + 8 B write, then 8 B read + 8 B write = 28 B / voxel for 4-byte voxels.
+// and z in a second, fully coalesced pass.  HBM traffic: voxel read + 8 B write, then 8 B read +
+// 16 B write (the second copy is the parity-split layout the response kernel gathers from)
+// = 36 B / voxel for 4-byte voxels, against 4 + 6 x 8 = 52 B for three separate passes.
+//
+// x/y pass: one CTA per z slice works through the slice in tiles of `rows` rows.  Phase 1: each warp
+// scans one row of the tile along x (32 voxels per step, shuffle scan, carry in lane 31) into shared
+// memory; phase 2: each thread owns columns, adds the tile's rows onto its running column sum (the
+// 2-D integral of the row above) and stores them, coalesced.  Two barriers per tile.
 // ---------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(512) integral_xy_kernel(const T* __restrict__ in, int32_t* __restrict__ cast_out,
-                                                           u64* __restrict__ out, int nx, int ny, double shift) {
+                                                           u64* __restrict__ out, int nx, int ny, int rows, double shift) {
   extern __shared__ u64 fs_sm[];
-  u64* col = fs_sm;        // nx running column sums: the 2-D integral of the row above
-  u64* wtot = fs_sm + nx;  // 32 warp totals
+  u64* col = fs_sm;        // nx running column sums
+  u64* tile = fs_sm + nx;  // rows x nx row prefixes
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
   const size_t slice = (size_t)nx * ny, base = (size_t)blockIdx.x * slice;
   for (int x = tid; x < nx; x += blockDim.x) col[x] = 0;
-  __syncthreads();
-  for (int y = 0; y < ny; y++) {
-    u64 carry = 0;
-    for (int x0 = 0; x0 < nx; x0 += blockDim.x) {
-      const int x = x0 + tid;
-      const size_t idx = base + (size_t)y * nx + x;
-      u64 v = 0;
-      if (x < nx) {
-        const int c = cast_shift(in[idx], shift);
-        if (cast_out) cast_out[idx] = c;
-        v = (u64)(long long)c;  // int -> unsigned long long as the reference's assignment does (integral.cxx:113)
-      }
+  for (int y0 = 0; y0 < ny; y0 += rows) {
+    const int nr = min(rows, ny - y0);
+    for (int r = warp; r < nr; r += nwarps) {
+      const size_t row = base + (size_t)(y0 + r) * nx;
+      u64 carry = 0;
+      for (int x0 = 0; x0 < nx; x0 += 32) {
+        const int x = x0 + lane;
+        u64 v = 0;
+        if (x < nx) {
+          const int c = cast_shift(in[row + x], shift);
+          if (cast_out) cast_out[row + x] = c;
+          v = (u64)(long long)c;  // int -> unsigned long long as the reference's assignment does (integral.cxx:113)
+        }
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const u64 t = __shfl_up_sync(0xffffffffu, v, o);
-        if (lane >= o) v += t;
+        for (int o = 1; o < 32; o <<= 1) {
+          const u64 t = __shfl_up_sync(0xffffffffu, v, o);
+          if (lane >= o) v += t;
+        }
+        v += carry;
+        if (x < nx) tile[(size_t)r * nx + x] = v;
+        carry = __shfl_sync(0xffffffffu, v, 31);
       }
-      if (lane == 31) wtot[warp] = v;
-      __syncthreads();
-      u64 before = carry, total = 0;
-      for (int w = 0; w < nwarps; w++) {
-        const u64 t = wtot[w];
-        if (w < warp) before += t;
-        total += t;
-      }
-      if (x < nx) {
-        const u64 s = col[x] + v + before;
-        col[x] = s;
-        out[idx] = s;
-      }
-      carry += total;
-      __syncthreads();
     }
+    __syncthreads();
+    for (int x = tid; x < nx; x += blockDim.x) {
+      u64 c = col[x];
+      for (int r = 0; r < nr; r++) {
+        c += tile[(size_t)r * nx + x];
+        out[base + (size_t)(y0 + r) * nx + x] = c;
+      }
+      col[x] = c;
+    }
+    __syncthreads();
   }
 }
 
-__global__ void integral_z_kernel(u64* __restrict__ vol, size_t slice, int nz) {
+// z pass, in place, plus the parity-split copy: split[x & 1][z][y][x >> 1] with row pitch hx = (nx + 1) / 2.  The
+// response layers sample the volume at even x only (steps 2 .. 16), and every box corner sits at a fixed offset
+// from that x, so one gather instruction of a warp touches x of ONE parity: in the split layout those 32 addresses
+// are contiguous (256 B) instead of strided over 512 B.
+__global__ void integral_z_kernel(u64* __restrict__ vol, u64* __restrict__ split, int nx, int ny, int nz) {
+  const size_t slice = (size_t)nx * ny;
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= slice) return;
+  const int x = (int)(i % nx), y = (int)(i / nx);
+  const int hx = (nx + 1) / 2;
+  const size_t sslice = (size_t)hx * ny;
+  u64* sp = split + (size_t)(x & 1) * sslice * nz + (size_t)y * hx + (x >> 1);
   u64 acc = vol[i];
+  sp[0] = acc;
   int z = 1;
   for (; z + 4 <= nz; z += 4) {
     u64* p = vol + (size_t)z * slice + i;
+    u64* q = sp + (size_t)z * sslice;
     const u64 a = p[0], b = p[slice], c = p[2 * slice], d = p[3 * slice];
-    acc += a; p[0] = acc;
-    acc += b; p[slice] = acc;
-    acc += c; p[2 * slice] = acc;
-    acc += d; p[3 * slice] = acc;
+    acc += a; p[0] = acc; q[0] = acc;
+    acc += b; p[slice] = acc; q[sslice] = acc;
+    acc += c; p[2 * slice] = acc; q[2 * sslice] = acc;
+    acc += d; p[3 * slice] = acc; q[3 * sslice] = acc;
   }
   for (; z < nz; z++) {
     u64* p = vol + (size_t)z * slice + i;
     acc += *p;
     *p = acc;
+    sp[(size_t)z * sslice] = acc;
   }
 }
 
@@ -139,23 +157,33 @@ struct Integral {
   int nx, ny, nz;
 };
 
-__device__ __forceinline__ u64 box_sum(const Integral& I, int x0, int y0, int z0, int sx, int sy, int sz) {
-  const long long x1 = x0 - 1, y1 = (long long)(y0 - 1) * I.sy, z1 = (long long)(z0 - 1) * I.sz;
-  const long long x2 = x0 + sx - 1, y2 = (long long)(y0 + sy - 1) * I.sy, z2 = (long long)(z0 + sz - 1) * I.sz;
-  const u64* p = I.p;
-  return __ldg(p + x2 + y2 + z2) - __ldg(p + x2 + y2 + z1) - __ldg(p + x2 + y1 + z2) - __ldg(p + x1 + y2 + z2) +
-         __ldg(p + x1 + y1 + z2) + __ldg(p + x1 + y2 + z1) + __ldg(p + x2 + y1 + z1) - __ldg(p + x1 + y1 + z1);
+// parity-split copy (see integral_z_kernel): (x odd ? p1 : p0) + (x >> 1) + y * sy + z * sz
+struct IntegralSplit {
+  const u64 *p0, *p1;  // even-x and odd-x halves
+  long long sy, sz;
+};
+
+__device__ __forceinline__ u64 box_sum(const IntegralSplit& I, int x0, int y0, int z0, int sx, int sy, int sz) {
+  const int x1 = x0 - 1, x2 = x0 + sx - 1;
+  const long long y1 = (long long)(y0 - 1) * I.sy, z1 = (long long)(z0 - 1) * I.sz;
+  const long long y2 = (long long)(y0 + sy - 1) * I.sy, z2 = (long long)(z0 + sz - 1) * I.sz;
+  const u64* a = ((x1 & 1) ? I.p1 : I.p0) + (x1 >> 1);
+  const u64* b = ((x2 & 1) ? I.p1 : I.p0) + (x2 >> 1);
+  return __ldg(b + y2 + z2) - __ldg(b + y2 + z1) - __ldg(b + y1 + z2) - __ldg(a + y2 + z2) +
+         __ldg(a + y1 + z2) + __ldg(a + y2 + z1) + __ldg(b + y1 + z1) - __ldg(a + y1 + z1);
 }
 
-__device__ __forceinline__ float boxf(const Integral& I, int x0, int y0, int z0, int sx, int sy, int sz) {
+__device__ __forceinline__ float boxf(const IntegralSplit& I, int x0, int y0, int z0, int sx, int sy, int sz) {
   return __ull2float_rn(box_sum(I, x0, y0, z0, sx, sy, sz));
 }
 
 // ---------------------------------------------------------------------------------------------
 // One response layer (FastHessian::buildResponseLayer, fasthessian.cxx:343-481): box-filter
 // approximations of the six second derivatives, determinant response, laplacian sign, blob flag.
-// 144 eight-byte gathers per voxel; neighbouring threads read neighbouring x (stride `step`), so a
-// warp's gathers fall into a handful of 128-byte lines that the following corner loads reuse from L1.
+// 144 eight-byte gathers per voxel, from the parity-split copy of the integral volume: neighbouring
+// threads take neighbouring layer voxels along x, so for the step-2 layers (7/8 of all voxels) each
+// gather instruction reads 256 contiguous bytes, and the lines it touches are reused from L1 by the
+// other corners of the same rows.
 // ---------------------------------------------------------------------------------------------
 struct LayerDev {
   float* responses;
@@ -166,12 +194,7 @@ struct LayerDev {
   float inv_volume9;   // fasthessian.cxx:355
 };
 
-__global__ void __launch_bounds__(256) response_layer_kernel(Integral I, LayerDev L) {
-  const int iw = L.width - 2 * L.limit, ih = L.height - 2 * L.limit, id = L.depth - 2 * L.limit;
-  const long long n = (long long)iw * ih * id;
-  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= n) return;
-  const int ax = L.limit + (int)(t % iw), ay = L.limit + (int)((t / iw) % ih), az = L.limit + (int)(t / ((long long)iw * ih));
+__device__ __forceinline__ void response_voxel(const IntegralSplit& I, const LayerDev& L, int ax, int ay, int az) {
   const int x = ax * L.step, y = ay * L.step, z = az * L.step;
   const int b = (L.filter - 1) / 2, l = L.filter / 3, w = L.filter;
   const int m = 2 * l - 1;
@@ -209,6 +232,29 @@ __global__ void __launch_bounds__(256) response_layer_kernel(Integral I, LayerDe
   L.isblob[index] = (Sdet2p > 0.0f) && (__fmul_rn(Trace, Det) > 0.0f);
   L.responses[index] = fabsf(__fmul_rn(Det, L.inv_volume9));
   L.laplacian[index] = Trace >= 0.0f ? 1 : 0;
+}
+
+// Thread -> voxel mapping: a CTA is a 32 x TY x TZ tile of layer voxels (each warp 32 consecutive x).  Voxels that are
+// neighbours in y and z read box corners on the same integral-volume rows (corner rows of one voxel are 2 * step apart
+// from its neighbour's), so a tile that extends in y and z reuses the lines it pulled into L1 instead of leaving
+// that reuse to whichever CTA runs next: the kernel is bound by L2 -> L1 traffic, not by HBM (ncu, profiles/).
+template <int TY, int TZ>
+__global__ void __launch_bounds__(32 * TY * TZ) response_layer_kernel(IntegralSplit I, LayerDev L) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int ax = L.limit + blockIdx.x * 32 + lane;
+  const int ay = L.limit + blockIdx.y * TY + warp % TY;
+  const int az = L.limit + blockIdx.z * TZ + warp / TY;
+  if (ax >= L.width - L.limit || ay >= L.height - L.limit || az >= L.depth - L.limit) return;
+  response_voxel(I, L, ax, ay, az);
+}
+
+// flat mapping (x fastest over the whole interior): kept for comparison, fs_debug_set_option("response_tile", 0)
+__global__ void __launch_bounds__(256) response_layer_flat_kernel(IntegralSplit I, LayerDev L) {
+  const int iw = L.width - 2 * L.limit, ih = L.height - 2 * L.limit, id = L.depth - 2 * L.limit;
+  const long long n = (long long)iw * ih * id;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  response_voxel(I, L, L.limit + (int)(t % iw), L.limit + (int)((t / iw) % ih), L.limit + (int)(t / ((long long)iw * ih)));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -315,6 +361,121 @@ __global__ void __launch_bounds__(256) extrema_kernel(ExtremaPass P, Candidate* 
 }
 
 // ---------------------------------------------------------------------------------------------
+// Interpolation step (FastHessian::interpolateStep / interpolateExtremum, fasthessian.cxx:575-661):
+// X = -pinv(H) dD with singular values below 0.001 of the largest dropped, keep the extremum when all
+// four offsets are below 1.  H is symmetric, so its SVD is its eigen-decomposition up to signs: a
+// cyclic Jacobi eigen-solver in double gives pinv(H) = sum over kept eigenpairs of q q^T / lambda.
+// The reference calls cv::SVD from OpenCV, which is not part of the reference tree; any accurate SVD
+// agrees with this to rounding (~1e-13 relative), and the tests pin the step to that tolerance.
+// One statement for host (CPU tests) and device (the library is compiled with -fmad=false, so both
+// sides execute the same IEEE operations).
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ inline void solve_offsets(const double dD[4], const double Hs[10], double X[4]) {
+  double A[4][4] = {{Hs[0], Hs[4], Hs[5], Hs[6]}, {Hs[4], Hs[1], Hs[7], Hs[8]}, {Hs[5], Hs[7], Hs[2], Hs[9]}, {Hs[6], Hs[8], Hs[9], Hs[3]}};
+  double Q[4][4] = {{1, 0, 0, 0}, {0, 1, 0, 0}, {0, 0, 1, 0}, {0, 0, 0, 1}};
+  for (int sweep = 0; sweep < 64; sweep++) {
+    double off = 0, diag = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      diag += A[i][i] * A[i][i];
+#pragma unroll
+      for (int j = i + 1; j < 4; j++) off += A[i][j] * A[i][j];
+    }
+    if (off <= 1e-32 * diag || off == 0) break;
+#pragma unroll
+    for (int p = 0; p < 3; p++)
+#pragma unroll
+      for (int q = p + 1; q < 4; q++) {
+        if (A[p][q] == 0) continue;
+        const double theta = (A[q][q] - A[p][p]) / (2 * A[p][q]);
+        const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1));
+        const double cs = 1 / sqrt(t * t + 1), sn = t * cs;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          const double akp = A[k][p], akq = A[k][q];
+          A[k][p] = cs * akp - sn * akq;
+          A[k][q] = sn * akp + cs * akq;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          const double apk = A[p][k], aqk = A[q][k];
+          A[p][k] = cs * apk - sn * aqk;
+          A[q][k] = sn * apk + cs * aqk;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          const double qkp = Q[k][p], qkq = Q[k][q];
+          Q[k][p] = cs * qkp - sn * qkq;
+          Q[k][q] = sn * qkp + cs * qkq;
+        }
+      }
+  }
+  double wmax = 0;
+  int largest = 0;
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+    if (fabs(A[i][i]) > wmax) { wmax = fabs(A[i][i]); largest = i; }
+#pragma unroll
+  for (int k = 0; k < 4; k++) X[k] = 0;
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const double lam = A[i][i];
+    // W_inv(0,0) = 1 / W(0) unconditionally (a zero matrix gives inf -> NaN -> rejected, as in the reference);
+    // the others are dropped when W(i) / W(0) < 0.001
+    if (i != largest && !(fabs(lam) / wmax >= 0.001)) continue;
+    double proj = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) proj += Q[k][i] * dD[k];
+    const double coef = proj / lam;
+#pragma unroll
+    for (int k = 0; k < 4; k++) X[k] -= Q[k][i] * coef;
+  }
+}
+
+struct PassScale {
+  int t_step, m_filter, b_filter;
+};
+struct PassScales {
+  PassScale p[8];
+};
+
+struct Interpolated {
+  u64 key;        // loop position of the extremum (Candidate::key)
+  fs_point point;
+  int accepted;
+  int pad_;
+};
+
+// fasthessian.cxx:591-611: the keypoint an accepted extremum becomes
+__host__ __device__ inline bool make_point(const Candidate& k, const PassScale& s, fs_point& p) {
+  double X[4];
+  solve_offsets(k.dD, k.H, X);
+  const double xX = X[0], xY = X[1], xZ = X[2], xS = X[3];
+  if (!(fabs(xX) < 1.0f && fabs(xY) < 1.0f && fabs(xZ) < 1.0f && fabs(xS) < 1.0f)) return false;
+  const int filterStep = s.m_filter - s.b_filter;
+  p.x = static_cast<float>((k.c + xX) * s.t_step);
+  p.y = static_cast<float>((k.r + xY) * s.t_step);
+  p.z = static_cast<float>((k.d + xZ) * s.t_step);
+  p.scale = static_cast<float>((double)(0.1333f) * (s.m_filter + xS * filterStep));
+  p.laplacian = k.laplacian;
+  p.response = k.response;
+  return true;
+}
+
+__global__ void __launch_bounds__(128) interpolate_kernel(const Candidate* __restrict__ cand, unsigned n, PassScales scales,
+                                                           Interpolated* __restrict__ out) {
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const Candidate k = cand[i];
+  Interpolated r;
+  r.key = k.key;
+  r.pad_ = 0;
+  r.point = fs_point{0, 0, 0, 0, 0, 0};
+  r.accepted = make_point(k, scales.p[(unsigned)(k.key >> 48) & 7], r.point) ? 1 : 0;
+  out[i] = r;
+}
+
+// ---------------------------------------------------------------------------------------------
 // glibc 2.39's expf (sysdeps/ieee754/flt-32/e_expf.c -- Szabolcs Nagy's table-driven algorithm:
 // x * 32/ln2 = k + r, 2^(k/32) from a 32-entry table, cubic in r, all in double, one final rounding
 // to float), restated from its published description.  Surf::gaussian calls expf (surf.cxx:227),
@@ -372,8 +533,8 @@ __host__ __device__ __forceinline__ float glibc_expf(float x) {
 
 // ---------------------------------------------------------------------------------------------
 // Descriptors (Surf::getDescriptor surf.cxx:63-156, getRawDescriptor :161-217).  One CTA per
-// keypoint: the (2 radius)^3 Haar samples are computed in parallel (36 gathers each: the two boxes of
-// a Haar wavelet share a face) and parked in shared memory as doubles; 48 threads then add up their
+// keypoint: the (2 radius)^3 Haar samples are computed in parallel (20 gathers each, see the kernel)
+// and parked in shared memory as doubles; 48 threads then add up their
 // sub-block's samples IN THE REFERENCE'S ORDER (u, v, w nested), because the sums are double
 // accumulations whose rounding depends on it.
 // ---------------------------------------------------------------------------------------------
@@ -411,50 +572,95 @@ __device__ __forceinline__ void haar3(const Integral& I, int x, int y, int z, in
   hz = __ll2float_rn(box_corners(I, xl, xR, yl, yR, zm, zr, cl) - box_corners(I, xl, xR, yl, yR, zl, zm, cl));
 }
 
-__global__ void __launch_bounds__(256) describe_kernel(Integral I, const fs_point* __restrict__ pts, unsigned n, int radius,
+// Per-axis tables of one keypoint: the sample grid is separable (sample_x depends on u only, ...), so the three
+// integral-volume planes a Haar wavelet touches along an axis -- lo = s - h - 1, mid = s - 1, hi = s + h - 1 for
+// sample coordinate s and half size h -- and the squared Gaussian offset are computed once per axis position.
+constexpr int kMaxRadius = 16;
+struct AxisTables {
+  long long lo[3][2 * kMaxRadius], mid[3][2 * kMaxRadius], hi[3][2 * kMaxRadius];  // premultiplied by the axis stride
+  int sample[3][2 * kMaxRadius];
+  float sq[3][2 * kMaxRadius];
+};
+
+__global__ void __launch_bounds__(128) describe_kernel(Integral I, const fs_point* __restrict__ pts, unsigned n, int radius,
                                                         int type, int normalize, float* __restrict__ desc,
                                                         unsigned* __restrict__ n_clamped) {
   extern __shared__ double fs_smd[];
   const unsigned id = blockIdx.x;
   if (id >= n) return;
   const fs_point pt = pts[id];
-  const int r3 = radius * radius * radius, S = 8 * r3;
+  const int r3 = radius * radius * radius, S = 8 * r3, R2 = 2 * radius;
   double* sx = fs_smd;  // [S] per component, sub-block major, (u, v, w) inside
   double* sy = fs_smd + S;
   double* sz = fs_smd + 2 * S;
   __shared__ double acc[48];
-  __shared__ int any_clamped;
-  if (threadIdx.x == 0) any_clamped = 0;
+  __shared__ AxisTables tab;
+  __shared__ int outside;
+  if (threadIdx.x == 0) outside = 0;
   __syncthreads();
 
   const double scale = (double)pt.scale;
-  const int x = f_round(pt.x), y = f_round(pt.y), z = f_round(pt.z);
   const float halfRadius = __double2float_rn(__ddiv_rn((double)__double2float_rn((double)radius - 1.0), 2.0));
   const int h = f_round(pt.scale);                                           // s = 2 * fRound(scale)
   const float sig = __double2float_rn(__dmul_rn((double)2.5f, scale));       // gaussian(..., 2.5f * scale)
   const float sig2 = __fmul_rn(sig, sig);
   const float norm = __fdiv_rn(1.0f, __fmul_rn(sig2, sig));                  // 1.0f / (sig*sig*sig)
   const float den = __fmul_rn(__fmul_rn(2.0f, sig), sig);                    // 2.0f*sig*sig
-  Clamp cl{false};
   const size_t dsize = type == 0 ? 48 : (size_t)3 * S;
+
+  if (threadIdx.x < 3 * R2) {
+    const int axis = threadIdx.x / R2, idx = threadIdx.x - axis * R2;
+    const float coord = axis == 0 ? pt.x : axis == 1 ? pt.y : pt.z;
+    const int dim = axis == 0 ? I.nx : axis == 1 ? I.ny : I.nz;
+    const long long stride = axis == 0 ? 1 : axis == 1 ? I.sy : I.sz;
+    const int centre = f_round(coord);
+    const int u = -radius + idx;
+    // sample_x = fRound(x + u*scale)
+    const int smp = f_round(__double2float_rn(__dadd_rn((double)centre, __dmul_rn((double)u, scale))));
+    // xs = fRound(ipt->x + (ix * scale)) with ix = (float) i + halfRadius, i the sub-block's first offset
+    const int i0 = -radius + (idx / radius) * radius;
+    const float ix = __fadd_rn((float)i0, halfRadius);
+    const int xs = f_round(__double2float_rn(__dadd_rn((double)coord, __dmul_rn((double)ix, scale))));
+    const float g = __fsub_rn((float)xs, (float)smp);
+    tab.sample[axis][idx] = smp;
+    tab.sq[axis][idx] = __fmul_rn(g, g);
+    tab.lo[axis][idx] = (long long)(smp - h - 1) * stride;
+    tab.mid[axis][idx] = (long long)(smp - 1) * stride;
+    tab.hi[axis][idx] = (long long)(smp + h - 1) * stride;
+    if (smp - h - 1 < 0 || smp + h - 1 >= dim) outside = 1;
+  }
+  __syncthreads();
+  const bool inside = outside == 0;
 
   for (int sidx = threadIdx.x; sidx < S; sidx += blockDim.x) {
     const int blk = sidx / r3, within = sidx - blk * r3;
-    const int i = -radius + (blk >> 2) * radius, j = -radius + ((blk >> 1) & 1) * radius, k = -radius + (blk & 1) * radius;
-    const int u = i + within / (radius * radius), v = j + (within / radius) % radius, w = k + within % radius;
-    const int sample_x = f_round(__double2float_rn(__dadd_rn((double)x, __dmul_rn((double)u, scale))));
-    const int sample_y = f_round(__double2float_rn(__dadd_rn((double)y, __dmul_rn((double)v, scale))));
-    const int sample_z = f_round(__double2float_rn(__dadd_rn((double)z, __dmul_rn((double)w, scale))));
+    const int iu = (blk >> 2) * radius + within / (radius * radius), iv = ((blk >> 1) & 1) * radius + (within / radius) % radius,
+              iw = (blk & 1) * radius + within % radius;
     float hx, hy, hz;
-    haar3(I, sample_x, sample_y, sample_z, h, hx, hy, hz, cl);
+    if (inside) {
+      // 20 gathers: the 8 corners {lo, hi}^3 are shared by the three wavelets, 4 more per wavelet through its mid plane
+      const u64* p = I.p;
+      const long long xl = tab.lo[0][iu], xm = tab.mid[0][iu], xh = tab.hi[0][iu];
+      const long long yl = tab.lo[1][iv], ym = tab.mid[1][iv], yh = tab.hi[1][iv];
+      const long long zl = tab.lo[2][iw], zm = tab.mid[2][iw], zh = tab.hi[2][iw];
+      const u64 clll = __ldg(p + xl + yl + zl), cllh = __ldg(p + xl + yl + zh), clhl = __ldg(p + xl + yh + zl), clhh = __ldg(p + xl + yh + zh);
+      const u64 chll = __ldg(p + xh + yl + zl), chlh = __ldg(p + xh + yl + zh), chhl = __ldg(p + xh + yh + zl), chhh = __ldg(p + xh + yh + zh);
+      const u64 mxll = __ldg(p + xm + yl + zl), mxlh = __ldg(p + xm + yl + zh), mxhl = __ldg(p + xm + yh + zl), mxhh = __ldg(p + xm + yh + zh);
+      const u64 myll = __ldg(p + xl + ym + zl), mylh = __ldg(p + xl + ym + zh), myhl = __ldg(p + xh + ym + zl), myhh = __ldg(p + xh + ym + zh);
+      const u64 mzll = __ldg(p + xl + yl + zm), mzlh = __ldg(p + xl + yh + zm), mzhl = __ldg(p + xh + yl + zm), mzhh = __ldg(p + xh + yh + zm);
+      // box(upper half) - box(lower half) along the wavelet's axis = hi - 2 mid + lo, inclusion-exclusion over the other two
+      const u64 ax = (chhh - 2 * mxhh + clhh) - (chhl - 2 * mxhl + clhl) - (chlh - 2 * mxlh + cllh) + (chll - 2 * mxll + clll);
+      const u64 ay = (chhh - 2 * myhh + chlh) - (chhl - 2 * myhl + chll) - (clhh - 2 * mylh + cllh) + (clhl - 2 * myll + clll);
+      const u64 az = (chhh - 2 * mzhh + chhl) - (chlh - 2 * mzhl + chll) - (clhh - 2 * mzlh + clhl) + (cllh - 2 * mzll + clll);
+      hx = __ll2float_rn((long long)ax);
+      hy = __ll2float_rn((long long)ay);
+      hz = __ll2float_rn((long long)az);
+    } else {
+      Clamp cl{false};
+      haar3(I, tab.sample[0][iu], tab.sample[1][iv], tab.sample[2][iw], h, hx, hy, hz, cl);
+    }
     if (type == 0) {
-      const float ix = __fadd_rn((float)i, halfRadius), jx = __fadd_rn((float)j, halfRadius), kx = __fadd_rn((float)k, halfRadius);
-      const int xs = f_round(__double2float_rn(__dadd_rn((double)pt.x, __dmul_rn((double)ix, scale))));
-      const int ys = f_round(__double2float_rn(__dadd_rn((double)pt.y, __dmul_rn((double)jx, scale))));
-      const int zs = f_round(__double2float_rn(__dadd_rn((double)pt.z, __dmul_rn((double)kx, scale))));
-      const float gx = __fsub_rn((float)xs, (float)sample_x), gy = __fsub_rn((float)ys, (float)sample_y),
-                  gz = __fsub_rn((float)zs, (float)sample_z);
-      const float num = __fadd_rn(__fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy)), __fmul_rn(gz, gz));
+      const float num = __fadd_rn(__fadd_rn(tab.sq[0][iu], tab.sq[1][iv]), tab.sq[2][iw]);
       const double gauss = (double)__fmul_rn(norm, glibc_expf(__fdiv_rn(-num, den)));
       sx[sidx] = __dmul_rn(gauss, (double)hx);
       sy[sidx] = __dmul_rn(gauss, (double)hy);
@@ -464,10 +670,9 @@ __global__ void __launch_bounds__(256) describe_kernel(Integral I, const fs_poin
       o[0] = hx; o[1] = hy; o[2] = hz;
     }
   }
-  if (cl.hit) any_clamped = 1;
-  __syncthreads();
-  if (threadIdx.x == 0 && any_clamped) atomicAdd(n_clamped, 1u);
+  if (threadIdx.x == 0 && !inside) atomicAdd(n_clamped, 1u);
   if (type != 0) return;
+  __syncthreads();
 
   if (threadIdx.x < 48) {
     const int blk = threadIdx.x / 6, comp = threadIdx.x % 6;

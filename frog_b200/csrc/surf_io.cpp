@@ -222,3 +222,39 @@ bool write_bounds_json(const std::string& path, const Volume& v) {
 }
 
 }  // namespace fsio
+
+// ---- plain-C face of the host I/O (frog_b200/libfsio.so), so the CPU test suite can compare the writers with the
+// reference's without a GPU ----
+extern "C" {
+
+// fmt: 0 csv, 1 csv.gz, 2 bin.  Returns 0 on success.
+int fsio_write_points(const char* path, int fmt, const char* gz_opts, int precision, const fs_point* pts, const float* desc,
+                      size_t n, size_t dsize, const double* spacing, const double* origin) {
+  bool ok = false;
+  if (fmt == 0) ok = fsio::write_points_csv(path, pts, desc, n, dsize, spacing, origin);
+  else if (fmt == 1) ok = fsio::write_points_csvgz(path, gz_opts, precision, pts, desc, n, dsize, spacing, origin);
+  else if (fmt == 2) ok = fsio::write_points_bin(path, pts, desc, n, dsize, spacing, origin);
+  return ok ? 0 : -1;
+}
+
+// Reads a MetaImage header + data; returns 0 and fills dims / spacing / origin / voxel_type, copying at most `cap`
+// bytes of voxel data into `data` (may be null to query the size through *bytes).
+int fsio_read_metaimage(const char* path, int* dims, double* spacing, double* origin, int* voxel_type, void* data, size_t cap,
+                        size_t* bytes) {
+  fsio::Volume v;
+  std::string err;
+  if (!fsio::read_metaimage(path, v, err)) return -1;
+  for (int i = 0; i < 3; i++) { dims[i] = v.dims[i]; spacing[i] = v.spacing[i]; origin[i] = v.origin[i]; }
+  *voxel_type = v.voxel_type;
+  if (bytes) *bytes = v.data.size();
+  if (data) std::memcpy(data, v.data.data(), v.data.size() < cap ? v.data.size() : cap);
+  return 0;
+}
+
+int fsio_write_bounds_json(const char* path, const int* dims, const double* spacing, const double* origin) {
+  fsio::Volume v;
+  for (int i = 0; i < 3; i++) { v.dims[i] = dims[i]; v.spacing[i] = spacing[i]; v.origin[i] = origin[i]; }
+  return fsio::write_bounds_json(path, v) ? 0 : -1;
+}
+
+}  // extern "C"

@@ -70,6 +70,8 @@ def load():
     L.fs_debug_solve_offsets.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.fs_debug_layers.restype = C.c_int
     L.fs_debug_layers.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
+    L.fs_debug_keep_cast_volume.argtypes = [C.c_void_p, C.c_int]
+    L.fs_debug_set_option.argtypes = [C.c_char_p, C.c_int]
     L.fs_debug_select.restype = C.c_uint32
     L.fs_debug_select.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.c_void_p]
     _lib = L
@@ -96,6 +98,9 @@ class Producer:
             self.close()
         except Exception:
             pass
+
+    def keep_cast_volume(self, on: bool = True):
+        self._L.fs_debug_keep_cast_volume(self._h, int(on))
 
     def _check(self, rc):
         if rc != 0:
@@ -179,6 +184,11 @@ def run(volume: np.ndarray, threshold=0.0, number_of_points=-1, descriptor_type=
 
 
 # ---- host-side pieces (CPU tests) ------------------------------------------------------------------
+def debug_set_option(name: str, value: int) -> None:
+    if load().fs_debug_set_option(name.encode(), value) != 0:
+        raise FrogSurfError(f"unknown option {name}")
+
+
 def debug_expf(x: np.ndarray) -> np.ndarray:
     L = load()
     x = np.ascontiguousarray(x, np.float32)
@@ -209,3 +219,70 @@ def debug_select(response: np.ndarray, number_of_points: int) -> np.ndarray:
     order = np.zeros(max(r.size, 1), np.uint32)
     n = L.fs_debug_select(r.ctypes.data, r.size, number_of_points, order.ctypes.data)
     return order[:n]
+
+
+# ---- host I/O of bin/surf3d (frog_b200/libfsio.so, no CUDA) ---------------------------------------------
+_fsio = None
+
+
+def _io():
+    global _fsio
+    if _fsio is None:
+        if not os.path.exists(build.FSIO):
+            raise FrogSurfError(f"{build.FSIO} is not built (python -m frog_b200.build)")
+        L = C.CDLL(build.FSIO)
+        L.fsio_write_points.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t,
+                                        C.c_size_t, C.c_void_p, C.c_void_p]
+        L.fsio_read_metaimage.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                          C.c_size_t, C.c_void_p]
+        L.fsio_write_bounds_json.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        _fsio = L
+    return _fsio
+
+
+def write_points(path: str, fmt: str, pts: np.ndarray, desc: np.ndarray, spacing=(1.0, 1.0, 1.0), origin=(0.0, 0.0, 0.0),
+                 gz_opts=None, precision=-1) -> None:
+    """vtk3DSURF::WritePointsCSV / CSVGZ / Binary (vtk3DSURF.cxx:405-525) on voxel-unit keypoints."""
+    pts = np.ascontiguousarray(pts, POINT_DTYPE)
+    desc = np.ascontiguousarray(desc, np.float32).reshape(len(pts), -1)
+    sp = np.asarray(spacing, np.float64)
+    org = np.asarray(origin, np.float64)
+    rc = _io().fsio_write_points(path.encode(), {"csv": 0, "csv.gz": 1, "bin": 2}[fmt], gz_opts.encode() if gz_opts else None,
+                                 precision, pts.ctypes.data, desc.ctypes.data, len(pts), desc.shape[1], sp.ctypes.data,
+                                 org.ctypes.data)
+    if rc != 0:
+        raise FrogSurfError(f"cannot write {path}")
+
+
+_MET = {0: np.uint8, 1: np.int16, 2: np.uint16, 3: np.int32, 4: np.float32}
+_MET_NAME = {np.dtype(np.uint8): "MET_UCHAR", np.dtype(np.int16): "MET_SHORT", np.dtype(np.uint16): "MET_USHORT",
+             np.dtype(np.int32): "MET_INT", np.dtype(np.float32): "MET_FLOAT"}
+
+
+def read_metaimage(path: str):
+    """(volume [z, y, x], spacing, origin) through bin/surf3d's own reader."""
+    dims = (C.c_int * 3)()
+    sp = (C.c_double * 3)()
+    org = (C.c_double * 3)()
+    vt = C.c_int()
+    nbytes = C.c_size_t()
+    if _io().fsio_read_metaimage(path.encode(), dims, sp, org, C.byref(vt), None, 0, C.byref(nbytes)) != 0:
+        raise FrogSurfError(f"cannot read {path}")
+    vol = np.zeros((dims[2], dims[1], dims[0]), _MET[vt.value])
+    _io().fsio_read_metaimage(path.encode(), dims, sp, org, C.byref(vt), vol.ctypes.data, vol.nbytes, C.byref(nbytes))
+    return vol, tuple(sp), tuple(org)
+
+
+def write_metaimage(path: str, volume: np.ndarray, spacing=(1.0, 1.0, 1.0), origin=(0.0, 0.0, 0.0), transform=None) -> None:
+    """Single-file MetaImage (.mha) of a [z, y, x] volume, for feeding bin/surf3d."""
+    v = np.ascontiguousarray(volume)
+    with open(path, "wb") as f:
+        hdr = "ObjectType = Image\nNDims = 3\nBinaryData = True\nBinaryDataByteOrderMSB = False\nCompressedData = False\n"
+        if transform is not None:
+            hdr += "TransformMatrix = " + " ".join(repr(float(t)) for t in transform) + "\n"
+        hdr += "Offset = %r %r %r\n" % tuple(float(o) for o in origin)
+        hdr += "ElementSpacing = %r %r %r\n" % tuple(float(s) for s in spacing)
+        hdr += "DimSize = %d %d %d\n" % (v.shape[2], v.shape[1], v.shape[0])
+        hdr += "ElementType = %s\nElementDataFile = LOCAL\n" % _MET_NAME[v.dtype]
+        f.write(hdr.encode())
+        f.write(v.tobytes())

@@ -205,7 +205,7 @@ def write_group(dirpath: str, kind: str, n_images: int, n_points: int, fmt: str 
     return lst
 
 
-def make_volume(shape, seed: int, blobs_per_mvox: float = 900.0, dtype=np.int16) -> np.ndarray:
+def make_volume(shape, seed: int, blobs_per_mvox: float = 900.0, dtype=np.int16, noise: float = 12.0, texture: float = 0.0) -> np.ndarray:
     """Synthetic CT-like volume [z, y, x] for the SURF3D producer: a smooth background, Gaussian
     blobs of both signs over the detector's scale range (sigma 1.2 .. 14 voxels, small ones most frequent) and
     a little noise, quantised to integers in roughly [-1000, 2500] like Hounsfield units."""
@@ -230,5 +230,9 @@ def make_volume(shape, seed: int, blobs_per_mvox: float = 900.0, dtype=np.int16)
         gy = np.exp(-0.5 * ((np.arange(y0, y1) - py) / s) ** 2).astype(np.float32)
         gx = np.exp(-0.5 * ((np.arange(x0, x1) - px) / s) ** 2).astype(np.float32)
         vol[z0:z1, y0:y1, x0:x1] += a * gz[:, None, None] * gy[None, :, None] * gx[None, None, :]
-    vol += rng.normal(0.0, 12.0, shape).astype(np.float32)
+    vol += rng.normal(0.0, noise, shape).astype(np.float32)
+    if texture > 0:  # fine-grained tissue-like texture: white noise smoothed to a ~2 voxel correlation length
+        from scipy.ndimage import gaussian_filter
+        t = gaussian_filter(rng.normal(0.0, 1.0, shape).astype(np.float32), 1.4)
+        vol += np.float32(texture) * t / t.std()
     return np.clip(np.rint(vol), -1000, 2500).astype(dtype)

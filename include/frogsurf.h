@@ -37,7 +37,7 @@ typedef enum fs_status {
   FS_ERR_INVALID = -1,
   FS_ERR_CUDA = -2,
   FS_ERR_NOMEM = -3,
-  FS_ERR_UNSUPPORTED = -4, /* descriptor type 2 (vtkImageResize sub-volumes), radius > 10 for type 0 */
+  FS_ERR_UNSUPPORTED = -4, /* descriptor type 2 (vtkImageResize sub-volumes), radius > 10 (type 0) or > 16 (type 1) */
   FS_ERR_STATE = -5        /* stage called before the one it depends on */
 } fs_status;
 
@@ -113,7 +113,8 @@ int fs_get_points(fs_ctx* ctx, fs_point* points, float* desc);
 int fs_get_stats(fs_ctx* ctx, fs_stats* out);
 
 /* ---- stage outputs, for the parity tests ------------------------------------------------------ */
-/* the shifted int volume (vtk3DSURF::Cast) and the integral volume, nx * ny * nz values each */
+/* the shifted int volume (vtk3DSURF::Cast; kept only after fs_debug_keep_cast_volume, frogsurf_debug.h) and the
+ * integral volume, nx * ny * nz values each */
 int fs_get_cast_volume(fs_ctx* ctx, int32_t* out);
 int fs_get_integral(fs_ctx* ctx, uint64_t* out);
 /* info: width, height, depth, step, filter (responselayer.h:26) */

@@ -23,6 +23,7 @@ def main():
     rx, rlap, rdesc = ref.update(threshold=0.0, number_of_points=npts)
     out["ref_update_s"] = time.time() - t
     p = surf.Producer(0)
+    p.keep_cast_volume(True)
     p.set_volume(vol)
     out["cast_equal"] = bool(np.array_equal(p.cast_volume(), ref.cast_volume()))
     out["integral_equal"] = bool(np.array_equal(p.integral(), ref.integral_volume()))
