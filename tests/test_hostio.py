@@ -241,3 +241,35 @@ def test_text_writer_matches_printf(built, tmp_path):
     synth.write_csv(kp, str(tmp_path / "a.csv"))
     synth._write_fast(kp, str(tmp_path / "b.csv"), "csv")
     assert (tmp_path / "a.csv").read_bytes() == (tmp_path / "b.csv").read_bytes()
+
+
+def test_descriptor_cells_are_strtof_on_every_value(built, tmp_path):
+    """The eight-bytes-at-a-time path for "%f" descriptor cells (`-?0.dddddd`): ALL 10^6 values, both signs, parsed
+    through the row loop and compared bit for bit with libc's strtof; and cells that only look like descriptor cells
+    fall through to the general path with the same result as before."""
+    import ctypes as C
+    libc = C.CDLL("libc.so.6")
+    libc.strtof.restype = C.c_float
+    libc.strtof.argtypes = [C.c_char_p, C.c_void_p]
+    vals = np.arange(1000000)
+    cells = np.char.add("0.", np.char.zfill(vals.astype(str), 6))
+    rng = np.random.default_rng(11)
+    neg = rng.random(1000000) < 0.5
+    cells = np.where(neg, np.char.add("-", cells), cells)
+    rows = cells.reshape(-1, 50)  # 6 header cells + 44 descriptor cells per row
+    text = "\n".join(",".join(r) for r in rows) + "\n"
+    path = str(tmp_path / "all.csv")
+    open(path, "w").write(text)
+    head, desc = hostio.read_keypoints(path, d_cap=64)
+    got = np.concatenate([head, desc], 1).reshape(-1)
+    assert got.size == 1000000
+    want = np.array([libc.strtof(c.encode(), None) for c in cells.tolist()], np.float32)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    assert np.signbit(got[vals == 0][neg[vals == 0]]).all()  # "-0.000000" keeps its sign
+    # near misses of the shape: seven decimals, exponent, a space, a hex digit, "1." instead of "0.", a short last cell
+    odd = ["0.1234567", "0.12345e1", "0.12 456", "0.12a456", "1.234567", "-1.000000", "0.123456 ", "+0.123456", "0.5"]
+    line = ",".join(["1", "2", "3", "4", "5", "6"] + odd) + "\n"
+    open(path, "w").write(line * 3)
+    head, desc = hostio.read_keypoints(path, d_cap=64)
+    want = np.array([libc.strtof(c.encode(), None) for c in odd], np.float32)
+    assert desc.shape == (3, len(odd)) and np.array_equal(desc[1].view(np.uint32), want.view(np.uint32))
