@@ -129,8 +129,8 @@ fs::IntegralSplit split_view(const fs_ctx* c) {
   const long long hx = (c->nx + 1) / 2;
   I.p0 = c->d_split;
   I.p1 = c->d_split + (size_t)hx * c->ny * c->nz;
-  I.sy = hx;
-  I.sz = hx * c->ny;
+  I.sy = (uint32_t)hx;
+  I.sz = (uint32_t)(hx * c->ny);
   return I;
 }
 
@@ -192,7 +192,43 @@ long long first_hit(int limit, int nr, int nc, int nd, PR pr, PC pc, PD pd) {
   return -1;
 }
 
-bool by_response(const fs_point& i, const fs_point& j) { return i.response > j.response; }  // vtk3DSURF.cxx:32
+// vtk3DSURF.cxx:209-226 with compareResponses (:32): partial_sort + resize when there are more points than asked for,
+// sort otherwise, nothing when number_of_points <= 0.  The reference sorts its Ipoint objects; which of two equal
+// responses comes first is decided by the algorithm's comparisons and moves only, never by the payload, so running the
+// SAME std::partial_sort / std::sort over 8-byte (response, index) keys and gathering afterwards gives the same order
+// at a third of the memory traffic.
+struct ResponseKey {
+  float response;
+  uint32_t index;
+};
+bool by_response(const ResponseKey& i, const ResponseKey& j) { return i.response > j.response; }
+
+void select_points(std::vector<fs_point>& pts, int number_of_points) {
+  if (number_of_points <= 0) return;
+  std::vector<ResponseKey> keys(pts.size());
+  for (size_t i = 0; i < pts.size(); i++) keys[i] = ResponseKey{pts[i].response, (uint32_t)i};
+  if (keys.size() > (size_t)number_of_points) {
+    // When no two responses are equal (and none is NaN) "the strongest K in descending order" is one sequence, whatever
+    // algorithm finds it: introsort over the keys is twice as fast as partial_sort's heap.  Any tie among the kept ones
+    // or across the cut sends the ORIGINAL order through the reference's own call instead.
+    std::vector<ResponseKey> fast(keys);
+    std::sort(fast.begin(), fast.end(), by_response);
+    bool unique = true;
+    for (size_t i = 0; i < (size_t)number_of_points && unique; i++) unique = fast[i].response > fast[i + 1].response;
+    for (size_t i = 0; i < fast.size() && unique; i++) unique = fast[i].response == fast[i].response;
+    if (unique) {
+      keys.swap(fast);
+    } else {
+      std::partial_sort(keys.begin(), keys.begin() + number_of_points, keys.end(), by_response);
+    }
+    keys.resize(number_of_points);
+  } else {
+    std::sort(keys.begin(), keys.end(), by_response);
+  }
+  std::vector<fs_point> out(keys.size());
+  for (size_t i = 0; i < keys.size(); i++) out[i] = pts[keys[i].index];
+  pts.swap(out);
+}
 
 int upload_points(fs_ctx* c) {
   const size_t n = c->points.size();
@@ -270,6 +306,7 @@ int fs_set_volume(fs_ctx* c, const void* voxels, int voxel_type, int nx, int ny,
   if (c->keep_cast)
     if (int rc = ensure(c, c->d_cast, c->cast_cap, n)) return rc;
   if (int rc = ensure(c, c->d_integral, c->vol_cap, n)) return rc;
+  if ((size_t)((nx + 1) / 2) * ny * nz >= (1ull << 32)) return fail(c, FS_ERR_UNSUPPORTED, "fs_set_volume: more than 2^33 voxels");
   if (int rc = ensure(c, c->d_split, c->split_cap, (size_t)2 * ((nx + 1) / 2) * ny * nz)) return rc;
   cudaPointerAttributes at{};
   const bool on_device = cudaPointerGetAttributes(&at, voxels) == cudaSuccess &&
@@ -467,14 +504,7 @@ int fs_detect(fs_ctx* c, float threshold, uint32_t* n_points) {
 
 int fs_select(fs_ctx* c, int number_of_points) {
   if (!c) return FS_ERR_INVALID;
-  if (number_of_points > 0) {
-    if (c->points.size() > (size_t)number_of_points) {
-      std::partial_sort(c->points.begin(), c->points.begin() + number_of_points, c->points.end(), by_response);
-      c->points.resize(number_of_points);
-    } else {
-      std::sort(c->points.begin(), c->points.end(), by_response);
-    }
-  }
+  select_points(c->points, number_of_points);
   c->desc_size = 0;
   c->stats.n_points = (uint32_t)c->points.size();
   return FS_OK;
@@ -566,14 +596,7 @@ int fs_debug_layers(int nx, int ny, int nz, int32_t* out6, int cap) {
 uint32_t fs_debug_select(const float* response, uint32_t n, int number_of_points, uint32_t* order) {
   std::vector<fs_point> pts(n);
   for (uint32_t i = 0; i < n; i++) { pts[i] = fs_point{0, 0, 0, 0, response[i], (int32_t)i}; }
-  if (number_of_points > 0) {
-    if (pts.size() > (size_t)number_of_points) {
-      std::partial_sort(pts.begin(), pts.begin() + number_of_points, pts.end(), by_response);
-      pts.resize(number_of_points);
-    } else {
-      std::sort(pts.begin(), pts.end(), by_response);
-    }
-  }
+  select_points(pts, number_of_points);
   for (size_t i = 0; i < pts.size(); i++) order[i] = (uint32_t)pts[i].laplacian;
   return (uint32_t)pts.size();
 }

@@ -157,24 +157,31 @@ struct Integral {
   int nx, ny, nz;
 };
 
-// parity-split copy (see integral_z_kernel): (x odd ? p1 : p0) + (x >> 1) + y * sy + z * sz
+// parity-split copy (see integral_z_kernel): (x odd ? p1 : p0) + (x >> 1) + y * sy + z * sz, element offsets in 32 bits
+// (volumes up to 2^32 voxels)
 struct IntegralSplit {
   const u64 *p0, *p1;  // even-x and odd-x halves
-  long long sy, sz;
+  uint32_t sy, sz;
 };
 
-__device__ __forceinline__ u64 box_sum(const IntegralSplit& I, int x0, int y0, int z0, int sx, int sy, int sz) {
-  const int x1 = x0 - 1, x2 = x0 + sx - 1;
-  const long long y1 = (long long)(y0 - 1) * I.sy, z1 = (long long)(z0 - 1) * I.sz;
-  const long long y2 = (long long)(y0 + sy - 1) * I.sy, z2 = (long long)(z0 + sz - 1) * I.sz;
-  const u64* a = ((x1 & 1) ? I.p1 : I.p0) + (x1 >> 1);
-  const u64* b = ((x2 & 1) ? I.p1 : I.p0) + (x2 >> 1);
-  return __ldg(b + y2 + z2) - __ldg(b + y2 + z1) - __ldg(b + y1 + z2) - __ldg(a + y2 + z2) +
-         __ldg(a + y1 + z2) + __ldg(a + y2 + z1) + __ldg(b + y1 + z1) - __ldg(a + y1 + z1);
+// Box sum (BoxIntegralOptim) for the voxel whose element offset in the split layout is `base` (its x is even: the
+// layers sample at steps 2 .. 16), the box given RELATIVE to the voxel.  Everything but `base` is the same for all
+// threads, so the corner offsets live in uniform registers and each gather costs one 32-bit add and one widening
+// multiply-add for its address instead of 64-bit arithmetic per corner.
+__device__ __forceinline__ u64 box_sum(const IntegralSplit& I, uint32_t base, int dx, int dy, int dz, int sx, int sy, int sz) {
+  const int x1 = dx - 1, x2 = dx + sx - 1;
+  const uint32_t y1 = (uint32_t)(dy - 1) * I.sy, y2 = (uint32_t)(dy + sy - 1) * I.sy;
+  const uint32_t z1 = (uint32_t)(dz - 1) * I.sz, z2 = (uint32_t)(dz + sz - 1) * I.sz;
+  const u64* a = (x1 & 1) ? I.p1 : I.p0;
+  const u64* b = (x2 & 1) ? I.p1 : I.p0;
+  const uint32_t oa = base + (uint32_t)(x1 >> 1), ob = base + (uint32_t)(x2 >> 1);  // modulo 2^32: the sums are offsets >= 0
+  return __ldg(b + (uint32_t)(ob + y2 + z2)) - __ldg(b + (uint32_t)(ob + y2 + z1)) - __ldg(b + (uint32_t)(ob + y1 + z2)) -
+         __ldg(a + (uint32_t)(oa + y2 + z2)) + __ldg(a + (uint32_t)(oa + y1 + z2)) + __ldg(a + (uint32_t)(oa + y2 + z1)) +
+         __ldg(b + (uint32_t)(ob + y1 + z1)) - __ldg(a + (uint32_t)(oa + y1 + z1));
 }
 
-__device__ __forceinline__ float boxf(const IntegralSplit& I, int x0, int y0, int z0, int sx, int sy, int sz) {
-  return __ull2float_rn(box_sum(I, x0, y0, z0, sx, sy, sz));
+__device__ __forceinline__ float boxf(const IntegralSplit& I, uint32_t base, int dx, int dy, int dz, int sx, int sy, int sz) {
+  return __ull2float_rn(box_sum(I, base, dx, dy, dz, sx, sy, sz));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -196,24 +203,26 @@ struct LayerDev {
 
 __device__ __forceinline__ void response_voxel(const IntegralSplit& I, const LayerDev& L, int ax, int ay, int az) {
   const int x = ax * L.step, y = ay * L.step, z = az * L.step;
+  const uint32_t base = (uint32_t)(x >> 1) + (uint32_t)y * I.sy + (uint32_t)z * I.sz;
   const int b = (L.filter - 1) / 2, l = L.filter / 3, w = L.filter;
   const int m = 2 * l - 1;
 
-  const float Dxx = __fsub_rn(boxf(I, x - b, y - l + 1, z - l + 1, w, m, m),
-                              __fmul_rn(boxf(I, x - l / 2, y - l + 1, z - l + 1, l, m, m), 3.0f));
-  const float Dyy = __fsub_rn(boxf(I, x - l + 1, y - b, z - l + 1, m, w, m),
-                              __fmul_rn(boxf(I, x - l + 1, y - l / 2, z - l + 1, m, l, m), 3.0f));
-  const float Dzz = __fsub_rn(boxf(I, x - l + 1, y - l + 1, z - b, m, m, w),
-                              __fmul_rn(boxf(I, x - l + 1, y - l + 1, z - l / 2, m, m, l), 3.0f));
-  const float Dxy = __fsub_rn(__fsub_rn(__fadd_rn(boxf(I, x - l, y - l, z - l + 1, l, l, m), boxf(I, x + 1, y + 1, z - l + 1, l, l, m)),
-                                        boxf(I, x - l, y + 1, z - l + 1, l, l, m)),
-                              boxf(I, x + 1, y - l, z - l + 1, l, l, m));
-  const float Dyz = __fsub_rn(__fsub_rn(__fadd_rn(boxf(I, x - l + 1, y - l, z - l, m, l, l), boxf(I, x - l + 1, y + 1, z + 1, m, l, l)),
-                                        boxf(I, x - l + 1, y - l, z + 1, m, l, l)),
-                              boxf(I, x - l + 1, y + 1, z - l, m, l, l));
-  const float Dxz = __fsub_rn(__fsub_rn(__fadd_rn(boxf(I, x - l, y - l + 1, z - l, l, m, l), boxf(I, x + 1, y - l + 1, z + 1, l, m, l)),
-                                        boxf(I, x - l, y - l + 1, z + 1, l, m, l)),
-                              boxf(I, x + 1, y - l + 1, z - l, l, m, l));
+  // boxes relative to (x, y, z), fasthessian.cxx:395-419
+  const float Dxx = __fsub_rn(boxf(I, base, -b, -l + 1, -l + 1, w, m, m),
+                              __fmul_rn(boxf(I, base, -(l / 2), -l + 1, -l + 1, l, m, m), 3.0f));
+  const float Dyy = __fsub_rn(boxf(I, base, -l + 1, -b, -l + 1, m, w, m),
+                              __fmul_rn(boxf(I, base, -l + 1, -(l / 2), -l + 1, m, l, m), 3.0f));
+  const float Dzz = __fsub_rn(boxf(I, base, -l + 1, -l + 1, -b, m, m, w),
+                              __fmul_rn(boxf(I, base, -l + 1, -l + 1, -(l / 2), m, m, l), 3.0f));
+  const float Dxy = __fsub_rn(__fsub_rn(__fadd_rn(boxf(I, base, -l, -l, -l + 1, l, l, m), boxf(I, base, 1, 1, -l + 1, l, l, m)),
+                                        boxf(I, base, -l, 1, -l + 1, l, l, m)),
+                              boxf(I, base, 1, -l, -l + 1, l, l, m));
+  const float Dyz = __fsub_rn(__fsub_rn(__fadd_rn(boxf(I, base, -l + 1, -l, -l, m, l, l), boxf(I, base, -l + 1, 1, 1, m, l, l)),
+                                        boxf(I, base, -l + 1, -l, 1, m, l, l)),
+                              boxf(I, base, -l + 1, 1, -l, m, l, l));
+  const float Dxz = __fsub_rn(__fsub_rn(__fadd_rn(boxf(I, base, -l, -l + 1, -l, l, m, l), boxf(I, base, 1, -l + 1, 1, l, m, l)),
+                                        boxf(I, base, -l, -l + 1, 1, l, m, l)),
+                              boxf(I, base, 1, -l + 1, -l, l, m, l));
 
   // fasthessian.cxx:428-430, in the reference's operand order and types (the 2.0 literal makes the second term,
   // and from there the running sum, double)

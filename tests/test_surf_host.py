@@ -162,3 +162,44 @@ def test_metaimage_reader(built, tmp_path):
     assert np.array_equal(got, vol[:, ::-1, :]) and org == (10.0, 20.0 - 2.0 * 4, 30.0)
     with pytest.raises(surf.FrogSurfError):
         surf.read_metaimage(str(tmp_path / "nope.mhd"))
+
+
+def test_select_ties_follow_libstdcxx_on_ipoint_like_objects(built, tmp_path):
+    """The order of equal responses after std::partial_sort / std::sort is decided by libstdc++'s algorithm, not by the
+    payload: the library's 8-byte keys must come out in the order an Ipoint-like object (with a std::vector member,
+    moved around like the reference's, ipoint.h:26-66; comparator as vtk3DSURF.cxx:32) does -- ties included, both
+    branches of vtk3DSURF.cxx:209-226."""
+    src = tmp_path / "ipsort.cpp"
+    src.write_text(r'''
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+struct Ip { float x, y, z, scale, response; int laplacian; std::vector<float> descriptor; int id; };
+bool compareResponses(Ip& i, Ip& j) { return (i.response > j.response); }
+int main(int argc, char** argv) {
+  int keep = atoi(argv[1]);
+  std::vector<Ip> points;
+  float r;
+  int id = 0;
+  while (scanf("%f", &r) == 1) { Ip p; p.response = r; p.id = id++; p.descriptor.assign(3, r); points.push_back(p); }
+  if (keep > 0) {
+    if ((int)points.size() > keep) {
+      std::partial_sort(points.begin(), points.begin() + keep, points.end(), compareResponses);
+      points.resize(keep);
+    } else {
+      std::sort(points.begin(), points.end(), compareResponses);
+    }
+  }
+  for (auto& p : points) printf("%d\n", p.id);
+}
+''')
+    exe = str(tmp_path / "ipsort")
+    subprocess.run(["g++", "-O3", "-std=c++17", str(src), "-o", exe], check=True)
+    rng = np.random.default_rng(21)
+    for n, keep, levels in ((500, 120, 7), (500, 800, 7), (3000, 2999, 40), (64, 16, 2), (2000, 500, 100000)):
+        resp = rng.integers(0, levels, n).astype(np.float32)
+        out = subprocess.run([exe, str(keep)], input="\n".join(repr(float(v)) for v in resp), capture_output=True, text=True, check=True)
+        want = np.array([int(t) for t in out.stdout.split()], np.uint32)
+        got = surf.debug_select(resp, keep)
+        assert np.array_equal(got, want), (n, keep, levels)
