@@ -309,6 +309,48 @@ def bin_match_wall(kps, kind, thr, ratio, gpus, formats):
     return out
 
 
+def producer_line(device, size=256, steps=5, warmup=3, points=20000):
+    """The step before the path: one size^3 volume through libfrogsurf.so (frog_b200.surf) -- host buffer
+    in, keypoints + descriptors out -- with the reference's own producer code (oracle/_ref/libsurf_ref.so, all cores)
+    timed on the same volume and the two outputs compared.  scripts/gpu_surf_bench.py is the full-size measurement."""
+    import time
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    import gpu_surf_bench as gsb
+    from frog_b200 import surf
+    from oracle import surf_oracle
+    vol = gsb.bench_volume(size)
+    p = surf.Producer(device)
+    walls = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        p.set_volume(vol)
+        n_det = p.detect(0.0)
+        p.select(points)
+        p.describe(0, 5, True)
+        pts, desc = p.points()
+        if it >= warmup:
+            walls.append(time.perf_counter() - t0)
+    st = p.stats()
+    p.close()
+    wall = float(np.median(walls))
+    out = {"metric": "voxels/s through the SURF3D producer (surf3d -t 0 -n 20000, type 0)", "workload": f"{size}^3 int16 volume",
+           "value": vol.size / wall, "unit": "voxels/s", "ms_per_volume": wall * 1e3,
+           "gpu_ms": {k: st[k] for k in ("ms_integral", "ms_response_map", "ms_extrema", "ms_describe")},
+           "n_detected": int(n_det), "n_points": int(len(pts)), "h2d_bytes": int(vol.nbytes), "d2h_bytes": int(pts.nbytes + desc.nbytes)}
+    if surf_oracle.available():
+        t0 = time.perf_counter()
+        ref = surf_oracle.RefSurf(vol)
+        rx, rlap, rdesc = ref.update(threshold=0.0, number_of_points=points)
+        ref_s = time.perf_counter() - t0
+        same = len(rx) == len(pts)
+        g = np.stack([pts["x"], pts["y"], pts["z"], pts["scale"], pts["response"]], 1)
+        out["cpu_baseline"] = {"kind": "reference", "seconds": ref_s, "value": vol.size / ref_s, "unit": "voxels/s", "cores": os.cpu_count()}
+        out["parity"] = {"n_points": [int(len(pts)), int(len(rx))],
+                         "point_values_differ": int(np.count_nonzero(g.view(np.uint32) != rx.view(np.uint32))) if same else None,
+                         "descriptor_values_differ": int(np.count_nonzero(desc.view(np.uint32) != rdesc.view(np.uint32))) if same else None}
+    return out
+
+
 def bench_ours(args):
     import torch
     import torch.distributed as dist
@@ -648,6 +690,11 @@ def bench_ours(args):
             except Exception as e:  # the baseline must never take the GPU numbers down with it
                 line["cpu_baseline"] = {"value": None, "unit": "descriptor pairs/s", "cores": os.cpu_count(), "kind": "reference",
                                         "sample": f"failed: {e}"}
+        if not args.no_producer and world == 1:
+            try:
+                line["producer"] = producer_line(local)  # (the reference producer's progress lines go to fd 1 = stderr here)
+            except Exception as e:
+                line["producer"] = {"error": str(e)[:300]}
         print(json.dumps(line), file=json_out, flush=True)
     if world > 1:
         dist.barrier(group=host_group)  # ranks > 0 wait here (on the CPU) while rank 0 times bin/match and the CPU baseline
@@ -663,6 +710,7 @@ def main():
     ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-wall", action="store_true")
+    ap.add_argument("--no-producer", action="store_true", help="skip the SURF3D producer sub-measurement (N = 1 only)")
     ap.add_argument("--no-wall-gz", action="store_true")
     ap.add_argument("--debug-opt", action="append", default=[], metavar="NAME=VALUE",
                     help="kernel-study switch (include/frogmatch_debug.h), e.g. variant=1; not for reported numbers")
