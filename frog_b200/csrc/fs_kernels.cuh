@@ -194,6 +194,7 @@ __device__ __forceinline__ float boxf(const IntegralSplit& I, uint32_t base, int
 // ---------------------------------------------------------------------------------------------
 struct LayerDev {
   float* responses;
+  float* masked;       // response where the voxel is a blob, -1 where it is not: what the extremum search compares with
   uint8_t* laplacian;
   uint8_t* isblob;
   int width, height, depth, step, filter;
@@ -238,8 +239,11 @@ __device__ __forceinline__ void response_voxel(const IntegralSplit& I, const Lay
   const float Det = __double2float_rn(det);
 
   const size_t index = (size_t)ax + (size_t)ay * L.width + (size_t)az * L.width * L.height;
-  L.isblob[index] = (Sdet2p > 0.0f) && (__fmul_rn(Trace, Det) > 0.0f);
-  L.responses[index] = fabsf(__fmul_rn(Det, L.inv_volume9));
+  const bool blob = (Sdet2p > 0.0f) && (__fmul_rn(Trace, Det) > 0.0f);
+  const float response = fabsf(__fmul_rn(Det, L.inv_volume9));
+  L.isblob[index] = blob;
+  L.responses[index] = response;
+  L.masked[index] = blob ? response : -1.0f;
   L.laplacian[index] = Trace >= 0.0f ? 1 : 0;
 }
 
@@ -274,6 +278,7 @@ __global__ void __launch_bounds__(256) response_layer_flat_kernel(IntegralSplit 
 // ---------------------------------------------------------------------------------------------
 struct LayerView {
   const float* responses;
+  const float* masked;  // see LayerDev
   const uint8_t* laplacian;
   const uint8_t* isblob;
   int width, height, depth;
@@ -286,8 +291,8 @@ __device__ __forceinline__ size_t lv_index(const LayerView& v, int scale, int r,
 __device__ __forceinline__ float lv_resp(const LayerView& v, int scale, int r, int c, int d) {
   return __ldg(v.responses + lv_index(v, scale, r, c, d));
 }
-__device__ __forceinline__ bool lv_blob(const LayerView& v, int scale, int r, int c, int d) {
-  return __ldg(v.isblob + lv_index(v, scale, r, c, d)) != 0;
+__device__ __forceinline__ float lv_masked(const LayerView& v, int scale, int r, int c, int d) {
+  return __ldg(v.masked + lv_index(v, scale, r, c, d));
 }
 
 struct ExtremaPass {
@@ -321,18 +326,29 @@ __global__ void __launch_bounds__(256) extrema_kernel(ExtremaPass P, Candidate* 
   if (pos >= P.first_sup) param &= 2;
   if (pos >= P.first_down) param &= 1;
 
-  const float candidate = lv_resp(P.m, P.scale_m, r, c, d);
-  if (candidate < P.thresh || !lv_blob(P.m, P.scale_m, r, c, d)) return;
-  for (int rr = -1; rr <= 1; ++rr)
-    for (int cc = -1; cc <= 1; ++cc)
-      for (int dd = -1; dd <= 1; ++dd) {
-        if ((param != 2 && lv_resp(P.t, 1, r + rr, c + cc, d + dd) >= candidate && lv_blob(P.t, 1, r + rr, c + cc, d + dd)) ||
-            ((rr != 0 || cc != 0) && lv_resp(P.m, P.scale_m, r + rr, c + cc, d + dd) >= candidate &&
-             lv_blob(P.m, P.scale_m, r + rr, c + cc, d + dd)) ||
-            (param != 1 && lv_resp(P.b, P.scale_b, r + rr, c + cc, d + dd) >= candidate &&
-             lv_blob(P.b, P.scale_b, r + rr, c + cc, d + dd)))
-          return;
-      }
+  // isExtremum (fasthessian.cxx:521-548): the candidate must be a blob at or above the threshold, and no blob voxel of
+  // the 3 x 3 x 3 neighbourhoods in the three layers may reach it (`>=`).  The reference walks the 27 offsets with an
+  // early return; the result does not depend on the order, so each rr plane's 27 values (9 offsets x 3 layers) are
+  // loaded together -- one latency instead of up to 54 dependent ones -- from the `masked` copy, where non-blob voxels
+  // hold -1 and can never reach a candidate (responses are >= 0, the threshold is >= 0).  Kept quirks: the middle layer
+  // skips every offset with rr == cc == 0 (dd = +-1 included), `param` decides whether top / bottom take part.
+  const float candidate = lv_masked(P.m, P.scale_m, r, c, d);  // -1 when the candidate is not a blob
+  if (!(candidate >= P.thresh) || !(candidate >= 0.0f)) return;  // (NaN = outside the layer's interior: never a candidate)
+  const bool use_t = param != 2, use_b = param != 1;
+  for (int rr = -1; rr <= 1; ++rr) {
+    float vt[9], vm[9], vb[9];
+#pragma unroll
+    for (int q = 0; q < 9; q++) {
+      const int cc = q / 3 - 1, dd = q % 3 - 1;
+      vt[q] = use_t ? lv_masked(P.t, 1, r + rr, c + cc, d + dd) : -1.0f;
+      vm[q] = (rr != 0 || cc != 0) ? lv_masked(P.m, P.scale_m, r + rr, c + cc, d + dd) : -1.0f;
+      vb[q] = use_b ? lv_masked(P.b, P.scale_b, r + rr, c + cc, d + dd) : -1.0f;
+    }
+    bool reached = false;
+#pragma unroll
+    for (int q = 0; q < 9; q++) reached |= (vt[q] >= candidate) | (vm[q] >= candidate) | (vb[q] >= candidate);
+    if (reached) return;
+  }
 
   const unsigned slot = atomicAdd(count, 1u);
   if (slot >= cap) return;
@@ -641,10 +657,14 @@ __global__ void __launch_bounds__(128) describe_kernel(Integral I, const fs_poin
   __syncthreads();
   const bool inside = outside == 0;
 
-  for (int sidx = threadIdx.x; sidx < S; sidx += blockDim.x) {
-    const int blk = sidx / r3, within = sidx - blk * r3;
-    const int iu = (blk >> 2) * radius + within / (radius * radius), iv = ((blk >> 1) & 1) * radius + (within / radius) % radius,
-              iw = (blk & 1) * radius + within % radius;
+  // Threads enumerate the samples with x fastest: the lanes of a warp then gather from a few rows of the integral
+  // volume (2 radius x-neighbours per row, `scale` voxels apart) instead of from 32 different z slices, which had the
+  // L1 data pipe at 97 % with one wavefront per lane per gather (ncu, profiles/).  Where a sample is STORED follows the
+  // reference's order -- sub-block major, (u, v, w) nested inside -- because that is the order the sums run in.
+  for (int g = threadIdx.x; g < S; g += blockDim.x) {
+    const int iu = g % R2, iv = (g / R2) % R2, iw = g / (R2 * R2);
+    const int bu = iu >= radius, bv = iv >= radius, bw = iw >= radius;
+    const int sidx = (bu * 4 + bv * 2 + bw) * r3 + ((iu - bu * radius) * radius + (iv - bv * radius)) * radius + (iw - bw * radius);
     float hx, hy, hz;
     if (inside) {
       // 20 gathers: the 8 corners {lo, hi}^3 are shared by the three wavelets, 4 more per wavelet through its mid plane

@@ -3,7 +3,7 @@ it on the box's cores, parity of the two outputs, per-kernel rooflines.
 
     python scripts/gpu_surf_bench.py [--size 400] [--steps 10] [--warmup 3] [--points 20000] [--no-ref] [--out FILE]
 
-Workload: one size^3 int16 volume (a 200^3 synthetic CT-like block mirrored to size^3, dense in blobs so that more than
+Workload: one size^3 int16 volume (eight independently seeded synthetic CT-like octants, dense in blobs so that more than
 `points` keypoints are detected), threshold 0, `-n points`, SURF3D descriptors (type 0, radius 5) -- run.sh's
 per-image surf3d call after resampling (run.sh:80-87).  A step = fs_set_volume (host buffer in: H2D inside the step)
 + fs_detect + fs_select + fs_describe + read-back of keypoints and descriptors.
@@ -22,9 +22,18 @@ from oracle import surf_oracle as so  # noqa: E402
 
 
 def bench_volume(size: int, seed: int = 50) -> np.ndarray:
+    """size^3 volume assembled from eight independently seeded octants (a mirrored volume would hold every structure
+    twice, hence pairs of exactly equal detector responses, which real images do not have)."""
     half = (size + 1) // 2
-    v = synth.make_volume((half, half, half), seed, blobs_per_mvox=1500.0, texture=250.0)
-    return np.ascontiguousarray(np.pad(v, ((0, size - half),) * 3, mode="symmetric"))
+    out = np.empty((size, size, size), np.int16)
+    k = 0
+    for z0 in (0, half):
+        for y0 in (0, half):
+            for x0 in (0, half):
+                v = synth.make_volume((half, half, half), seed + k, blobs_per_mvox=1500.0, texture=250.0)
+                out[z0:z0 + half, y0:y0 + half, x0:x0 + half] = v[:size - z0, :size - y0, :size - x0]
+                k += 1
+    return out
 
 
 def main():
