@@ -15,7 +15,7 @@
 namespace {
 
 thread_local std::string g_create_error;
-int g_response_tile = 2;  // fs_debug_set_option("response_tile", v): 0 flat, 1 32x8x1, 2 32x4x2, 3 32x2x4, 4 32x1x8, 5 32x4x4
+int g_response_tile = 5;  // fs_debug_set_option("response_tile", v): 0 flat, 1 32x8x1, 2 32x4x2, 3 32x2x4, 4 32x1x8, 5 32x4x4 (default), 6-9 register / CTA-size variants
 
 struct Layer {
   fs::LayerDev dev{};
@@ -379,8 +379,12 @@ int fs_detect(fs_ctx* c, float threshold, uint32_t* n_points) {
         case 1: fs::response_layer_kernel<8, 1><<<grid(8, 1), 256, 0, c->stream>>>(I, L.dev); break;
         case 3: fs::response_layer_kernel<2, 4><<<grid(2, 4), 256, 0, c->stream>>>(I, L.dev); break;
         case 4: fs::response_layer_kernel<1, 8><<<grid(1, 8), 256, 0, c->stream>>>(I, L.dev); break;
-        case 5: fs::response_layer_kernel<4, 4><<<grid(4, 4), 512, 0, c->stream>>>(I, L.dev); break;
-        default: fs::response_layer_kernel<4, 2><<<grid(4, 2), 256, 0, c->stream>>>(I, L.dev); break;
+        case 2: fs::response_layer_kernel<4, 2><<<grid(4, 2), 256, 0, c->stream>>>(I, L.dev); break;
+        case 6: fs::response_layer_kernel<4, 2, 5><<<grid(4, 2), 256, 0, c->stream>>>(I, L.dev); break;  // <= 51 registers
+        case 7: fs::response_layer_kernel<4, 2, 6><<<grid(4, 2), 256, 0, c->stream>>>(I, L.dev); break;  // <= 42 registers
+        case 8: fs::response_layer_kernel<4, 1, 8><<<grid(4, 1), 128, 0, c->stream>>>(I, L.dev); break;  // 128-thread CTAs
+        case 9: fs::response_layer_kernel<2, 1, 16><<<grid(2, 1), 64, 0, c->stream>>>(I, L.dev); break;  // 64-thread CTAs
+        default: fs::response_layer_kernel<4, 4><<<grid(4, 4), 512, 0, c->stream>>>(I, L.dev); break;
       }
     }
     c->layers.push_back(L);

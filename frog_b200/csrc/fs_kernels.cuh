@@ -251,8 +251,8 @@ __device__ __forceinline__ void response_voxel(const IntegralSplit& I, const Lay
 // neighbours in y and z read box corners on the same integral-volume rows (corner rows of one voxel are 2 * step apart
 // from its neighbour's), so a tile that extends in y and z reuses the lines it pulled into L1 instead of leaving
 // that reuse to whichever CTA runs next: the kernel is bound by L2 -> L1 traffic, not by HBM (ncu, profiles/).
-template <int TY, int TZ>
-__global__ void __launch_bounds__(32 * TY * TZ) response_layer_kernel(IntegralSplit I, LayerDev L) {
+template <int TY, int TZ, int kMinBlocks = 1>
+__global__ void __launch_bounds__(32 * TY * TZ, kMinBlocks) response_layer_kernel(IntegralSplit I, LayerDev L) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int ax = L.limit + blockIdx.x * 32 + lane;
   const int ay = L.limit + blockIdx.y * TY + warp % TY;

@@ -25,7 +25,8 @@ uint32_t fs_debug_select(const float* response, uint32_t n, int number_of_points
 /* keep the shifted int volume (vtk3DSURF::Cast) of the following fs_set_volume calls so that fs_get_cast_volume can
  * return it; off by default (256 MB of extra writes for a 400^3 volume that nothing but the tests reads) */
 /* experiment switches; "response_tile": thread-to-voxel mapping of the response-layer kernel (0 flat, 1 32x8x1,
- * 2 32x4x2 (default), 3 32x2x4, 4 32x1x8, 5 32x4x4).  Results are identical for every value. */
+ * 2 32x4x2, 3 32x2x4, 4 32x1x8, 5 32x4x4 (default), 6-9 register-capped / smaller-CTA variants).  Results are identical
+ * for every value. */
 int fs_debug_set_option(const char* name, int value);
 struct fs_ctx;
 void fs_debug_keep_cast_volume(struct fs_ctx* ctx, int on);

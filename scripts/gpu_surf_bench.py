@@ -113,7 +113,8 @@ def main():
         if "gather_bytes_l1" in r:
             r["gather_gbs"] = r["gather_bytes_l1"] / (r["ms"] * 1e-3) / 1e9
     if a.tile_sweep:
-        names = {0: "flat", 1: "32x8x1", 2: "32x4x2", 3: "32x2x4", 4: "32x1x8", 5: "32x4x4"}
+        names = {0: "flat", 1: "32x8x1", 2: "32x4x2", 3: "32x2x4", 4: "32x1x8", 5: "32x4x4", 6: "32x4x2 <=51 regs",
+                 7: "32x4x2 <=42 regs", 8: "32x4x1 (128 threads)", 9: "32x2x1 (64 threads)"}
         sweep = {}
         for v, name in names.items():
             surf.debug_set_option("response_tile", v)
@@ -122,7 +123,7 @@ def main():
                 p.detect(0.0)
                 ms.append(p.stats()["ms_response_map"])
             sweep[name] = float(np.median(ms[1:]))
-        surf.debug_set_option("response_tile", 2)
+        surf.debug_set_option("response_tile", 5)
         out["response_tile_sweep_ms"] = sweep
     if not a.no_ref:
         t0 = time.perf_counter()
