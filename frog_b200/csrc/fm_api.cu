@@ -647,6 +647,22 @@ int fm_match(fm_ctx* c, const uint32_t* pair_first, const uint32_t* pair_second,
           if (want_dist) compact_onepass_kernel<true><<<b.chunks, kCompactThreads, 0, c->stream>>>(ca);
           else compact_onepass_kernel<false><<<b.chunks, kCompactThreads, 0, c->stream>>>(ca);
           c->stats.kernel_launches += 1;
+        } else if (g_debug.compact_v >= 2) {
+          // persistent, software-pipelined count pass: three CTAs per SM, each with the next chunk's rows in flight
+          const uint32_t grid_count = std::min<uint32_t>(b.chunks, (uint32_t)c->sm_count * 3u);
+          const uint32_t grid = std::min<uint32_t>(b.chunks, (uint32_t)c->sm_count * 8u);
+          if (want_dist) {
+            if (g_debug.compact_v >= 3) compact_count3_kernel<true><<<grid_count, kCompactThreads, 0, c->stream>>>(ca);
+            else compact_count2_kernel<true><<<grid_count, kCompactThreads, 0, c->stream>>>(ca);
+            compact_scan2_kernel<<<1, 1024, 0, c->stream>>>(ca);
+            compact_scatter2_kernel<true><<<grid, kCompactThreads, 0, c->stream>>>(ca);
+          } else {
+            if (g_debug.compact_v >= 3) compact_count3_kernel<false><<<grid_count, kCompactThreads, 0, c->stream>>>(ca);
+            else compact_count2_kernel<false><<<grid_count, kCompactThreads, 0, c->stream>>>(ca);
+            compact_scan2_kernel<<<1, 1024, 0, c->stream>>>(ca);
+            compact_scatter2_kernel<false><<<grid, kCompactThreads, 0, c->stream>>>(ca);
+          }
+          c->stats.kernel_launches += 3;
         } else if (want_dist) {
           const uint32_t grid = std::min<uint32_t>(b.chunks, (uint32_t)c->sm_count * 8u);  // grid-stride over the chunks
           compact_count_kernel<true><<<b.chunks, kCompactThreads, 0, c->stream>>>(ca);  // (one CTA per chunk measured faster here)
@@ -918,6 +934,7 @@ int fm_debug_set_option(const char* name, int value) {
   else if (!strcmp(name, "pre_tiles")) g_debug.pre_tiles = value;
   else if (!strcmp(name, "two_phase")) g_debug.two_phase = value;
   else if (!strcmp(name, "surv_cap")) g_debug.surv_cap = value;
+  else if (!strcmp(name, "compact_v")) g_debug.compact_v = value;
   else return FM_ERR_INVALID;
   return FM_OK;
 }

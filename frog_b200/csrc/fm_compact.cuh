@@ -227,6 +227,312 @@ compact_scatter_kernel(const CompactArgs a) {
   }
 }
 
+// ---- version 2 of the three passes (fm_debug_set_option("compact_v", 1) selects the ones above for comparison) ----
+// What the per-launch profile of the passes above showed on 24 M-row batches (100 MB of rows): count 32 us at 40 % of
+// DRAM throughput, scan 11 us in a single CTA, scatter 14 us of dependent loads.  The count pass keeps rows in flight
+// only while a CTA waits for its own loads -- descriptor, then rows, then two barriers and a serial warp scan during
+// which nothing is in flight.  Here the CTAs are persistent and software-pipelined: the rows (and the descriptor after
+// next) of the FOLLOWING chunk are requested before the current chunk is ranked, so every resident CTA always has
+// 16 KB on its way; ranks are recomputed in the rare parking branch instead of being held in registers, which keeps
+// three CTAs per SM.  Per-pair counts are accumulated here (one atomic per non-empty chunk, spread over the grid)
+// instead of by the single scan CTA, and the scatter pass moves parked chunks with one WARP per chunk.
+struct ChunkRows {
+  uint32_t m[kCompactPer];
+};
+
+__device__ __forceinline__ void chunk_load(const uint32_t* __restrict__ rowres, const ChunkDesc& d, ChunkRows& r) {
+  const uint32_t n = d.n_swap & 0x7FFFFFFFu;
+  const uint32_t* src = rowres + d.row_abs;
+#pragma unroll
+  for (int i = 0; i < kCompactPer; i++) {
+    const uint32_t q = i * kCompactThreads + threadIdx.x;
+    r.m[i] = q < n ? __ldg(src + q) : kNone;  // default caching: dense chunks are read again by the scatter pass, from L2
+  }
+}
+
+template <bool kDist>
+__global__ void __launch_bounds__(kCompactThreads, 3)
+compact_count2_kernel(const CompactArgs a) {
+  __shared__ uint32_t s_slice[kCompactSlices];
+  __shared__ uint32_t s_total;
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  uint32_t chunk = blockIdx.x;
+  if (chunk >= a.n_chunks) return;
+  const uint4* descs = reinterpret_cast<const uint4*>(a.chunks);
+  uint4 dv = __ldg(descs + chunk);
+  ChunkRows cur, nxt;
+  chunk_load(a.rowres, ChunkDesc{dv.x, dv.y, dv.z, dv.w}, cur);
+  uint4 dnext = chunk + gridDim.x < a.n_chunks ? __ldg(descs + chunk + gridDim.x) : dv;
+  for (;;) {
+    const uint32_t next = chunk + gridDim.x;
+    const bool has_next = next < a.n_chunks;  // CTA-uniform
+    uint4 dnext2 = dnext;
+    if (has_next) {
+      chunk_load(a.rowres, ChunkDesc{dnext.x, dnext.y, dnext.z, dnext.w}, nxt);  // in flight while `cur` is ranked
+      if (next + gridDim.x < a.n_chunks) dnext2 = __ldg(descs + next + gridDim.x);
+    }
+    const ChunkDesc d{dv.x, dv.y, dv.z, dv.w};
+    // slice totals, their exclusive prefix, the chunk total
+#pragma unroll
+    for (int i = 0; i < kCompactPer; i++) {
+      const uint32_t b = __ballot_sync(0xffffffffu, cur.m[i] != kNone);
+      if (lane == 0) s_slice[i * (kCompactThreads / 32) + warp] = __popc(b);
+    }
+    __syncthreads();
+    if (warp == 0) {
+      uint32_t carry = 0;
+#pragma unroll
+      for (int k = 0; k < kCompactSlices / 32; k++) {
+        const uint32_t v = s_slice[32 * k + lane];
+        uint32_t inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint32_t nb = __shfl_up_sync(0xffffffffu, inc, o);
+          if (lane >= (uint32_t)o) inc += nb;
+        }
+        s_slice[32 * k + lane] = carry + inc - v;
+        carry += __shfl_sync(0xffffffffu, inc, 31);
+      }
+      if (lane == 0) {
+        s_total = carry;
+        a.chunk_count[chunk] = carry;
+        if (carry) atomicAdd(a.pair_count + d.pair, carry);
+      }
+    }
+    __syncthreads();
+    const uint32_t total = s_total;
+    if (!kDist && total != 0 && total <= kStageCap) {  // CTA-uniform: park the few pairs, the rows are not read again
+      const bool swap = d.n_swap >> 31;
+      uint2* st = a.stage + (size_t)chunk * kStageCap;
+#pragma unroll
+      for (int i = 0; i < kCompactPer; i++) {
+        const uint32_t b = __ballot_sync(0xffffffffu, cur.m[i] != kNone);
+        if (cur.m[i] != kNone) {
+          const uint32_t row = d.row_local + i * kCompactThreads + tid;
+          const uint32_t pos = s_slice[i * (kCompactThreads / 32) + warp] + __popc(b & ((1u << lane) - 1u));
+          st[pos] = swap ? make_uint2(row, cur.m[i]) : make_uint2(cur.m[i], row);
+        }
+      }
+    }
+    if (!has_next) break;
+    __syncthreads();  // s_slice / s_total are rewritten by the next chunk
+    cur = nxt;
+    dv = dnext;
+    dnext = dnext2;
+    chunk = next;
+  }
+}
+
+// Count pass, version 3: the per-launch profile of version 2 (29 us per 100 MB: 43 % of DRAM throughput with the next
+// chunk's rows always in flight) says the ranking work bounds the pass, not the loads -- two barriers, a serial
+// 128-slice scan by one warp while seven wait, and a second round of ballots for the parked pairs.  Here every WARP owns
+// 512 CONSECUTIVE rows of the chunk (16 coalesced 128-byte loads), so the rank of a match inside its warp needs nothing
+// but that warp's own ballots, and the chunk needs one barrier: eight warp totals through shared memory.
+template <bool kDist>
+__global__ void __launch_bounds__(kCompactThreads, 3)
+compact_count3_kernel(const CompactArgs a) {
+  __shared__ uint32_t s_warp[2][kCompactThreads / 32];  // warp totals, double-buffered: one barrier per chunk
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr uint32_t kWarpRows = 32 * kCompactPer;  // 512
+  uint32_t chunk = blockIdx.x;
+  if (chunk >= a.n_chunks) return;
+  const uint4* descs = reinterpret_cast<const uint4*>(a.chunks);
+  auto load = [&](const uint4& dq, ChunkRows& r) {
+    const uint32_t n = dq.y & 0x7FFFFFFFu;
+    const uint32_t* src = a.rowres + dq.x + warp * kWarpRows;
+#pragma unroll
+    for (int i = 0; i < kCompactPer; i++) {
+      const uint32_t q = warp * kWarpRows + i * 32 + lane;  // row inside the chunk
+      r.m[i] = q < n ? __ldg(src + i * 32 + lane) : kNone;
+    }
+  };
+  uint4 dv = __ldg(descs + chunk);
+  ChunkRows cur, nxt;
+  load(dv, cur);
+  uint4 dnext = chunk + gridDim.x < a.n_chunks ? __ldg(descs + chunk + gridDim.x) : dv;
+  uint32_t buf = 0;
+  for (;;) {
+    const uint32_t next = chunk + gridDim.x;
+    const bool has_next = next < a.n_chunks;  // CTA-uniform
+    uint4 dnext2 = dnext;
+    if (has_next) {
+      load(dnext, nxt);  // in flight while `cur` is counted
+      if (next + gridDim.x < a.n_chunks) dnext2 = __ldg(descs + next + gridDim.x);
+    }
+    uint32_t ball[kCompactPer];
+    uint32_t mine = 0;
+#pragma unroll
+    for (int i = 0; i < kCompactPer; i++) {
+      ball[i] = __ballot_sync(0xffffffffu, cur.m[i] != kNone);
+      mine += __popc(ball[i]);
+    }
+    if (lane == 0) s_warp[buf][warp] = mine;
+    __syncthreads();
+    uint32_t before = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < kCompactThreads / 32; w++) {
+      const uint32_t t = s_warp[buf][w];
+      before += w < (int)warp ? t : 0u;
+      total += t;
+    }
+    if (tid == 0) {
+      a.chunk_count[chunk] = total;
+      if (total) atomicAdd(a.pair_count + dv.w, total);
+    }
+    if (!kDist && total != 0 && total <= kStageCap && mine != 0) {  // warp-uniform: park this warp's few pairs in row order
+      const bool swap = dv.y >> 31;
+      uint2* st = a.stage + (size_t)chunk * kStageCap + before;
+      uint32_t run = 0;
+#pragma unroll
+      for (int i = 0; i < kCompactPer; i++) {
+        if (cur.m[i] != kNone) {
+          const uint32_t row = dv.z + warp * kWarpRows + i * 32 + lane;
+          st[run + __popc(ball[i] & ((1u << lane) - 1u))] = swap ? make_uint2(row, cur.m[i]) : make_uint2(cur.m[i], row);
+        }
+        run += __popc(ball[i]);
+      }
+    }
+    if (!has_next) break;
+    buf ^= 1u;  // the other buffer was last read before the barrier above
+    cur = nxt;
+    dv = dnext;
+    dnext = dnext2;
+    chunk = next;
+  }
+}
+
+// One CTA: exclusive prefix of the chunk totals (offsets relative to *running_total) and the new total.
+__global__ void __launch_bounds__(1024)
+compact_scan2_kernel(const CompactArgs a) {
+  __shared__ unsigned long long s_warp[32];
+  const unsigned long long base0 = *a.running_total;
+  const uint32_t n = a.n_chunks, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // thread t owns chunks [t * per, (t + 1) * per), per a multiple of 4 so that the counts load as uint4
+  const uint32_t per = ((n + 1023u) / 1024u + 3u) & ~3u;
+  const uint32_t c0 = min(n, threadIdx.x * per), c1 = min(n, c0 + per);
+  constexpr uint32_t kMaxPer = 32;  // 32 K chunks = 134 M rows per batch; larger batches take the loop below
+  uint32_t cnt[kMaxPer];
+  unsigned long long sum = 0;
+  const bool in_regs = per <= kMaxPer;
+  if (in_regs) {
+#pragma unroll
+    for (uint32_t q = 0; q < kMaxPer; q += 4) {
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (q < per && c0 + q < c1) {
+        if (c0 + q + 4 <= c1) v = *reinterpret_cast<const uint4*>(a.chunk_count + c0 + q);
+        else {
+          v.x = a.chunk_count[c0 + q];
+          if (c0 + q + 1 < c1) v.y = a.chunk_count[c0 + q + 1];
+          if (c0 + q + 2 < c1) v.z = a.chunk_count[c0 + q + 2];
+        }
+      }
+      cnt[q] = v.x; cnt[q + 1] = v.y; cnt[q + 2] = v.z; cnt[q + 3] = v.w;
+      sum += (unsigned long long)v.x + v.y + v.z + v.w;
+    }
+  } else {
+    for (uint32_t c = c0; c < c1; c++) sum += a.chunk_count[c];
+  }
+  unsigned long long inc = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned long long v = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= (uint32_t)o) inc += v;
+  }
+  if (lane == 31) s_warp[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    const unsigned long long w = s_warp[lane];
+    unsigned long long winc = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned long long v = __shfl_up_sync(0xffffffffu, winc, o);
+      if (lane >= (uint32_t)o) winc += v;
+    }
+    s_warp[lane] = winc - w;
+    if (lane == 31) *a.running_total = base0 + winc;
+  }
+  __syncthreads();
+  unsigned long long run = base0 + s_warp[warp] + inc - sum;
+  if (in_regs) {
+#pragma unroll
+    for (uint32_t q = 0; q < kMaxPer; q++) {
+      if (q < per && c0 + q < c1) {
+        a.chunk_out[c0 + q] = run;
+        run += cnt[q];
+      }
+    }
+  } else {
+    for (uint32_t c = c0; c < c1; c++) {
+      a.chunk_out[c] = run;
+      run += a.chunk_count[c];
+    }
+  }
+}
+
+// Scatter: parked chunks by one warp each (count, offset and the <= 64 staged pairs are three short dependent loads;
+// a CTA per chunk spent its whole life waiting for them), then the dense chunks by whole CTAs as before.
+template <bool kDist>
+__global__ void __launch_bounds__(kCompactThreads)
+compact_scatter2_kernel(const CompactArgs a) {
+  __shared__ uint32_t s_slice[kCompactSlices];
+  __shared__ uint32_t s_total;
+  __shared__ __align__(16) uint2 s_stage[kCompactChunk + 2];
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (!kDist) {
+    const uint32_t n_warps = gridDim.x * (kCompactThreads / 32);
+    for (uint32_t chunk = blockIdx.x * (kCompactThreads / 32) + warp; chunk < a.n_chunks; chunk += n_warps) {
+      const uint32_t total = a.chunk_count[chunk];
+      if (total == 0 || total > kStageCap) continue;  // warp-uniform
+      const unsigned long long dst0 = a.chunk_out[chunk];
+      const uint2* st = a.stage + (size_t)chunk * kStageCap;
+      for (uint32_t q = lane; q < total; q += 32) a.out_pairs[dst0 + q] = st[q];
+    }
+  }
+  for (uint32_t chunk = blockIdx.x; chunk < a.n_chunks; chunk += gridDim.x) {
+    const uint32_t total = a.chunk_count[chunk];
+    if (total == 0 || (!kDist && total <= kStageCap)) continue;  // CTA-uniform
+    const unsigned long long dst0 = a.chunk_out[chunk];
+    const uint4 dv = __ldg(reinterpret_cast<const uint4*>(a.chunks) + chunk);
+    const ChunkDesc d{dv.x, dv.y, dv.z, dv.w};
+    uint32_t m[kCompactPer], rank[kCompactPer];
+    chunk_rank(d, a.rowres, m, rank, s_slice, &s_total);
+    const uint32_t shift = (uint32_t)(dst0 & 1ull);
+    const bool swap = d.n_swap >> 31;
+#pragma unroll
+    for (int i = 0; i < kCompactPer; i++) {
+      if (m[i] != kNone) {
+        const uint32_t row = d.row_local + i * kCompactThreads + tid;
+        const uint32_t pos = s_slice[i * (kCompactThreads / 32) + warp] + rank[i];
+        s_stage[pos + shift] = swap ? make_uint2(row, m[i]) : make_uint2(m[i], row);
+      }
+    }
+    __syncthreads();
+    uint2* dst = a.out_pairs + (dst0 - shift);
+    const uint32_t n_slots = total + shift;
+    const uint4* st4 = reinterpret_cast<const uint4*>(s_stage);
+    for (uint32_t q = tid; q < (n_slots + 1) / 2; q += kCompactThreads) {
+      const uint32_t s0 = 2 * q;
+      const bool lo_ok = s0 >= shift, hi_ok = s0 + 1 < n_slots;
+      if (lo_ok && hi_ok) __stcs(reinterpret_cast<uint4*>(dst) + q, st4[q]);
+      else if (lo_ok) dst[s0] = s_stage[s0];
+      else if (hi_ok) dst[s0 + 1] = s_stage[s0 + 1];
+    }
+    if (kDist) {
+      __syncthreads();
+      float* s_dist = reinterpret_cast<float*>(s_stage);
+#pragma unroll
+      for (int i = 0; i < kCompactPer; i++) {
+        if (m[i] != kNone)
+          s_dist[s_slice[i * (kCompactThreads / 32) + warp] + rank[i]] = a.rowdist[d.row_abs + i * kCompactThreads + tid];
+      }
+      __syncthreads();
+      float* dd = a.out_dist + dst0;
+      for (uint32_t q = tid; q < total; q += kCompactThreads) dd[q] = s_dist[q];
+    }
+    __syncthreads();
+  }
+}
+
 // ---- small batches: ONE launch -------------------------------------------------------------------------
 // Up to a wave or two of chunks the three launches above are launch latency and nothing else (C2: 19 us against 11).
 // Here a chunk obtains the exclusive prefix of the chunk totals by decoupled look-back over one 64-bit status word per

@@ -114,6 +114,8 @@ struct DebugOptions {
   int pre_tiles = -1;  // look-ahead depth override; -1 = kPreTiles
   int surv_cap = -1;   // two-phase scoring: survivor-unit capacity override (tests of the overflow route); -1 = built-in
   int two_phase = -1;  // two-phase scoring: -1 = the library decides (fm_api.cu), 0 = never, 1 = whenever it is applicable
+  int compact_v = 3;   // large-batch compaction (fm_compact.cuh): 3 = warp-autonomous pipelined count, 2 = pipelined count with the
+                       // block-wide ranking, 1 = the first version (one CTA per chunk, scan with the per-pair counts)
 };
 inline DebugOptions g_debug;
 
