@@ -199,6 +199,50 @@ bool write_points_bin(const std::string& path, const fs_point* pts, const float*
   return true;
 }
 
+bool read_points_file(const std::string& path, const double spacing[3], const double origin[3], const int dims[3],
+                      std::vector<float>& xyzs, size_t& n_outside, std::string& err) {
+  std::ifstream f(path);
+  if (!f) { err = "cannot open " + path; return false; }
+  const double ss = sspacing(spacing);
+  double lo[3], hi[3];
+  for (int i = 0; i < 3; i++) { lo[i] = origin[i]; hi[i] = origin[i] + (dims[i] - 1) * spacing[i]; }
+  xyzs.clear();
+  n_outside = 0;
+  std::string line, cell;
+  size_t line_no = 0;
+  while (std::getline(f, line)) {
+    line_no++;
+    size_t pos = 0;
+    bool exhausted = line.empty();  // an empty stream yields no first cell: the line is skipped
+    if (exhausted) continue;
+    float v[4];
+    for (int k = 0; k < 4; k++) {
+      if (!exhausted) {
+        if (k > 0 && pos >= line.size()) {  // the line ended with a comma: getline erases its string, extracts nothing
+          cell.clear();
+          exhausted = true;
+        } else {
+          const size_t comma = line.find(',', pos);
+          if (comma == std::string::npos) { cell = line.substr(pos); exhausted = true; }
+          else { cell = line.substr(pos, comma - pos); pos = comma + 1; }
+        }
+      }  // else: `cell` keeps its previous content, as the reference's failed getline leaves it
+      try {
+        v[k] = std::stof(cell);
+      } catch (...) {
+        err = "stof failed at line " + std::to_string(line_no) + " of " + path;
+        return false;
+      }
+    }
+    xyzs.push_back((float)((v[0] - origin[0]) / spacing[0]));
+    xyzs.push_back((float)((v[1] - origin[1]) / spacing[1]));
+    xyzs.push_back((float)((v[2] - origin[2]) / spacing[2]));
+    xyzs.push_back((float)(v[3] / ss));
+    if (!(v[0] >= lo[0] && v[0] <= hi[0] && v[1] >= lo[1] && v[1] <= hi[1] && v[2] >= lo[2] && v[2] <= hi[2])) n_outside++;
+  }
+  return true;
+}
+
 bool write_bounds_json(const std::string& path, const Volume& v) {
   // picojson serialises a std::map (keys sorted) and numbers as "%.f" when integral below 2^53, else "%.17g"
   auto num = [](double x) {
@@ -249,6 +293,19 @@ int fsio_read_metaimage(const char* path, int* dims, double* spacing, double* or
   if (bytes) *bytes = v.data.size();
   if (data) std::memcpy(data, v.data.data(), v.data.size() < cap ? v.data.size() : cap);
   return 0;
+}
+
+// x, y, z, scale per point in voxel units; returns the number of points (at most cap are copied), -1 on error
+long fsio_read_points(const char* path, const double* spacing, const double* origin, const int* dims, float* xyzs, long cap,
+                      long* n_outside) {
+  std::vector<float> v;
+  std::string err;
+  size_t outside = 0;
+  if (!fsio::read_points_file(path, spacing, origin, dims, v, outside, err)) return -1;
+  if (n_outside) *n_outside = (long)outside;
+  const long n = (long)(v.size() / 4);
+  if (xyzs) std::memcpy(xyzs, v.data(), sizeof(float) * 4 * (size_t)(n < cap ? n : cap));
+  return n;
 }
 
 int fsio_write_bounds_json(const char* path, const int* dims, const double* spacing, const double* origin) {

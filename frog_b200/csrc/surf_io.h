@@ -31,6 +31,14 @@ bool write_points_csvgz(const std::string& path, const char* gz_opts, int precis
                         size_t n, size_t dsize, const double spacing[3], const double origin[3]);
 bool write_points_bin(const std::string& path, const fs_point* pts, const float* desc, size_t n, size_t dsize,
                       const double spacing[3], const double origin[3]);
+// vtk3DSURF::ReadIPoints (vtk3DSURF.cxx:34-77, surf3d -p): one keypoint per line, "x,y,z,scale" in world units; returns
+// x, y, z, scale per point in VOXEL units (as fs_set_points takes them).  A cell that is missing at the end of a line
+// repeats the previous cell (the reference's getline leaves its string untouched), an empty line is skipped, a cell
+// that is not a number is an error (std::stof throws in the reference).  n_outside counts the points the reference
+// reports as "outside image" (they are kept).
+bool read_points_file(const std::string& path, const double spacing[3], const double origin[3], const int dims[3],
+                      std::vector<float>& xyzs, size_t& n_outside, std::string& err);
+
 // surf3d.cxx:269-285: {"bounds":{"xmax":..,"xmin":..,...}} in picojson's number format
 bool write_bounds_json(const std::string& path, const Volume& v);
 

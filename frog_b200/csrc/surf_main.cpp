@@ -1,7 +1,7 @@
 // bin/surf3d -- the SURF3D producer's executable over libfrogsurf.so.
 // Same command line as the reference's surf3d (vtkOpenSURF3D/surf3d.cxx:16-157): the option loop advances two
 // tokens per key and ignores keys it does not know.  Options that need VTK's own image filters (-s / -d
-// resampling, -m mask, -pad, -type 2, -json 1) are rejected loudly instead of being approximated; the input is a
+// resampling, -m mask, -pad, -type 2) or picojson (-json 1) are rejected loudly instead of being approximated; the input is a
 // MetaImage volume already at its final sampling.
 #include <chrono>
 #include <cstdio>
@@ -51,6 +51,7 @@ int main(int argc, char* argv[]) {
     cout << "-n number      : maximum number of points" << endl;
     cout << "-normalize 0/1 : normalize descriptors (default : 1 )" << endl;
     cout << "-o basename    : set output file name. Default: \"points\"" << endl;
+    cout << "-p file        : describe the points of a csv file (x,y,z,scale) instead of detecting" << endl;
     cout << "-r radius      : descriptor volume radius. Default : 5" << endl;
     cout << "-t threshold   : set detector threshold. Default: 0" << endl;
     cout << "-type 0/1      : set descriptor type :" << endl;
@@ -99,7 +100,6 @@ int main(int argc, char* argv[]) {
   if (pad) return unsupported("-pad (vtkImageMirrorPad)");
   if (descriptorType == 2) return unsupported("-type 2 (vtkImageResize)");
   if (writeJSON) return unsupported("-json 1 (picojson point dump)");
-  if (pointFile) return unsupported("-p (point file)");
 
   cout << "load : " << argv[1] << endl;
   double t0 = now();
@@ -140,9 +140,24 @@ int main(int argc, char* argv[]) {
   cout << "Integral computed in " << now() - t0 << "s" << endl;
   t0 = now();
   uint32_t n = 0;
-  if (fs_detect(ctx, (float)threshold, &n) != FS_OK) return die("detector");
-  cout << " Ipoints : " << n << endl;
-  cout << "FastHessian computed in " << now() - t0 << "s" << endl;
+  if (pointFile) {  // vtk3DSURF.cxx:183: ReadIPoints instead of the detector
+    cout << "Use points in " << pointFile << endl;
+    cout << "Read : " << pointFile << endl;
+    std::vector<float> xyzs;
+    size_t outside = 0;
+    if (!fsio::read_points_file(pointFile, vol.spacing, vol.origin, vol.dims, xyzs, outside, err)) {
+      std::cerr << "surf3d (B200): " << err << endl;
+      fs_destroy(ctx);
+      return 1;
+    }
+    if (outside) cout << "Error : " << outside << " points are outside image" << endl;
+    n = (uint32_t)(xyzs.size() / 4);
+    if (fs_set_points(ctx, xyzs.data(), n) != FS_OK) return die("points");
+  } else {
+    if (fs_detect(ctx, (float)threshold, &n) != FS_OK) return die("detector");
+    cout << " Ipoints : " << n << endl;
+    cout << "FastHessian computed in " << now() - t0 << "s" << endl;
+  }
   t0 = now();
   if (fs_select(ctx, numberOfPoints) != FS_OK) return die("select");
   uint32_t dsize = 0;

@@ -236,6 +236,8 @@ def _io():
         L.fsio_read_metaimage.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                           C.c_size_t, C.c_void_p]
         L.fsio_write_bounds_json.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.fsio_read_points.restype = C.c_long
+        L.fsio_read_points.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.c_void_p]
         _fsio = L
     return _fsio
 
@@ -252,6 +254,22 @@ def write_points(path: str, fmt: str, pts: np.ndarray, desc: np.ndarray, spacing
                                  org.ctypes.data)
     if rc != 0:
         raise FrogSurfError(f"cannot write {path}")
+
+
+def read_points_file(path: str, spacing, origin, shape):
+    """vtk3DSURF::ReadIPoints (surf3d -p): (xyzs [n, 4] float32 in voxel units, number of points outside the image);
+    `shape` is the volume's [z, y, x] shape."""
+    sp = np.asarray(spacing, np.float64)
+    org = np.asarray(origin, np.float64)
+    dims = np.asarray([shape[2], shape[1], shape[0]], np.int32)
+    outside = C.c_long()
+    n = _io().fsio_read_points(path.encode(), sp.ctypes.data, org.ctypes.data, dims.ctypes.data, None, 0, C.byref(outside))
+    if n < 0:
+        raise FrogSurfError(f"cannot read points from {path}")
+    out = np.zeros((n, 4), np.float32)
+    if n:
+        _io().fsio_read_points(path.encode(), sp.ctypes.data, org.ctypes.data, dims.ctypes.data, out.ctypes.data, n, C.byref(outside))
+    return out, outside.value
 
 
 _MET = {0: np.uint8, 1: np.int16, 2: np.uint16, 3: np.int32, 4: np.float32}

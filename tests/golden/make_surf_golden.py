@@ -11,6 +11,8 @@ Cases (synthetic volumes from frog_b200.synth.make_volume, regenerated from the 
          keypoint files the reference's own writers produce (csv, csv.gz, bin)
   mid    216 x 200 x 208 int16, seed 2 (three octaves, ~1000 keypoints): keypoints + descriptors + hashes
   f32    96 x 110 x 104 float32 with a fractional minimum (cast / shift rounding), seed 3: keypoints + hashes
+  pfile  the small volume described at the points of a csv file (surf3d -p), see make_point_file_case
+         (python tests/golden/make_surf_golden.py --only-pfile regenerates this case alone)
 """
 import hashlib
 import json
@@ -56,8 +58,39 @@ def layer_hashes(layers):
     return out
 
 
+def make_point_file_case():
+    """surf3d -p (vtk3DSURF::ReadIPoints): the small volume described at given points.  Input: 50 of the small case's
+    keypoints in world units plus an empty line and a CRLF line; outputs of the reference: the converted points in
+    file order with their descriptors (-n absent), and the csv.gz it writes with -n 30 (all responses are 0, so the
+    order is std::partial_sort's on equal keys)."""
+    c = CASES["small"]
+    vol = case_volume("small")
+    g = np.load(os.path.join(OUT, "small.npz"))
+    sp, org = np.array(c["spacing"]), np.array(c["origin"])
+    ss = float(np.prod(sp) ** (1.0 / 3.0))
+    lines = []
+    for i, p in enumerate(g["xyzsr"][:50]):
+        w = p[:3].astype(np.float64) * sp + org
+        lines.append("%.6f,%.6f,%.6f,%.6f" % (w[0], w[1], w[2], float(p[3]) * ss))
+        if i == 10:
+            lines.append("")
+    text = "\n".join(lines[:20]) + "\r\n" + "\n".join(lines[20:]) + "\n"
+    path = os.path.join(OUT, "pfile_points.csv")
+    open(path, "w", newline="").write(text)
+    ref = so.RefSurf(vol, c["spacing"], c["origin"])
+    xyzsr, lap, desc = ref.update(threshold=0.0, number_of_points=-1, point_file=path)
+    ref2 = so.RefSurf(vol, c["spacing"], c["origin"])
+    x2, _, d2 = ref2.update(threshold=0.0, number_of_points=30, point_file=path)
+    ref2.write(os.path.join(OUT, "pfile_points_n30.csv.gz"), "csv.gz")
+    np.savez_compressed(os.path.join(OUT, "pfile.npz"), xyzsr=xyzsr, lap=lap, desc=desc, n30_xyzsr=x2, n30_desc=d2)
+    print("pfile", len(xyzsr), "points;", len(x2), "kept with -n 30")
+
+
 def main():
     oracle.build(ref=True)
+    if "--only-pfile" in sys.argv:
+        make_point_file_case()
+        return
     os.makedirs(OUT, exist_ok=True)
     manifest = {}
     for name, c in CASES.items():
@@ -82,6 +115,7 @@ def main():
         manifest[name] = m
         print(name, m["n_points"], "keypoints,", m["n_detected"], "detected")
     json.dump(manifest, open(os.path.join(OUT, "manifest.json"), "w"), indent=1)
+    make_point_file_case()
 
 
 if __name__ == "__main__":

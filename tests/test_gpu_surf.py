@@ -197,3 +197,22 @@ def test_producer_feeds_matcher_like_run_sh(built, tmp_path):
     assert rr.returncode == 0
     got, want = open(gdir / "pairs.bin", "rb").read(), open(rdir / "pairs.bin", "rb").read()
     assert len(got) > 1000 and got == want
+
+
+def test_cli_point_file(built, tmp_path):
+    """surf3d -p points.csv: descriptors at given points instead of detection (vtk3DSURF::ReadIPoints); with -n 30 the
+    reference's partial_sort runs over 50 equal (zero) responses and decides which 30 survive and in what order."""
+    c = mg.CASES["small"]
+    g = np.load(os.path.join(GOLD, "pfile.npz"))
+    mha = str(tmp_path / "small.mha")
+    surf.write_metaimage(mha, mg.case_volume("small"), c["spacing"], c["origin"])
+    pfile = os.path.join(GOLD, "pfile_points.csv")
+    base = str(tmp_path / "p")
+    r = subprocess.run([build.SURF_BIN, mha, "-o", base, "-p", pfile, "-bin", "1", "-csvgz", "0"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    rec = np.fromfile(base + ".bin", np.float32).reshape(-1, 54)
+    assert rec.shape[0] == 50 and np.array_equal(bits(rec[:, 6:]), bits(g["desc"]))
+    assert not rec[:, 4:6].any()  # laplacian and response stay 0 (Ipoint(), ipoint.h:33)
+    r = subprocess.run([build.SURF_BIN, mha, "-o", base + "30", "-p", pfile, "-n", "30"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert open(base + "30.csv.gz", "rb").read() == open(os.path.join(GOLD, "pfile_points_n30.csv.gz"), "rb").read()

@@ -203,3 +203,27 @@ int main(int argc, char** argv) {
         want = np.array([int(t) for t in out.stdout.split()], np.uint32)
         got = surf.debug_select(resp, keep)
         assert np.array_equal(got, want), (n, keep, levels)
+
+
+def test_point_file_reader_matches_reference(built, tmp_path):
+    """surf3d -p: vtk3DSURF::ReadIPoints (vtk3DSURF.cxx:34-77).  World-unit lines -> voxel-unit keypoints identical to what
+    the reference converted from the same file (empty line skipped, CRLF tolerated); its quirks on short lines."""
+    c = mg.CASES["small"]
+    g = np.load(os.path.join(GOLD, "pfile.npz"))
+    xyzs, outside = surf.read_points_file(os.path.join(GOLD, "pfile_points.csv"), c["spacing"], c["origin"], c["shape"])
+    assert outside == 0 and xyzs.shape == (50, 4)
+    assert np.array_equal(xyzs.view(np.uint32), g["xyzsr"][:, :4].view(np.uint32))
+    # a failed getline leaves the cell string as it was: missing cells repeat the last one; a trailing comma erases it
+    p = str(tmp_path / "q.csv")
+    open(p, "w").write("1.5,2.5\n\n4,5,6,7,8\n  3.25 ,1e1,-2,0.5junk\n")
+    xyzs, outside = surf.read_points_file(p, (1.0, 2.0, 4.0), (0.5, 0.5, 0.5), (100, 100, 100))
+    ss = (1.0 * 2.0 * 4.0) ** (1.0 / 3.0)
+    want = np.array([[1.0, 1.0, 0.5, np.float32(2.5) / ss], [3.5, 2.25, 1.375, np.float32(7) / ss],
+                     [2.75, 4.75, -0.625, np.float32(0.5) / ss]], np.float32)
+    assert np.array_equal(xyzs, want) and outside == 1  # z = -2 lies outside the image; the point is kept
+    open(p, "w").write("1,2,3,\n")
+    with pytest.raises(surf.FrogSurfError):
+        surf.read_points_file(p, (1.0, 1.0, 1.0), (0.0, 0.0, 0.0), (10, 10, 10))  # std::stof("") throws in the reference
+    open(p, "w").write("1,x,3,4\n")
+    with pytest.raises(surf.FrogSurfError):
+        surf.read_points_file(p, (1.0, 1.0, 1.0), (0.0, 0.0, 0.0), (10, 10, 10))
