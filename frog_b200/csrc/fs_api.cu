@@ -265,7 +265,7 @@ int fs_create(int device, fs_ctx** out) {
       cudaMalloc((void**)&c->d_blockmin, 592 * sizeof(double)) != cudaSuccess ||
       cudaMalloc((void**)&c->d_count, 2 * sizeof(unsigned)) != cudaSuccess) {
     fail(nullptr, FS_ERR_CUDA, "fs_create: %s", cudaGetErrorString(cudaGetLastError()));
-    delete c;
+    fs_destroy(c);  // releases whatever was created before the failing call
     return FS_ERR_CUDA;
   }
   *out = c;

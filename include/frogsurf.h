@@ -80,7 +80,8 @@ const char* fs_version(void);
 
 /*
  * Hand over a volume of nx * ny * nz voxels, x fastest (VTK's layout).  `voxels` may be a host or a
- * device pointer.  Does what vtk3DSURF::Update does before the detector runs: cast to int with
+ * device pointer (a device buffer is read in place on the context's own stream: whatever produced it must have
+ * completed, e.g. by a synchronisation on the producing stream, before the call).  Does what vtk3DSURF::Update does before the detector runs: cast to int with
  * clamping, subtract the volume's minimum (vtkImageShiftScale, shift = -range[0]), integral volume
  * (unsigned 64-bit, inclusive prefix sums along x, y, z).
  */
