@@ -72,6 +72,7 @@ def load():
     L.fs_debug_layers.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
     L.fs_debug_keep_cast_volume.argtypes = [C.c_void_p, C.c_int]
     L.fs_debug_set_option.argtypes = [C.c_char_p, C.c_int]
+    L.fs_debug_sort_keys.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
     L.fs_debug_select.restype = C.c_uint32
     L.fs_debug_select.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.c_void_p]
     _lib = L
@@ -187,6 +188,13 @@ def run(volume: np.ndarray, threshold=0.0, number_of_points=-1, descriptor_type=
 def debug_set_option(name: str, value: int) -> None:
     if load().fs_debug_set_option(name.encode(), value) != 0:
         raise FrogSurfError(f"unknown option {name}")
+
+
+def debug_sort_keys(keys: np.ndarray) -> np.ndarray:
+    k = np.ascontiguousarray(keys, np.uint64)
+    order = np.zeros(max(k.size, 1), np.uint32)
+    load().fs_debug_sort_keys(k.ctypes.data, k.size, order.ctypes.data)
+    return order[:k.size]
 
 
 def debug_expf(x: np.ndarray) -> np.ndarray:

@@ -24,6 +24,9 @@ uint32_t fs_debug_select(const float* response, uint32_t n, int number_of_points
 
 /* keep the shifted int volume (vtk3DSURF::Cast) of the following fs_set_volume calls so that fs_get_cast_volume can
  * return it; off by default (256 MB of extra writes for a 400^3 volume that nothing but the tests reads) */
+/* the ordering fs_detect applies to its extrema (loop position keys): order[] = input indices ascending by key, ties in
+ * input order */
+void fs_debug_sort_keys(const uint64_t* keys, uint32_t n, uint32_t* order);
 /* experiment switches; "response_tile": thread-to-voxel mapping of the response-layer kernel (0 flat, 1 32x8x1,
  * 2 32x4x2, 3 32x2x4, 4 32x1x8, 5 32x4x4 (default), 6-9 register-capped / smaller-CTA variants).  Results are identical
  * for every value. */

@@ -227,3 +227,16 @@ def test_point_file_reader_matches_reference(built, tmp_path):
     open(p, "w").write("1,x,3,4\n")
     with pytest.raises(surf.FrogSurfError):
         surf.read_points_file(p, (1.0, 1.0, 1.0), (0.0, 0.0, 0.0), (10, 10, 10))
+
+
+def test_extrema_ordering_is_a_stable_sort(built):
+    """fs_detect restores the reference's push_back order by sorting loop-position keys: the radix sort must equal a
+    stable sort for every key pattern (constant bytes skipped, duplicates, high bits, empty and single inputs)."""
+    rng = np.random.default_rng(4)
+    cases = [np.zeros(0, np.uint64), np.array([7], np.uint64), rng.integers(0, 5, 1000).astype(np.uint64),
+             (rng.integers(0, 8, 30000).astype(np.uint64) << np.uint64(48)) | rng.integers(0, 1 << 23, 30000).astype(np.uint64),
+             rng.integers(0, 1 << 62, 5000, dtype=np.int64).astype(np.uint64),
+             np.full(300, 0xABCDEF0123, np.uint64), np.arange(4000, 0, -1).astype(np.uint64) * np.uint64(257)]
+    for keys in cases:
+        got = surf.debug_sort_keys(keys)
+        assert np.array_equal(got, np.argsort(keys, kind="stable").astype(np.uint32))
