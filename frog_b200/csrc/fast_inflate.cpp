@@ -8,9 +8,10 @@
 // (10-bit root for literals/lengths, 8-bit for distances) and word-wise match copies.  Keypoint text
 // is match-heavy (99.8 % of a surf3d file's bytes come out of 3-5 byte matches: ",0." / ",-0." and digit groups that
 // occurred in the last 32 KB), so the decode rate is set by the serial chain lookup -> shift -> lookup of each
-// length / distance pair, not by table size: 1.3x zlib with the first version of this loop, 2.1x now (one shift per
-// symbol with the extra bits cut from a copy of the buffer, the next entry looked up before the match is copied, a
-// BMI2 clone for the variable shifts, CRC-32 by carry-less multiplication, per-thread scratch buffers).  It accepts
+// length / distance pair, not by table size: 1.3x zlib with the first version of this loop, 3x now (a pair table that
+// resolves a whole match -- length and distance code -- in one lookup, two matches per refill, one shift per symbol
+// with the extra bits cut from a copy of the buffer, a BMI2 clone for the variable shifts, CRC-32 by carry-less
+// multiplication, per-thread scratch buffers).  It accepts
 // exactly what RFC 1951/1952 allow; on ANYTHING unexpected (bad header, invalid code, distance too
 // far, size or CRC-32 mismatch, truncated input) it returns false and the caller falls back to
 // zlib, so the accepted language and the error behaviour stay zlib's.
@@ -129,11 +130,46 @@ bool build_table(const uint8_t* lens, int n, Kind kind, int root, Entry* table, 
   return true;
 }
 
+// A whole match in one lookup: when a length code (with its extra bits) and the distance code that follows fit in the
+// next kPairBits bits of the stream, the entry holds the length, the distance base and how to cut the distance's extra
+// bits.  Keypoint text is matches of length 3-6 at arbitrary distances: a 2-4 bit length code, a 4-6 bit distance code.
+constexpr int kPairBits = 11;
+struct Pair {
+  uint16_t len;     // 0: no pair here, take the general path
+  uint16_t dbase;
+  uint8_t total;    // bits to consume: both codes and all extra bits
+  uint8_t code;     // bits before the distance's extra bits
+  uint8_t dextra;
+  uint8_t pad;
+};
 struct Decoder {
   Entry lit[kLitSize];
   Entry dist[kDistSize];
   Entry clen[kLenSize];
+  Pair pair[1 << kPairBits];
 };
+
+void build_pairs(Decoder& D) {
+  for (uint32_t idx = 0; idx < (1u << kPairBits); idx++) {
+    Pair p{0, 0, 0, 0, 0, 0};
+    const Entry e = D.lit[idx & ((1u << kLitRoot) - 1)];
+    if ((e.op & kBase) && !(e.op & (kLink | kEnd | kInvalid)) && e.bits <= kPairBits) {
+      const int lextra = e.op & 15;
+      const uint32_t len = e.val + ((idx >> (e.bits - lextra)) & ((1u << lextra) - 1));
+      const int rem = kPairBits - e.bits;
+      const Entry d = D.dist[(idx >> e.bits) & ((1u << kDistRoot) - 1)];
+      const int dextra = d.op & 15;
+      if ((d.op & kBase) && !(d.op & (kLink | kInvalid)) && d.bits - dextra <= rem) {
+        p.len = (uint16_t)len;
+        p.dbase = d.val;
+        p.code = (uint8_t)(e.bits + d.bits - dextra);
+        p.dextra = (uint8_t)dextra;
+        p.total = (uint8_t)(e.bits + d.bits);
+      }
+    }
+    D.pair[idx] = p;
+  }
+}
 
 inline uint64_t load64(const uint8_t* p) {
   uint64_t v;
@@ -292,6 +328,7 @@ bool fast_inflate_gzip(const uint8_t* src, size_t n, std::vector<char>& out, siz
       for (int i = 0; i < 32; i++) lens[288 + i] = 5;
       if (!build_table(lens, 288, kLitLen, kLitRoot, D.lit, kLitSize)) return false;
       if (!build_table(lens + 288, 32, kDist, kDistRoot, D.dist, kDistSize)) return false;
+      build_pairs(D);
     } else {  // dynamic code (3.2.7)
       const int hlit = (int)(bitbuf & 31) + 257, hdist = (int)((bitbuf >> 5) & 31) + 1, hclen = (int)((bitbuf >> 10) & 15) + 4;
       FM_TAKE(14);
@@ -334,22 +371,53 @@ bool fast_inflate_gzip(const uint8_t* src, size_t n, std::vector<char>& out, siz
       if (lens[256] == 0) return false;  // no end-of-block code
       if (!build_table(lens, hlit, kLitLen, kLitRoot, D.lit, kLitSize)) return false;
       if (!build_table(lens + hlit, hdist, kDist, kDistRoot, D.dist, kDistSize)) return false;
+      build_pairs(D);
     }
 
     // ---- the block's symbols ----
     // Keypoint text inflates almost entirely from matches (99.8 % of the bytes of a surf3d file, average length 4.2),
-    // so the loop is built around the match: one refill per match, the extra bits of length and distance are cut from
-    // a copy of the bit buffer while the buffer itself is shifted once per symbol (code + extra bits together, see
-    // build_table), and the next literal/length entry is looked up BEFORE the copy so its load overlaps it.
+    // so the loop is built around the match.  Fast path: the pair table resolves length AND distance in one lookup
+    // (two dependent table loads per match were the critical chain), two matches per refill.  General path: one shift
+    // per symbol with the extra bits cut from a copy of the bit buffer (code + extra bits together, see build_table).
 #define FM_LOOKUP(e)                                  \
   e = D.lit[bitbuf & ((1u << kLitRoot) - 1)];         \
   if (e.op & kLink) e = D.lit[e.val + ((bitbuf >> kLitRoot) & ((1u << (e.op & 15)) - 1))]
+#define FM_COPY_MATCH(len, dist)                                                                          \
+  do {                                                                                                    \
+    if ((dist) > (size_t)(o - out_begin) || o + (len) > out_limit) return false;                          \
+    const uint8_t* from = o - (dist);                                                                     \
+    uint8_t* const stop = o + (len);                                                                      \
+    if ((dist) >= 8) { /* words may run up to 7 bytes past `stop`: inside the slack, overwritten by what follows */ \
+      memcpy(o, from, 8);                                                                                 \
+      if ((len) > 8) {                                                                                    \
+        o += 8; from += 8;                                                                                \
+        do { memcpy(o, from, 8); o += 8; from += 8; } while (o < stop);                                   \
+      }                                                                                                   \
+    } else {                                                                                              \
+      do { *o++ = *from++; } while (o < stop);                                                            \
+    }                                                                                                     \
+    o = stop;                                                                                             \
+  } while (0)
     FM_REFILL();
-    Entry e;
-    FM_LOOKUP(e);
     for (;;) {
-      // here: at least 56 valid bits, `e` decoded from the bottom of the buffer
+      // here: at least 56 valid bits
       if (in > in_end + 8 || o > out_limit) return false;
+      const Pair p = D.pair[bitbuf & ((1u << kPairBits) - 1)];
+      if (p.len) {  // a whole match: at most kPairBits + 13 = 24 bits, so a second one fits before the refill
+        const uint32_t dist = p.dbase + (uint32_t)((bitbuf >> p.code) & ((1u << p.dextra) - 1));
+        FM_TAKE(p.total);
+        const Pair p2 = D.pair[bitbuf & ((1u << kPairBits) - 1)];  // in flight during the copy
+        FM_COPY_MATCH(p.len, dist);
+        if (p2.len) {
+          const uint32_t dist2 = p2.dbase + (uint32_t)((bitbuf >> p2.code) & ((1u << p2.dextra) - 1));
+          FM_TAKE(p2.total);
+          FM_COPY_MATCH(p2.len, dist2);
+        }
+        FM_REFILL();
+        continue;
+      }
+      Entry e;
+      FM_LOOKUP(e);
       if (e.op == kLiteral) {
         *o++ = (uint8_t)e.val;
         FM_TAKE(e.bits);
@@ -362,7 +430,6 @@ bool fast_inflate_gzip(const uint8_t* src, size_t n, std::vector<char>& out, siz
             *o++ = (uint8_t)e.val;
             FM_TAKE(e.bits);
             FM_REFILL();
-            FM_LOOKUP(e);
             continue;
           }
         }
@@ -383,21 +450,9 @@ bool fast_inflate_gzip(const uint8_t* src, size_t n, std::vector<char>& out, siz
       const uint32_t dist = d.val + (uint32_t)((dbits >> (d.bits - dextra)) & ((1u << dextra) - 1));
       FM_TAKE(d.bits);
       FM_REFILL();
-      FM_LOOKUP(e);  // next symbol, in flight during the copy
-      if (dist > (size_t)(o - out_begin) || o + len > out_limit) return false;
-      const uint8_t* from = o - dist;
-      uint8_t* const stop = o + len;
-      if (dist >= 8) {  // words may run up to 7 bytes past `stop`: inside the slack, overwritten by what follows
-        memcpy(o, from, 8);
-        if (len > 8) {
-          o += 8; from += 8;
-          do { memcpy(o, from, 8); o += 8; from += 8; } while (o < stop);
-        }
-      } else {
-        do { *o++ = *from++; } while (o < stop);
-      }
-      o = stop;
+      FM_COPY_MATCH(len, dist);
     }
+#undef FM_COPY_MATCH
 #undef FM_LOOKUP
   }
 #undef FM_REFILL
