@@ -88,8 +88,8 @@ inline bool fast_strtof(const char* c, const char* ce, float& v, const char*& en
 // The cell shape that makes up 48 of the 54 cells of a surf3d row: an L2-normalised descriptor component written with
 // "%f" -- optional '-', then "0." and six digits, then ',' or the end of the line.  Eight bytes are loaded at once,
 // the '.' is overwritten by '0' ("00dddddd"), all eight bytes are checked to be digits and converted with three
-// multiplications (SWAR); the value is m / 10^6 by the same exact-operands division as fast_strtof, with the same
-// deferral of float midpoints.  `q` points past the sign; at least 8 readable bytes follow it.
+// multiplications (SWAR); the value is m / 10^6 rounded to float (see below).  `q` points past the sign; at least 8
+// readable bytes follow it.
 inline bool descriptor_cell(const char* q, bool neg, float& v) {
   uint64_t w;
   memcpy(&w, q, 8);
@@ -100,11 +100,12 @@ inline bool descriptor_cell(const char* q, bool neg, float& v) {
   w = (w & 0x0F0F0F0F0F0F0F0Full) * 2561 >> 8;            // pairs of digits
   w = (w & 0x00FF00FF00FF00FFull) * 6553601 >> 16;        // groups of four
   const uint64_t m = (w & 0x0000FFFF0000FFFFull) * 42949672960001ull >> 32;
-  const double d = (double)m / 1e6;  // m == 0 gives +0.0, signed below like strtof's "-0.000000"
-  uint64_t bits;
-  memcpy(&bits, &d, 8);
-  if ((bits & 0x1FFFFFFFull) == 0x10000000ull) return false;  // exactly on a float midpoint: strtof decides
-  const float f = (float)d;
+  // m / 10^6 rounded to float.  No division: m * fl(1e-6) is within 2^-52 (relative) of the exact quotient, while the
+  // quotient of an integer below 10^6 by 10^6 is either a float itself (m a multiple of 5^6) or at least 2^-24 / 10^6
+  // = 6e-14 (relative) away from every midpoint of two floats (m 2^t - k 10^6 is a non-zero integer), so both round
+  // to the same float.  tests/test_hostio.py checks all 10^6 values against strtof.  (m == 0 gives +0.0, signed below
+  // like strtof's "-0.000000".)
+  const float f = (float)((double)m * 1e-6);
   uint32_t fb;
   memcpy(&fb, &f, 4);
   fb |= (uint32_t)neg << 31;  // the sign is as random as the data: no branch on it
