@@ -38,6 +38,58 @@ void flip_axis(std::vector<unsigned char>& data, const int dims[3], int axis) {
 
 double sspacing(const double spacing[3]) { return std::pow(spacing[0] * spacing[1] * spacing[2], 1.0 / 3.0); }
 
+// printf("%.<decimals>f", v) without printf: the writers format a million values per image and glibc's exact
+// multi-precision conversion costs ~0.45 us each.  A double is M * 2^e with M < 2^53, so v * 10^decimals is the
+// integer M * 10^decimals shifted by e: formed exactly in 128 bits, rounded half-to-even on the exact remainder as
+// printf does in the default rounding mode.  Anything outside the comfortable range (|v| * 10^decimals >= 9e18,
+// decimals > 9, inf, nan) goes to snprintf.  Returns the number of characters written (no terminator).
+inline size_t format_fixed(double v, int decimals, char* out, size_t cap) {
+  static const uint64_t kPow10[10] = {1ull, 10ull, 100ull, 1000ull, 10000ull, 100000ull, 1000000ull, 10000000ull, 100000000ull, 1000000000ull};
+  uint64_t bits;
+  std::memcpy(&bits, &v, 8);
+  const uint64_t frac = bits & ((1ull << 52) - 1);
+  const int expo = (int)((bits >> 52) & 0x7FF);
+  if (decimals < 0 || decimals > 9 || expo == 0x7FF || !(std::fabs(v) * (double)kPow10[decimals > 9 || decimals < 0 ? 0 : decimals] < 9e18)) {
+    char fmt[16];
+    std::snprintf(fmt, sizeof fmt, "%%.%df", decimals < 0 ? 6 : decimals);
+    return (size_t)std::snprintf(out, cap, fmt, v);
+  }
+  const uint64_t mant = expo ? (frac | (1ull << 52)) : frac;
+  const int e2 = (expo ? expo : 1) - 1075;
+  const unsigned __int128 prod = (unsigned __int128)mant * kPow10[decimals];  // < 2^53 * 2^30
+  uint64_t n;
+  if (e2 >= 0) {
+    n = (uint64_t)(prod << e2);  // the range check keeps this below 2^64
+  } else {
+    const int k = -e2;
+    if (k >= 100) {
+      n = 0;  // prod < 2^83: far below one half
+    } else {
+      const unsigned __int128 q = prod >> k, rem = prod & ((((unsigned __int128)1) << k) - 1), half = ((unsigned __int128)1) << (k - 1);
+      n = (uint64_t)q;
+      if (rem > half || (rem == half && (n & 1ull))) n++;
+    }
+  }
+  const uint64_t ip = n / kPow10[decimals], fp = n % kPow10[decimals];
+  char tmp[40];
+  size_t len = 0;
+  if (bits >> 63) tmp[len++] = '-';
+  char digits[24];
+  int nd = 0;
+  uint64_t t = ip;
+  do { digits[nd++] = (char)('0' + t % 10); t /= 10; } while (t);
+  while (nd) tmp[len++] = digits[--nd];
+  if (decimals) {
+    tmp[len++] = '.';
+    uint64_t f = fp;
+    for (int i = decimals - 1; i >= 0; i--) { tmp[len + i] = (char)('0' + f % 10); f /= 10; }
+    len += decimals;
+  }
+  if (len > cap) len = cap;
+  std::memcpy(out, tmp, len);
+  return len;
+}
+
 }  // namespace
 
 bool read_metaimage(const std::string& path, Volume& out, std::string& err) {
@@ -150,27 +202,25 @@ bool write_points_csvgz(const std::string& path, const char* gz_opts, int precis
   if (gz_opts) opts += gz_opts;
   gzFile gz = gzopen(path.c_str(), opts.c_str());
   if (!gz) return false;
-  std::string coeff("%f,"), coeff_end("%f");
-  if (precision >= 0) {
-    coeff_end = "%.";
-    coeff_end += std::to_string(precision);
-    coeff_end += "f";
-    coeff = coeff_end + ",";
-  }
   // one formatted row per gzwrite instead of one gzprintf per cell: the deflate stream depends on the bytes only
+  const int dec = precision >= 0 ? precision : 6;  // "%f" = six decimals
   std::vector<char> row(64 * (dsize + 8) + 512);
   for (size_t i = 0; i != n; i++) {
     const fs_point& p = pts[i];
     size_t o = 0;
-    o += std::snprintf(row.data() + o, row.size() - o, "%f,", p.x * spacing[0] + origin[0]);
-    o += std::snprintf(row.data() + o, row.size() - o, "%f,", p.y * spacing[1] + origin[1]);
-    o += std::snprintf(row.data() + o, row.size() - o, "%f,", p.z * spacing[2] + origin[2]);
-    o += std::snprintf(row.data() + o, row.size() - o, "%f,", p.scale * ss);
-    o += std::snprintf(row.data() + o, row.size() - o, "%d,", p.laplacian);
-    o += std::snprintf(row.data() + o, row.size() - o, "%f,", p.response);
-    for (size_t k = 0; k < dsize; k++) {
+    auto put = [&](double v, int decimals) {
       if (row.size() - o < 400) row.resize(row.size() * 2);
-      o += std::snprintf(row.data() + o, row.size() - o, (k < dsize - 1 ? coeff : coeff_end).c_str(), desc[i * dsize + k]);
+      o += format_fixed(v, decimals, row.data() + o, row.size() - o);
+    };
+    put(p.x * spacing[0] + origin[0], 6); row[o++] = ',';
+    put(p.y * spacing[1] + origin[1], 6); row[o++] = ',';
+    put(p.z * spacing[2] + origin[2], 6); row[o++] = ',';
+    put(p.scale * ss, 6); row[o++] = ',';
+    o += std::snprintf(row.data() + o, row.size() - o, "%d,", p.laplacian);
+    put(p.response, 6); row[o++] = ',';
+    for (size_t k = 0; k < dsize; k++) {
+      put(desc[i * dsize + k], dec);
+      if (k < dsize - 1) row[o++] = ',';
     }
     row[o++] = '\n';
     if (gzwrite(gz, row.data(), (unsigned)o) != (int)o) { gzclose(gz); return false; }
@@ -306,6 +356,21 @@ long fsio_read_points(const char* path, const double* spacing, const double* ori
   const long n = (long)(v.size() / 4);
   if (xyzs) std::memcpy(xyzs, v.data(), sizeof(float) * 4 * (size_t)(n < cap ? n : cap));
   return n;
+}
+
+// test hook: formats every v[i] with `decimals` decimals and compares with snprintf("%.<decimals>f"); returns the
+// number of values that differ (the first one's index in *first_bad)
+long fsio_debug_format_check(const double* v, long n, int decimals, long* first_bad) {
+  long bad = 0;
+  char fmt[16], a[512], b[512];
+  std::snprintf(fmt, sizeof fmt, "%%.%df", decimals);
+  for (long i = 0; i < n; i++) {
+    const size_t la = fsio::format_fixed(v[i], decimals, a, sizeof a - 1);
+    a[la] = 0;
+    std::snprintf(b, sizeof b, fmt, v[i]);
+    if (std::strcmp(a, b) != 0) { if (!bad && first_bad) *first_bad = i; bad++; }
+  }
+  return bad;
 }
 
 int fsio_write_bounds_json(const char* path, const int* dims, const double* spacing, const double* origin) {

@@ -240,3 +240,30 @@ def test_extrema_ordering_is_a_stable_sort(built):
     for keys in cases:
         got = surf.debug_sort_keys(keys)
         assert np.array_equal(got, np.argsort(keys, kind="stable").astype(np.uint32))
+
+
+def test_fixed_decimal_formatter_is_printf(built):
+    """The writers' "%f" / "%.<n>f" replacement (exact 128-bit integer arithmetic, ties to even) against snprintf:
+    descriptor-like floats, coordinates, responses, tiny and negative-zero values, exact binary ties, every precision
+    the fast path takes, and the ranges it hands back to snprintf."""
+    import ctypes as C
+    L = C.CDLL(build.FSIO)
+    L.fsio_debug_format_check.restype = C.c_long
+    L.fsio_debug_format_check.argtypes = [C.c_void_p, C.c_long, C.c_int, C.c_void_p]
+    rng = np.random.default_rng(8)
+    sets = [
+        rng.uniform(-1, 1, 400000).astype(np.float32).astype(np.float64),
+        rng.uniform(-2000, 2000, 200000),
+        (rng.uniform(0, 1, 100000) * 10.0 ** rng.integers(-12, 13, 100000)),
+        rng.uniform(0, 3e6, 100000).astype(np.float32).astype(np.float64),
+        np.array([0.0, -0.0, 5e-7, -5e-7, 4.9999999e-7, 1e-300, -1e-300, 5e-324, 0.9999995, 0.99999949999, 999999.9999995,
+                  8.9e12, 9.1e12, 1e20, -1e20, np.inf, -np.inf, 0.5, 1.5, 2.5, -0.5, 0.125, 0.375, 0.0625, 2.0 ** -20, 1.0, -1.0]),
+        (np.arange(-2000, 2000) + 0.5) / 8.0,       # exact binary ties at one, two and three decimals
+        np.arange(0, 4096) / 4096.0,
+    ]
+    for vals in sets:
+        v = np.ascontiguousarray(vals, np.float64)
+        for decimals in (6, 0, 1, 2, 3, 4, 9, 12):
+            bad = C.c_long(-1)
+            n_bad = L.fsio_debug_format_check(v.ctypes.data, v.size, decimals, C.byref(bad))
+            assert n_bad == 0, f"decimals {decimals}: {n_bad} differ, first {v[bad.value]!r}"
