@@ -83,15 +83,17 @@ def test_verbatim_writers_reproduce_golden_files(tmp_path):
         assert open(out, "rb").read() == open(os.path.join(GOLD, "small_points." + fmt), "rb").read()
 
 
-@needs_ref
-def test_shim_svd_is_an_svd():
-    """The OpenCV stand-in's SVD (oracle/shim_surf/opencv2/opencv.hpp) against numpy on the interpolation's own
-    use: offsets recomputed from golden extrema agree to 1e-9 -- the tolerance the sub-voxel step is pinned to."""
-    # the detector's accepted offsets are bounded by 1 in magnitude; compare the truncated pseudo-inverse solve
-    rng = np.random.default_rng(5)
+def test_interpolation_solve_is_the_truncated_pseudo_inverse():
+    """fasthessian.cxx:614-661 solves X = -pinv(H) dD through cv::SVD with singular values below 0.001 of the largest
+    dropped.  OpenCV is absent, so this step is pinned to a TOLERANCE: the product's solve (cyclic Jacobi on the
+    symmetric H, host and device statement of fs_kernels.cuh) against numpy's SVD-based truncated pseudo-inverse,
+    including nearly singular H, to 1e-9.  (The oracle's own stand-in, a one-sided Jacobi SVD in
+    oracle/shim_surf/opencv2/opencv.hpp, is a third method; the keypoints it leads to are bit-identical to the
+    product's on every golden volume, tests/test_gpu_surf.py.)"""
     from frog_b200 import surf
     if not os.path.exists(surf.build.SURF_LIB):
         pytest.skip("libfrogsurf.so not built")
+    rng = np.random.default_rng(5)
     for t in range(300):
         a = rng.standard_normal((4, 4))
         a = a + a.T
