@@ -216,3 +216,28 @@ def test_cli_point_file(built, tmp_path):
     r = subprocess.run([build.SURF_BIN, mha, "-o", base + "30", "-p", pfile, "-n", "30"], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     assert open(base + "30.csv.gz", "rb").read() == open(os.path.join(GOLD, "pfile_points_n30.csv.gz"), "rb").read()
+
+
+@pytest.mark.skipif(not so.available(), reason="oracle/_ref/libsurf_ref.so did not travel")
+def test_odd_dimensions_against_the_reference_build(producer):
+    """Odd sizes on every axis (131 x 103 x 117 voxels, z y x): the parity-split layout's half rows differ in length,
+    the layers drop the last voxel of each axis."""
+    vol = synth.make_volume((131, 103, 117), 5)
+    ref = so.RefSurf(vol)
+    rx, rlap, rdesc = ref.update(threshold=0.0, number_of_points=20000)
+    p = producer
+    p.set_volume(vol)
+    assert np.array_equal(p.integral(), ref.integral_volume())
+    n = p.detect(0.0)
+    assert mg.layer_hashes(p.layers()) == mg.layer_hashes(ref.response_layers(0.0))
+    det, det_lap = ref.detect(0.0)
+    assert n == len(det) and n > 20
+    pts, _ = p.points(with_descriptors=False)
+    differing = assert_points_close(pts_matrix(pts), det)
+    p.select(20000)
+    p.describe(0, 5, True)
+    pts, desc = p.points()
+    differing += assert_points_close(pts_matrix(pts), rx)
+    assert np.array_equal(pts["laplacian"], rlap)
+    if differing == 0:
+        assert np.array_equal(bits(desc), bits(rdesc))
